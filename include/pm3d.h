@@ -1,0 +1,211 @@
+/*
+ * pm3d.h — C-ABI of libpm3d.so: the B200-native (sm_100a CUDA) raycasting hot path of
+ * PixelMek 3D behind the interfaces the game's Go code drives.
+ *
+ * Each entry point names the reference interface it replaces; paths are relative to the
+ * reference repo (pixelmek-3d/pixelmek-3d).  The arithmetic the camera entry points replace
+ * lives in the un-vendored module github.com/harbdog/raycaster-go v1.12.0 (go.mod:13), so
+ * those citations are the reference's CALL SITES into it.  INTEGRATION.md shows the cgo
+ * binding a maintainer adds on the Go side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types.  Every function returns 0 on
+ *     success and a negative pm3d_status otherwise; pm3d_last_error() has the message.
+ *     There is NO CPU fallback: without a CUDA device every compute call fails.
+ *   - grid order is [level][x][y] exactly like model.Map.Levels (game/model/map.go:82).
+ *   - all RGBA8 images are premultiplied alpha, row-major (what ebiten.Image / image.RGBA hold).
+ *   - transcendental functions stay on the host: a view carries dir/plane/pitch already
+ *     evaluated (Go's math.Sin/Cos are software routines that differ from CUDA's in the
+ *     last ulp); the device path uses only + - * / sqrt in IEEE binary64 without FMA
+ *     contraction so hit cells, sides and texture columns are bit-exact.
+ *   - a ctx is single-threaded (one CUDA stream); use one ctx per GPU.
+ */
+#ifndef PM3D_H
+#define PM3D_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM3D_VERSION 100
+
+typedef struct pm3d_ctx pm3d_ctx;
+
+typedef enum pm3d_status {
+    PM3D_OK = 0,
+    PM3D_ERR_ARG = -1,      /* bad argument / call order */
+    PM3D_ERR_CUDA = -2,     /* CUDA runtime failure (incl. "no device": no CPU fallback) */
+    PM3D_ERR_CAPACITY = -3, /* exceeds a limit fixed by pm3d_set_view */
+    PM3D_ERR_NCCL = -4
+} pm3d_status;
+
+/* raycaster.SpriteAnchor as used at game/model/map.go:143-155 */
+enum { PM3D_ANCHOR_BOTTOM = 0, PM3D_ANCHOR_CENTER = 1, PM3D_ANCHOR_TOP = 2 };
+
+/* memory-space flags for the batched calls */
+enum {
+    PM3D_OUT_DEVICE = 1u << 0, /* output pointers are device memory (no D2H copy) */
+    PM3D_IN_DEVICE = 1u << 1,  /* input arrays are device memory (no H2D copy)  */
+    PM3D_NO_SYNC = 1u << 2     /* enqueue only; caller syncs with pm3d_sync     */
+};
+
+/* One camera view = the state set through the raycaster.Camera setters:
+ *   SetPosition/SetPositionZ/SetHeadingAngle/SetPitchAngle  game/camera.go:31-34
+ *   SetFovAngle game/config.go:290, game/input.go:767,771
+ *   SetRenderDistance game/mission.go:75; SetLightFalloff/SetGlobalIllumination/SetLightRGB
+ *   game/mission.go:90-92.   (host mirror: pixelmek-3d_b200/host/raycaster_camera.hpp)     */
+typedef struct pm3d_view {
+    double pos_x, pos_y;        /* camera position in cells                          */
+    double cam_z_px;            /* (posZ - 0.5) * h, camera height in pixel units    */
+    double dir_x, dir_y;        /* fovDepth * (cos, sin)(heading)                    */
+    double plane_x, plane_y;    /* camera plane, |plane| = |dir| * tan(fov/2)        */
+    int32_t pitch_px;           /* pitch as a pixel offset of the horizon            */
+    int32_t _reserved[3];
+    double render_distance;     /* cells; < 0 = infinite (game/sprites.go:113)       */
+    double light_falloff;
+    double global_illumination;
+    uint8_t min_light[4];       /* RGB, [3] ignored                                  */
+    uint8_t max_light[4];
+} pm3d_view;                    /* 104 bytes */
+
+/* One raycaster.Sprite snapshot (game/render/sprites/sprite.go:49-91). */
+typedef struct pm3d_sprite {
+    double x, y, z;             /* Pos(), PosZ()                                     */
+    double scale;               /* Scale()                                           */
+    double illumination;        /* Illumination()                                    */
+    int32_t sheet;              /* Texture(): id given to pm3d_upload_sprite_sheets  */
+    int32_t rx0, ry0, rx1, ry1; /* TextureRect() inside that sheet                   */
+    uint8_t anchor;             /* VerticalAnchor()                                  */
+    uint8_t focusable;          /* IsFocusable()                                     */
+    uint8_t _pad[2];
+} pm3d_sprite;                  /* 64 bytes */
+
+/* Sprite.SetScreenRect argument (sprite.go:85); x0 > x1 means nil. */
+typedef struct pm3d_rect { int32_t x0, y0, x1, y1; } pm3d_rect;
+
+/* Camera.GetConvergenceSprite / convergence point (game/scene_game.go:164, game/game.go:576-629) */
+typedef struct pm3d_convergence {
+    double distance;
+    double point_x, point_y;
+    int32_t sprite;             /* index into that view's sprite list, -1 = none     */
+    int32_t _pad;
+} pm3d_convergence;
+
+/* Per (level, column) wall-cast record, for parity checks (pm3d_download_columns). */
+typedef struct pm3d_column {
+    double perp_dist;
+    int64_t line_height;
+    int64_t draw_start, draw_end;
+    int32_t map_x, map_y;       /* hit cell                                          */
+    int32_t tex_x;              /* texture column                                    */
+    int16_t tile;               /* atlas tile drawn, -1 = none                       */
+    uint8_t side;               /* 0 = x side, 1 = y side                            */
+    uint8_t hit;                /* 1 = wall, 2 = ray left the grid                   */
+    uint8_t tint[4];
+} pm3d_column;                  /* 56 bytes */
+
+/* ------------------------------------------------------------------ lifetime */
+
+/* device: CUDA ordinal.  stream: a cudaStream_t to enqueue on, or NULL for a private
+ * non-blocking stream. */
+int pm3d_create(int device, void *stream, pm3d_ctx **out);
+void pm3d_destroy(pm3d_ctx *ctx);
+/* message of the last failure on ctx (ctx may be NULL for pm3d_create failures) */
+const char *pm3d_last_error(const pm3d_ctx *ctx);
+int pm3d_version(void);
+int pm3d_device_count(void);
+int pm3d_sync(pm3d_ctx *ctx);
+
+/* ------------------------------------------------------------------ mission-time uploads
+ * raycaster.NewCamera(w, h, texSize, Map, TextureHandler) — game/mission.go:74 — resolved
+ * once per mission instead of called back per ray/pixel.                                 */
+
+/* raycaster.Map: NumLevels()/Level(l) (game/model/map.go:253-264).  Levels above
+ * stored_levels repeat the top stored level, as Level() does. */
+int pm3d_upload_grid(pm3d_ctx *ctx, const uint16_t *grid, int stored_levels, int map_w, int map_h,
+                     int num_raycast_levels);
+/* TextureHandler.TextureAt + MapTexture.GetImage (game/texture/texture.go:69-97,
+ * game/model/map.go:106-115): for texture index tex_index[i] the tile drawn on side 0 / 1
+ * (-1 = nil image).  Unlisted indices draw nothing. */
+int pm3d_upload_wall_textures(pm3d_ctx *ctx, const int32_t *tex_index, const int32_t *tile_side0,
+                              const int32_t *tile_side1, int n);
+/* the tex_size x tex_size wall/floor/sky images (resources.TexSize = 256); tex_size must be
+ * a power of two */
+int pm3d_upload_atlas(pm3d_ctx *ctx, const uint8_t *rgba, int n_tiles, int tex_size);
+/* TextureHandler.FloorTextureAt (game/texture/texture.go:119-133): tile per cell [x][y],
+ * -1 = nil (floor texturing disabled) */
+int pm3d_upload_floor_tiles(pm3d_ctx *ctx, const int16_t *tiles, int map_w, int map_h);
+/* Camera.SetSkyTexture / SetFloorTexture (game/mission.go:78-83); -1 = none */
+int pm3d_set_box_tiles(pm3d_ctx *ctx, int sky_tile, int floorbox_tile);
+/* Sprite.Texture() images (sheets are uploaded once; per frame a sprite names sheet + rect,
+ * game/render/sprites/sprite.go:161-185) */
+int pm3d_upload_sprite_sheets(pm3d_ctx *ctx, const uint8_t *pixels, const int64_t *byte_offset,
+                              const int32_t *width, const int32_t *height, int n_sheets);
+/* Camera.SetViewSize (game/config.go:249) + capacity for batched calls */
+int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_sprites_total);
+/* options: PM3D_OPT_KEEP_COLUMNS (default 0) keeps the pm3d_column records of every view for
+ * pm3d_download_columns; PM3D_OPT_FORCE_PAINTER (default 0) disables the front-to-back
+ * shortcut of the compose kernel (A/B check: output must not change). */
+enum { PM3D_OPT_KEEP_COLUMNS = 1, PM3D_OPT_FORCE_PAINTER = 2 };
+int pm3d_set_option(pm3d_ctx *ctx, int option, int value);
+
+/* ------------------------------------------------------------------ frame path
+ * Camera.Update(sprites) + GetConvergenceSprite() + Camera.Draw(screen)
+ * (game/scene_game.go:161-167) for n_views independent cameras in one call.
+ *   sprites: all views' sprite snapshots concatenated; sprite_offset[n_views+1] delimits them
+ *   out_rgba: n_views * h * w * 4 bytes, premultiplied RGBA8 (NULL = keep on device only)
+ *   out_rects: one per sprite (SetScreenRect); out_conv: one per view.  Either may be NULL.
+ *   flags: PM3D_OUT_DEVICE -> out_rgba is device memory.                                  */
+int pm3d_render(pm3d_ctx *ctx, const pm3d_view *views, int n_views, const pm3d_sprite *sprites,
+                const int32_t *sprite_offset, uint8_t *out_rgba, pm3d_rect *out_rects,
+                pm3d_convergence *out_conv, uint32_t flags);
+/* wall-cast records + z-buffer of one view of the last pm3d_render (parity/debug).
+ * columns: [num_levels][w]; zbuf: [w] */
+int pm3d_download_columns(pm3d_ctx *ctx, int view, pm3d_column *columns, double *zbuf);
+/* 64-bit FNV-1a checksum of each view's framebuffer of the last pm3d_render, computed on the
+ * device (compact per-view result for sharded batches). */
+int pm3d_frame_checksums(pm3d_ctx *ctx, int n_views, uint64_t *out, uint32_t flags);
+/* device pointer of the internal framebuffer ring slot written by the last pm3d_render */
+void *pm3d_last_frame_device(pm3d_ctx *ctx);
+
+/* ------------------------------------------------------------------ LOS / collision path */
+
+/* g.collisionMap = Map.GenerateWallCollisionLines(clipDistance) (game/mission.go:40):
+ * n segments as x1,y1,x2,y2 */
+int pm3d_upload_segments(pm3d_ctx *ctx, const double *xyxy, int n);
+/* Game.lineOfSight (game/collision.go:40-65) for n rays (srcX,srcY,tgtX,tgtY):
+ * out[i] = 1 iff no collision-map segment intersects ray i. */
+int pm3d_los_batch(pm3d_ctx *ctx, const double *rays, int64_t n, uint8_t *out, uint32_t flags);
+/* Wall part of Game.getValidMove (game/collision.go:69-97, 202-203, 307-342) for n moves
+ * (posX,posY,newX,newY), checkAlternate=false, no sprite colliders: out_pos = x,y per move. */
+int pm3d_move_batch(pm3d_ctx *ctx, const double *moves, int64_t n, double clip_distance, double *out_pos,
+                    uint8_t *out_collided, uint32_t flags);
+
+/* Host mirror of Map.GenerateWallCollisionLines (game/model/map.go:811-851) so synthetic
+ * workloads can build g.collisionMap without the Go side.  level0: [map_w][map_h].
+ * Returns the number of segments (writes at most cap), or a negative status. */
+int pm3d_generate_wall_collision_lines(const uint16_t *level0, int map_w, int map_h, int has_boundary_wall,
+                                       double clip_distance, double *out_xyxy, int cap);
+
+/* ------------------------------------------------------------------ device memory + timing
+ * (so a cgo / ctypes host needs no CUDA binding of its own) */
+int pm3d_device_alloc(pm3d_ctx *ctx, int64_t bytes, void **out);
+int pm3d_device_free(pm3d_ctx *ctx, void *ptr);
+int pm3d_host_alloc(pm3d_ctx *ctx, int64_t bytes, void **out); /* pinned */
+int pm3d_host_free(pm3d_ctx *ctx, void *ptr);
+int pm3d_memcpy_h2d(pm3d_ctx *ctx, void *dst, const void *src, int64_t bytes);
+int pm3d_memcpy_d2h(pm3d_ctx *ctx, void *dst, const void *src, int64_t bytes);
+/* CUDA-event timers on the ctx stream: slot in [0, 16) */
+int pm3d_timer_start(pm3d_ctx *ctx, int slot);
+int pm3d_timer_stop(pm3d_ctx *ctx, int slot);
+int pm3d_timer_elapsed_ms(pm3d_ctx *ctx, int slot, float *ms); /* syncs on the stop event */
+/* kernels launched by this ctx since creation (bench.py "gpu_launches") */
+int64_t pm3d_launch_count(const pm3d_ctx *ctx);
+/* write `bytes` of a scratch buffer (> L2) to flush the L2 between timed iterations */
+int pm3d_flush_l2(pm3d_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,197 @@
+"""ctypes front end of the CPU ORACLE (oracle/pm3d_oracle.c).
+
+TEST INFRASTRUCTURE ONLY — see oracle/pm3d_oracle.h.  PARITY UNPINNED against the Go binary.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  Nothing under pixelmek-3d_b200/ does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+SPRITE_DTYPE = np.dtype(
+    [
+        ("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("scale", "<f8"), ("illumination", "<f8"),
+        ("sheet", "<i4"), ("rx0", "<i4"), ("ry0", "<i4"), ("rx1", "<i4"), ("ry1", "<i4"),
+        ("anchor", "u1"), ("focusable", "u1"), ("_pad", "u1", (2,)),
+    ],
+    align=False,
+)
+assert SPRITE_DTYPE.itemsize == 64
+
+COLUMN_DTYPE = np.dtype(
+    [
+        ("perp_dist", "<f8"), ("line_height", "<i8"), ("draw_start", "<i8"), ("draw_end", "<i8"),
+        ("map_x", "<i4"), ("map_y", "<i4"), ("tex_x", "<i4"), ("tile", "<i2"), ("side", "u1"), ("hit", "u1"),
+        ("tint", "u1", (4,)), ("_tail", "u1", (4,)),
+    ],
+    align=False,
+)
+assert COLUMN_DTYPE.itemsize == 56
+
+
+class OrcScene(C.Structure):
+    _fields_ = [
+        ("map_w", C.c_int32), ("map_h", C.c_int32), ("stored_levels", C.c_int32), ("num_levels", C.c_int32),
+        ("grid", C.c_void_p), ("wall_lut", C.c_void_p), ("floor_tiles", C.c_void_p), ("atlas", C.c_void_p),
+        ("n_tiles", C.c_int32), ("tex_size", C.c_int32), ("sky_tile", C.c_int32), ("floorbox_tile", C.c_int32),
+        ("sheet_pixels", C.c_void_p), ("sheet_offset", C.c_void_p), ("sheet_w", C.c_void_p), ("sheet_h", C.c_void_p),
+        ("n_sheets", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
+class OrcCamera(C.Structure):
+    _fields_ = [
+        ("pos_x", C.c_double), ("pos_y", C.c_double), ("cam_z_px", C.c_double),
+        ("dir_x", C.c_double), ("dir_y", C.c_double), ("plane_x", C.c_double), ("plane_y", C.c_double),
+        ("pitch_px", C.c_int32), ("w", C.c_int32), ("h", C.c_int32), ("_pad", C.c_int32),
+        ("render_distance", C.c_double), ("light_falloff", C.c_double), ("global_illumination", C.c_double),
+        ("min_light", C.c_uint8 * 4), ("max_light", C.c_uint8 * 4),
+    ]
+
+
+class OrcConvergence(C.Structure):
+    _fields_ = [("distance", C.c_double), ("point_x", C.c_double), ("point_y", C.c_double),
+                ("sprite", C.c_int32), ("_pad", C.c_int32)]
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/libpm3d_oracle.so with the committed Makefile (building the checker is
+    not using it)."""
+    so = os.path.join(_HERE, "libpm3d_oracle.so")
+    src = os.path.join(_HERE, "pm3d_oracle.c")
+    hdr = os.path.join(_HERE, "pm3d_oracle.h")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libpm3d_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_go_int.restype = C.c_int64
+        _LIB.orc_go_int.argtypes = [C.c_double]
+        _LIB.orc_line_intersection.restype = C.c_int
+    return _LIB
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Scene:
+    """Flattened Map + TextureHandler + sprite sheets.  `data` is any object with the
+    attributes of pm3d.scene.SceneData (duck-typed so oracle/ does not import the product)."""
+
+    def __init__(self, data):
+        self.grid = np.ascontiguousarray(data.grid, dtype=np.uint16)
+        ls, w, h = self.grid.shape
+        self.wall_lut = np.full((32768, 2), -1, dtype=np.int16)
+        for tex, t0, t1 in zip(data.wall_tex_index, data.wall_tile_side0, data.wall_tile_side1):
+            self.wall_lut[int(tex), 0] = t0
+            self.wall_lut[int(tex), 1] = t1
+        self.floor_tiles = np.ascontiguousarray(data.floor_tiles, dtype=np.int16)
+        assert self.floor_tiles.shape == (w, h)
+        self.atlas = np.ascontiguousarray(data.atlas, dtype=np.uint8)
+        nt, ts, ts2, ch = self.atlas.shape
+        assert ts == ts2 and ch == 4
+        sheets = [np.ascontiguousarray(s, dtype=np.uint8) for s in data.sheets]
+        sizes = [s.size for s in sheets]
+        self.sheet_offset = np.zeros(max(len(sheets), 1), dtype=np.int64)
+        if sheets:
+            self.sheet_offset[: len(sheets)] = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+        self.sheet_pixels = np.concatenate([s.reshape(-1) for s in sheets]) if sheets else np.zeros(4, np.uint8)
+        self.sheet_w = np.array([s.shape[1] for s in sheets] or [0], dtype=np.int32)
+        self.sheet_h = np.array([s.shape[0] for s in sheets] or [0], dtype=np.int32)
+        self.c = OrcScene(
+            w, h, ls, int(data.num_levels), _ptr(self.grid), _ptr(self.wall_lut), _ptr(self.floor_tiles),
+            _ptr(self.atlas), nt, ts, int(data.sky_tile), int(data.floorbox_tile), _ptr(self.sheet_pixels),
+            _ptr(self.sheet_offset), _ptr(self.sheet_w), _ptr(self.sheet_h), len(sheets), 0,
+        )
+
+
+def make_camera(p) -> OrcCamera:
+    """p: any object/dict-like with the low-level pose fields (pm3d.camera.Camera.pose())."""
+    g = (lambda k: p[k]) if isinstance(p, dict) else (lambda k: getattr(p, k))
+    cam = OrcCamera()
+    for k in ("pos_x", "pos_y", "cam_z_px", "dir_x", "dir_y", "plane_x", "plane_y", "render_distance",
+              "light_falloff", "global_illumination"):
+        setattr(cam, k, float(g(k)))
+    for k in ("pitch_px", "w", "h"):
+        setattr(cam, k, int(g(k)))
+    mn, mx = g("min_light"), g("max_light")
+    for i in range(3):
+        cam.min_light[i] = int(mn[i])
+        cam.max_light[i] = int(mx[i])
+    cam.min_light[3] = cam.max_light[3] = 255
+    return cam
+
+
+def cast_walls(scene: Scene, cam: OrcCamera):
+    cols = np.zeros((scene.c.num_levels, cam.w), dtype=COLUMN_DTYPE)
+    zbuf = np.zeros(cam.w, dtype=np.float64)
+    lib().orc_cast_walls(C.byref(scene.c), C.byref(cam), _ptr(cols), _ptr(zbuf))
+    return cols, zbuf
+
+
+def render(scene: Scene, cam: OrcCamera, sprites: np.ndarray, threads: int = 1):
+    sprites = np.ascontiguousarray(sprites, dtype=SPRITE_DTYPE)
+    n = len(sprites)
+    rgba = np.zeros((cam.h, cam.w, 4), dtype=np.uint8)
+    rects = np.zeros((max(n, 1), 4), dtype=np.int32)
+    conv = OrcConvergence()
+    cols = np.zeros((scene.c.num_levels, cam.w), dtype=COLUMN_DTYPE)
+    zbuf = np.zeros(cam.w, dtype=np.float64)
+    lib().orc_render(C.byref(scene.c), C.byref(cam), _ptr(sprites), C.c_int32(n), _ptr(rgba), _ptr(rects),
+                     C.byref(conv), _ptr(cols), _ptr(zbuf), C.c_int32(threads))
+    return {
+        "rgba": rgba, "rects": rects[:n], "columns": cols, "zbuf": zbuf,
+        "convergence": {"distance": conv.distance, "point": (conv.point_x, conv.point_y), "sprite": conv.sprite},
+    }
+
+
+def sprite_order(cam: OrcCamera, sprites: np.ndarray):
+    sprites = np.ascontiguousarray(sprites, dtype=SPRITE_DTYPE)
+    order = np.zeros(max(len(sprites), 1), dtype=np.int32)
+    lib().orc_sprite_order(C.byref(cam), _ptr(sprites), C.c_int32(len(sprites)), _ptr(order))
+    return order[: len(sprites)]
+
+
+def line_intersection(l1, l2):
+    a = np.ascontiguousarray(l1, dtype=np.float64)
+    b = np.ascontiguousarray(l2, dtype=np.float64)
+    px, py = C.c_double(), C.c_double()
+    ok = lib().orc_line_intersection(_ptr(a), _ptr(b), C.byref(px), C.byref(py))
+    return (px.value, py.value, True) if ok else (0.0, 0.0, False)
+
+
+def los_batch(segs: np.ndarray, rays: np.ndarray, threads: int = 1) -> np.ndarray:
+    segs = np.ascontiguousarray(segs, dtype=np.float64).reshape(-1, 4)
+    rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 4)
+    out = np.zeros(len(rays), dtype=np.uint8)
+    lib().orc_los_batch(_ptr(segs), C.c_int32(len(segs)), _ptr(rays), C.c_int64(len(rays)), _ptr(out),
+                        C.c_int32(threads))
+    return out
+
+
+def move_walls_batch(scene: Scene, segs: np.ndarray, moves: np.ndarray, clip: float, threads: int = 1):
+    segs = np.ascontiguousarray(segs, dtype=np.float64).reshape(-1, 4)
+    moves = np.ascontiguousarray(moves, dtype=np.float64).reshape(-1, 4)
+    n = len(moves)
+    pos = np.zeros((n, 2), dtype=np.float64)
+    collided = np.zeros(n, dtype=np.uint8)
+    hits = np.zeros(n, dtype=np.int32)
+    lib().orc_move_walls_batch(C.byref(scene.c), _ptr(segs), C.c_int32(len(segs)), _ptr(moves), C.c_int64(n),
+                               C.c_double(clip), _ptr(pos), _ptr(collided), _ptr(hits), C.c_int32(threads))
+    return pos, collided, hits
+
+
+def go_int(v: float) -> int:
+    return int(lib().orc_go_int(float(v)))

@@ -1,0 +1,151 @@
+/*
+ * pm3d_oracle.h — CPU ORACLE for the PixelMek 3D raycasting hot path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.  The product path
+ * (pixelmek-3d_b200/csrc, libpm3d.so) never links, imports or calls anything in oracle/.
+ *
+ * PARITY UNPINNED: the arithmetic of this path lives in the third-party Go module
+ * github.com/harbdog/raycaster-go v1.12.0 (reference go.mod:13, go.sum:60-61), which is
+ * NOT vendored under /root/reference, and the reference ships no tests or golden
+ * vectors.  No Go toolchain exists in this image, so the
+ * reference cannot be built or run.  This file restates
+ *   [V] what is verifiable on disk (call sites, callback semantics, grid layout,
+ *       collision queries) with file:line citations, and
+ *   [R] the module's published algorithm (Lode-style DDA raycaster as adapted by
+ *       raycaster-go) recalled from the public source, without file:line, and
+ *   [D] a design decision of this repo where neither [V] nor [R] pins the behaviour
+ *       (chiefly: the integer blit arithmetic Ebitengine performs on the GPU).
+ * Every function below carries one of those tags.
+ *
+ * Numeric contract (mirrors Go on amd64): IEEE-754 binary64, no FMA contraction
+ * (compile with -ffp-contract=off), int(float64) truncates toward zero and yields
+ * INT64_MIN on NaN/overflow (CVTTSD2SQ), Go `int` is 64-bit and wraps silently.
+ */
+#ifndef PM3D_ORACLE_H
+#define PM3D_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* raycaster.SpriteAnchor [R]: AnchorBottom = iota, AnchorCenter, AnchorTop
+ * (used by the reference at game/model/map.go:143-155). */
+enum { ORC_ANCHOR_BOTTOM = 0, ORC_ANCHOR_CENTER = 1, ORC_ANCHOR_TOP = 2 };
+
+/* Level grid + texture callbacks, flattened.
+ * grid index order is [level][x][y]  (reference game/model/map.go:82, :245-264).   */
+typedef struct orc_scene {
+    int32_t map_w, map_h;          /* Map.Size()                       map.go:245-251 */
+    int32_t stored_levels;         /* len(Map.Levels)                                 */
+    int32_t num_levels;            /* Map.NumLevels() = NumRaycastLevels map.go:253   */
+    const uint16_t *grid;          /* [stored_levels][map_w][map_h], >0 = wall        */
+    const int16_t *wall_lut;       /* [32768][2]: tile for (texIndex, side); -1 = nil.
+                                      Encodes TextureAt + MapTexture.GetImage
+                                      (texture.go:69-97, map.go:106-115)              */
+    const int16_t *floor_tiles;    /* [map_w][map_h] tile per cell, -1 = nil.
+                                      Encodes FloorTextureAt (texture.go:119-133)     */
+    const uint8_t *atlas;          /* [n_tiles][tex][tex][4] premultiplied RGBA8      */
+    int32_t n_tiles, tex_size;     /* resources.TexSize = 256  resources.go:35        */
+    int32_t sky_tile, floorbox_tile; /* SetSkyTexture/SetFloorTexture mission.go:78-83 */
+    /* sprite sheets: premultiplied RGBA8, row-major, concatenated */
+    const uint8_t *sheet_pixels;
+    const int64_t *sheet_offset;   /* [n_sheets] byte offset into sheet_pixels        */
+    const int32_t *sheet_w, *sheet_h;
+    int32_t n_sheets;
+    int32_t _pad;
+} orc_scene;
+
+/* Camera state the reference sets through K5 setters.
+ * Transcendentals (cos/sin/tan) are evaluated by the HOST shim; the hot path sees
+ * only dir/plane/pitch_px/cam_z_px so it needs + - * / sqrt only.                    */
+typedef struct orc_camera {
+    double pos_x, pos_y;           /* SetPosition                    camera.go:31     */
+    double cam_z_px;               /* [R] (posZ-0.5)*h               camera.go:32     */
+    double dir_x, dir_y;           /* [R] fovDepth*(cos,sin)(heading) camera.go:33    */
+    double plane_x, plane_y;       /* [R] perp(dir)*tan(fov/2)        config.go:287   */
+    int32_t pitch_px;              /* [R] from SetPitchAngle         camera.go:34     */
+    int32_t w, h;                  /* SetViewSize                    config.go:249    */
+    int32_t _pad;
+    double render_distance;        /* SetRenderDistance, <0 = inf    mission.go:75    */
+    double light_falloff;          /* SetLightFalloff                mission.go:90    */
+    double global_illumination;    /* SetGlobalIllumination          mission.go:91    */
+    uint8_t min_light[4];          /* SetLightRGB                    mission.go:92    */
+    uint8_t max_light[4];
+} orc_camera;
+
+/* One raycaster.Sprite snapshot (reference game/render/sprites/sprite.go:49-91). */
+typedef struct orc_sprite {
+    double x, y, z;                /* Pos(), PosZ()                                   */
+    double scale;                  /* Scale()                                         */
+    double illumination;           /* Illumination()                                  */
+    int32_t sheet;                 /* Texture() -> sheet id                           */
+    int32_t rx0, ry0, rx1, ry1;    /* TextureRect()                                   */
+    uint8_t anchor;                /* VerticalAnchor()                                */
+    uint8_t focusable;             /* IsFocusable()                                   */
+    uint8_t _pad[2];
+} orc_sprite;                      /* 64 bytes */
+
+/* Per (level, column) wall-cast record ("slice") [R]. */
+typedef struct orc_column {
+    double perp_dist;              /* perpWallDist                                    */
+    int64_t line_height;           /* int(h / perpWallDist)                           */
+    int64_t draw_start, draw_end;  /* unclamped slice rows [start, end)               */
+    int32_t map_x, map_y;          /* hit cell (clamped when the ray left the grid)   */
+    int32_t tex_x;                 /* texture column                                  */
+    int16_t tile;                  /* atlas tile, -1 = nothing drawn                  */
+    uint8_t side;                  /* 0 = x-side, 1 = y-side                          */
+    uint8_t hit;                   /* 1 = wall, 2 = left the grid                     */
+    uint8_t tint[4];               /* RGB light tint, A = 255                         */
+} orc_column;                      /* 56 bytes */
+
+typedef struct orc_rect { int32_t x0, y0, x1, y1; } orc_rect;   /* x0 > x1 = nil */
+
+typedef struct orc_convergence {
+    double distance;               /* [D] see pm3d_oracle.c orc_render                */
+    double point_x, point_y;
+    int32_t sprite;                /* index into the sprite list, -1 = none           */
+    int32_t _pad;
+} orc_convergence;
+
+/* ---- camera path -------------------------------------------------------------- */
+
+/* K2 wall cast only: columns[level*w + x], zbuf[x] (level 0).  [R] */
+void orc_cast_walls(const orc_scene *s, const orc_camera *c, orc_column *columns, double *zbuf);
+
+/* K2+K3+K4: Camera.Update(sprites) followed by Camera.Draw(screen).
+ * rgba: [h][w][4] premultiplied RGBA8 out.  rects: [n_sprites] (SetScreenRect).
+ * columns/zbuf may be NULL.  threads <= 1 runs single threaded. */
+void orc_render(const orc_scene *s, const orc_camera *c, const orc_sprite *sprites, int32_t n_sprites,
+                uint8_t *rgba, orc_rect *rects, orc_convergence *conv, orc_column *columns, double *zbuf,
+                int32_t threads);
+
+/* far -> near order used for sprite painting; order[i] = sprite index. [R]/[D] */
+void orc_sprite_order(const orc_camera *c, const orc_sprite *sprites, int32_t n, int32_t *order);
+
+/* ---- LOS / collision path ------------------------------------------------------ */
+
+/* geom.LineIntersection [R] (call sites game/collision.go:58,94). segs/rays: x1,y1,x2,y2 */
+int orc_line_intersection(const double *l1, const double *l2, double *px, double *py);
+
+/* Game.lineOfSight over a batch (game/collision.go:40-65) [V]: out[i] = 1 iff no segment
+ * of the collision map intersects ray i. */
+void orc_los_batch(const double *segs, int32_t n_segs, const double *rays, int64_t n_rays, uint8_t *out,
+                   int32_t threads);
+
+/* Wall part of Game.getValidMove with checkAlternate=false and no sprite colliders
+ * (game/collision.go:82-97, 202-203, 307-342) [V]:
+ * moves: posX,posY,newX,newY per entry; out_pos: x,y ; out_collided; out_hits = number of
+ * intersection points. */
+void orc_move_walls_batch(const orc_scene *s, const double *segs, int32_t n_segs, const double *moves,
+                          int64_t n_moves, double clip_distance, double *out_pos, uint8_t *out_collided,
+                          int32_t *out_hits, int32_t threads);
+
+/* Go int(float64) on amd64. */
+int64_t orc_go_int(double v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,496 @@
+// pm3d_api.cu — the C-ABI of libpm3d.so (include/pm3d.h): ctx lifetime, mission-time uploads,
+// the frame path orchestration and the device-memory / timing helpers.  Host code only; the
+// kernels live in cast_kernel.cu, view_kernel.cu, compose_kernel.cu and los_kernel.cu.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "pm3d_internal.cuh"
+
+static thread_local std::string g_create_error;
+
+int pm3d_fail(pm3d_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+template <typename T>
+static int dev_realloc(pm3d_ctx *ctx, T **ptr, size_t count) {
+    if (*ptr) { PM3D_CUDA(ctx, cudaFree(*ptr)); *ptr = nullptr; }
+    if (count == 0) count = 1;
+    PM3D_CUDA(ctx, cudaMalloc((void **)ptr, count * sizeof(T)));
+    return PM3D_OK;
+}
+
+static int ensure_stage(pm3d_ctx *ctx, size_t bytes) {
+    if (ctx->stage_bytes >= bytes) return PM3D_OK;
+    if (ctx->stage) { PM3D_CUDA(ctx, cudaFreeHost(ctx->stage)); ctx->stage = nullptr; ctx->stage_bytes = 0; }
+    size_t cap = std::max<size_t>(bytes, 1 << 20);
+    PM3D_CUDA(ctx, cudaMallocHost(&ctx->stage, cap));
+    ctx->stage_bytes = cap;
+    return PM3D_OK;
+}
+
+extern "C" {
+
+int pm3d_version(void) { return PM3D_VERSION; }
+
+int pm3d_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *pm3d_last_error(const pm3d_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int pm3d_create(int device, void *stream, pm3d_ctx **out) {
+    if (!out) return pm3d_fail(nullptr, PM3D_ERR_ARG, "out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return pm3d_fail(nullptr, PM3D_ERR_CUDA, "no CUDA device (%s); libpm3d has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= n) return pm3d_fail(nullptr, PM3D_ERR_ARG, "device %d out of range [0,%d)", device, n);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return pm3d_fail(nullptr, PM3D_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    pm3d_ctx *ctx = new pm3d_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete ctx;
+            return pm3d_fail(nullptr, PM3D_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        }
+        ctx->own_stream = true;
+    }
+    *out = ctx;
+    return PM3D_OK;
+}
+
+void pm3d_destroy(pm3d_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    void *ptrs[] = {ctx->grid, ctx->wall_lut, ctx->atlas, ctx->floor_tiles, ctx->sheet_pixels, ctx->sheet_info,
+                    ctx->views, ctx->col_rec, ctx->floor_rec, ctx->zbuf, ctx->row_rec, ctx->dbg_cols, ctx->sprites,
+                    ctx->sprite_offset, ctx->draw_rec, ctx->n_draw, ctx->bin_list, ctx->bin_count, ctx->rects,
+                    ctx->conv, ctx->frame, ctx->checksums, ctx->segs, ctx->seg_irect, ctx->cell_start,
+                    ctx->cell_items, ctx->io_a, ctx->io_b, ctx->io_c, ctx->flush_buf};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (ctx->stage) cudaFreeHost(ctx->stage);
+    for (int i = 0; i < 16; i++) {
+        if (ctx->ev_start[i]) cudaEventDestroy(ctx->ev_start[i]);
+        if (ctx->ev_stop[i]) cudaEventDestroy(ctx->ev_stop[i]);
+    }
+    if (ctx->stage_ev) cudaEventDestroy(ctx->stage_ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int pm3d_sync(pm3d_ctx *ctx) {
+    if (!ctx) return PM3D_ERR_ARG;
+    PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PM3D_OK;
+}
+
+// ------------------------------------------------------------------ uploads
+
+int pm3d_upload_grid(pm3d_ctx *ctx, const uint16_t *grid, int stored_levels, int map_w, int map_h,
+                     int num_raycast_levels) {
+    if (!ctx) return PM3D_ERR_ARG;
+    if (!grid || stored_levels < 1 || map_w < 1 || map_h < 1 || num_raycast_levels < 1 || map_w > 32768 ||
+        map_h > 32768 || num_raycast_levels > 64)
+        return pm3d_fail(ctx, PM3D_ERR_ARG, "bad grid dimensions");
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t count = (size_t)stored_levels * map_w * map_h;
+    int rc = dev_realloc(ctx, &ctx->grid, count);
+    if (rc) return rc;
+    PM3D_CUDA(ctx, cudaMemcpyAsync(ctx->grid, grid, count * 2, cudaMemcpyHostToDevice, ctx->stream));
+    PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stored_levels = stored_levels; ctx->map_w = map_w; ctx->map_h = map_h;
+    const bool levels_changed = ctx->num_levels != num_raycast_levels;
+    ctx->num_levels = num_raycast_levels;
+    if (levels_changed && ctx->w > 0) return pm3d_set_view(ctx, ctx->w, ctx->h, ctx->max_views, ctx->max_sprites);
+    return PM3D_OK;
+}
+
+int pm3d_upload_wall_textures(pm3d_ctx *ctx, const int32_t *tex_index, const int32_t *tile_side0,
+                              const int32_t *tile_side1, int n) {
+    if (!ctx) return PM3D_ERR_ARG;
+    if (n < 0 || (n > 0 && (!tex_index || !tile_side0 || !tile_side1))) return pm3d_fail(ctx, PM3D_ERR_ARG, "null LUT");
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<int16_t> lut(32768 * 2, (int16_t)-1);
+    for (int i = 0; i < n; i++) {
+        if (tex_index[i] < 0 || tex_index[i] > 32767) return pm3d_fail(ctx, PM3D_ERR_ARG, "texture index %d out of [0,32767]", tex_index[i]);
+        if (tile_side0[i] < -1 || tile_side0[i] > 32767 || tile_side1[i] < -1 || tile_side1[i] > 32767)
+            return pm3d_fail(ctx, PM3D_ERR_ARG, "tile out of range");
+        lut[tex_index[i] * 2 + 0] = (int16_t)tile_side0[i];
+        lut[tex_index[i] * 2 + 1] = (int16_t)tile_side1[i];
+    }
+    int rc = dev_realloc(ctx, &ctx->wall_lut, lut.size());
+    if (rc) return rc;
+    PM3D_CUDA(ctx, cudaMemcpy(ctx->wall_lut, lut.data(), lut.size() * 2, cudaMemcpyHostToDevice));
+    return PM3D_OK;
+}
+
+int pm3d_upload_atlas(pm3d_ctx *ctx, const uint8_t *rgba, int n_tiles, int tex_size) {
+    if (!ctx) return PM3D_ERR_ARG;
+    if (!rgba || n_tiles < 1 || n_tiles > 32767 || tex_size < 1 || tex_size > 4096 || (tex_size & (tex_size - 1)))
+        return pm3d_fail(ctx, PM3D_ERR_ARG, "atlas: tex_size must be a power of two <= 4096, n_tiles in [1,32767]");
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t bytes = (size_t)n_tiles * tex_size * tex_size * 4;
+    int rc = dev_realloc(ctx, &ctx->atlas, bytes);
+    if (rc) return rc;
+    PM3D_CUDA(ctx, cudaMemcpy(ctx->atlas, rgba, bytes, cudaMemcpyHostToDevice));
+    ctx->n_tiles = n_tiles; ctx->tex_size = tex_size;
+    ctx->tex_shift = 0;
+    while ((1 << ctx->tex_shift) < tex_size) ctx->tex_shift++;
+    return PM3D_OK;
+}
+
+int pm3d_upload_floor_tiles(pm3d_ctx *ctx, const int16_t *tiles, int map_w, int map_h) {
+    if (!ctx) return PM3D_ERR_ARG;
+    if (!tiles || map_w < 1 || map_h < 1) return pm3d_fail(ctx, PM3D_ERR_ARG, "bad floor grid");
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = dev_realloc(ctx, &ctx->floor_tiles, (size_t)map_w * map_h);
+    if (rc) return rc;
+    PM3D_CUDA(ctx, cudaMemcpy(ctx->floor_tiles, tiles, (size_t)map_w * map_h * 2, cudaMemcpyHostToDevice));
+    ctx->floor_w = map_w; ctx->floor_h = map_h;
+    return PM3D_OK;
+}
+
+int pm3d_set_box_tiles(pm3d_ctx *ctx, int sky_tile, int floorbox_tile) {
+    if (!ctx) return PM3D_ERR_ARG;
+    ctx->sky_tile = sky_tile; ctx->floorbox_tile = floorbox_tile;
+    return PM3D_OK;
+}
+
+int pm3d_upload_sprite_sheets(pm3d_ctx *ctx, const uint8_t *pixels, const int64_t *byte_offset, const int32_t *width,
+                              const int32_t *height, int n_sheets) {
+    if (!ctx) return PM3D_ERR_ARG;
+    if (n_sheets < 0 || (n_sheets > 0 && (!pixels || !byte_offset || !width || !height)))
+        return pm3d_fail(ctx, PM3D_ERR_ARG, "null sheet arrays");
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t total = 0;
+    std::vector<SheetInfo> info(std::max(n_sheets, 1));
+    for (int i = 0; i < n_sheets; i++) {
+        if (width[i] < 1 || height[i] < 1 || byte_offset[i] < 0 || (byte_offset[i] & 3))
+            return pm3d_fail(ctx, PM3D_ERR_ARG, "sheet %d: bad size/offset", i);
+        info[i].px_offset = byte_offset[i] / 4;
+        info[i].w = width[i]; info[i].h = height[i];
+        total = std::max(total, (size_t)byte_offset[i] + (size_t)width[i] * height[i] * 4);
+    }
+    int rc = dev_realloc(ctx, &ctx->sheet_pixels, std::max<size_t>(total, 4));
+    if (rc) return rc;
+    if (total) PM3D_CUDA(ctx, cudaMemcpy(ctx->sheet_pixels, pixels, total, cudaMemcpyHostToDevice));
+    rc = dev_realloc(ctx, &ctx->sheet_info, info.size());
+    if (rc) return rc;
+    PM3D_CUDA(ctx, cudaMemcpy(ctx->sheet_info, info.data(), info.size() * sizeof(SheetInfo), cudaMemcpyHostToDevice));
+    ctx->n_sheets = n_sheets;
+    return PM3D_OK;
+}
+
+int pm3d_set_option(pm3d_ctx *ctx, int option, int value) {
+    if (!ctx) return PM3D_ERR_ARG;
+    switch (option) {
+    case PM3D_OPT_KEEP_COLUMNS:
+        ctx->keep_columns = value ? 1 : 0;
+        if (ctx->keep_columns && ctx->w > 0) return pm3d_set_view(ctx, ctx->w, ctx->h, ctx->max_views, ctx->max_sprites);
+        return PM3D_OK;
+    case PM3D_OPT_FORCE_PAINTER:
+        ctx->force_painter = value ? 1 : 0;
+        return PM3D_OK;
+    }
+    return pm3d_fail(ctx, PM3D_ERR_ARG, "unknown option %d", option);
+}
+
+int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_sprites_total) {
+    if (!ctx) return PM3D_ERR_ARG;
+    if (width < 1 || height < 1 || width > 16384 || height > 16384 || max_views < 1 || max_views > 65535 ||
+        max_sprites_total < 0)
+        return pm3d_fail(ctx, PM3D_ERR_ARG, "bad view size / capacity");
+    if (ctx->num_levels < 1) return pm3d_fail(ctx, PM3D_ERR_ARG, "pm3d_upload_grid must precede pm3d_set_view");
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->w = width; ctx->h = height; ctx->max_views = max_views; ctx->max_sprites = max_sprites_total;
+    ctx->n_groups = (width + 63) / 64;
+    const size_t V = max_views, L = ctx->num_levels, W = width, H = height, S = std::max(max_sprites_total, 1);
+    int rc;
+    if ((rc = dev_realloc(ctx, &ctx->views, V))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->col_rec, V * L * W))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->floor_rec, V * W))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->zbuf, V * W))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->row_rec, V * H))) return rc;
+    if (ctx->keep_columns) {
+        if ((rc = dev_realloc(ctx, &ctx->dbg_cols, V * L * W))) return rc;
+        ctx->dbg_levels = (int)L; ctx->dbg_views = (int)V;
+    }
+    if ((rc = dev_realloc(ctx, &ctx->sprites, S))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->sprite_offset, V + 1))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->draw_rec, S))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->n_draw, V))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->bin_list, S * ctx->n_groups))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->bin_count, V * ctx->n_groups))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->rects, S))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->conv, V))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->frame, V * W * H * 4))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->checksums, V))) return rc;
+    ctx->last_frame = nullptr;
+    ctx->last_views = 0;
+    return PM3D_OK;
+}
+
+// ------------------------------------------------------------------ frame path
+
+int pm3d_render(pm3d_ctx *ctx, const pm3d_view *views, int n_views, const pm3d_sprite *sprites,
+                const int32_t *sprite_offset, uint8_t *out_rgba, pm3d_rect *out_rects, pm3d_convergence *out_conv,
+                uint32_t flags) {
+    if (!ctx) return PM3D_ERR_ARG;
+    if (!ctx->grid || !ctx->wall_lut || !ctx->atlas || !ctx->floor_tiles || ctx->w < 1)
+        return pm3d_fail(ctx, PM3D_ERR_ARG, "grid, wall textures, atlas, floor tiles and view size must be set first");
+    if (ctx->floor_w != ctx->map_w || ctx->floor_h != ctx->map_h)
+        return pm3d_fail(ctx, PM3D_ERR_ARG, "floor tile grid %dx%d does not match map %dx%d", ctx->floor_w, ctx->floor_h, ctx->map_w, ctx->map_h);
+    if (!views || n_views < 1) return pm3d_fail(ctx, PM3D_ERR_ARG, "no views");
+    if (n_views > ctx->max_views) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "%d views > max_views %d", n_views, ctx->max_views);
+    if (ctx->sky_tile >= ctx->n_tiles || ctx->floorbox_tile >= ctx->n_tiles)
+        return pm3d_fail(ctx, PM3D_ERR_ARG, "sky/floor box tile outside the atlas");
+    std::vector<int32_t> zero_off;
+    if (!sprite_offset) {
+        zero_off.assign(n_views + 1, 0);
+        sprite_offset = zero_off.data();
+    }
+    const int n_sprites = sprite_offset[n_views];
+    if (sprite_offset[0] != 0 || n_sprites < 0) return pm3d_fail(ctx, PM3D_ERR_ARG, "sprite_offset must start at 0");
+    if (n_sprites > ctx->max_sprites) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "%d sprites > max_sprites_total %d", n_sprites, ctx->max_sprites);
+    if (n_sprites > 0 && !sprites) return pm3d_fail(ctx, PM3D_ERR_ARG, "sprites is null");
+    for (int v = 0; v < n_views; v++) {
+        const int nv = sprite_offset[v + 1] - sprite_offset[v];
+        if (nv < 0) return pm3d_fail(ctx, PM3D_ERR_ARG, "sprite_offset not monotone");
+        if (nv > 2048) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "view %d has %d sprites (limit 2048 per view)", v, nv);
+    }
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    // stage the small per-frame inputs through pinned memory, one H2D each
+    const size_t vb = (size_t)n_views * sizeof(pm3d_view), ob = (size_t)(n_views + 1) * 4,
+                 sb = (size_t)n_sprites * sizeof(pm3d_sprite);
+    const size_t ob_pad = (ob + 15) & ~(size_t)15;
+    int rc = ensure_stage(ctx, vb + ob_pad + sb);
+    if (rc) return rc;
+    // a PM3D_NO_SYNC caller may still have the previous frame's H2D copies in flight
+    if (ctx->stage_ev) PM3D_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev));
+    else PM3D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev, cudaEventDisableTiming));
+    uint8_t *st = (uint8_t *)ctx->stage;
+    memcpy(st, views, vb);
+    memcpy(st + vb, sprite_offset, ob);
+    if (sb) memcpy(st + vb + ob_pad, sprites, sb);
+    PM3D_CUDA(ctx, cudaMemcpyAsync(ctx->views, st, vb, cudaMemcpyHostToDevice, ctx->stream));
+    PM3D_CUDA(ctx, cudaMemcpyAsync(ctx->sprite_offset, st + vb, ob, cudaMemcpyHostToDevice, ctx->stream));
+    if (sb) PM3D_CUDA(ctx, cudaMemcpyAsync(ctx->sprites, st + vb + ob_pad, sb, cudaMemcpyHostToDevice, ctx->stream));
+    PM3D_CUDA(ctx, cudaEventRecord(ctx->stage_ev, ctx->stream));
+
+    uint8_t *target = (out_rgba && (flags & PM3D_OUT_DEVICE)) ? out_rgba : ctx->frame;
+    if ((rc = pm3d_launch_cast(ctx, n_views))) return rc;
+    if ((rc = pm3d_launch_view_setup(ctx, n_views, n_sprites))) return rc;
+    if ((rc = pm3d_launch_compose(ctx, n_views, target))) return rc;
+    ctx->last_frame = target;
+    ctx->last_views = n_views;
+
+    const size_t fb = (size_t)n_views * ctx->w * ctx->h * 4;
+    if (out_rgba && !(flags & PM3D_OUT_DEVICE))
+        PM3D_CUDA(ctx, cudaMemcpyAsync(out_rgba, ctx->frame, fb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_rects && n_sprites)
+        PM3D_CUDA(ctx, cudaMemcpyAsync(out_rects, ctx->rects, (size_t)n_sprites * sizeof(pm3d_rect), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_conv)
+        PM3D_CUDA(ctx, cudaMemcpyAsync(out_conv, ctx->conv, (size_t)n_views * sizeof(pm3d_convergence), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!(flags & PM3D_NO_SYNC)) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PM3D_OK;
+}
+
+int pm3d_download_columns(pm3d_ctx *ctx, int view, pm3d_column *columns, double *zbuf) {
+    if (!ctx) return PM3D_ERR_ARG;
+    if (view < 0 || view >= ctx->last_views) return pm3d_fail(ctx, PM3D_ERR_ARG, "view %d not rendered", view);
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (columns) {
+        if (!ctx->keep_columns || !ctx->dbg_cols) return pm3d_fail(ctx, PM3D_ERR_ARG, "PM3D_OPT_KEEP_COLUMNS is off");
+        const size_t cnt = (size_t)ctx->num_levels * ctx->w;
+        PM3D_CUDA(ctx, cudaMemcpyAsync(columns, ctx->dbg_cols + (size_t)view * cnt, cnt * sizeof(pm3d_column), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (zbuf)
+        PM3D_CUDA(ctx, cudaMemcpyAsync(zbuf, ctx->zbuf + (size_t)view * ctx->w, (size_t)ctx->w * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PM3D_OK;
+}
+
+int pm3d_frame_checksums(pm3d_ctx *ctx, int n_views, uint64_t *out, uint32_t flags) {
+    if (!ctx) return PM3D_ERR_ARG;
+    if (!ctx->last_frame || n_views < 1 || n_views > ctx->last_views || !out) return pm3d_fail(ctx, PM3D_ERR_ARG, "nothing rendered / bad arguments");
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = pm3d_launch_checksum(ctx, n_views, ctx->last_frame);
+    if (rc) return rc;
+    if (flags & PM3D_OUT_DEVICE)
+        PM3D_CUDA(ctx, cudaMemcpyAsync(out, ctx->checksums, (size_t)n_views * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    else
+        PM3D_CUDA(ctx, cudaMemcpyAsync(out, ctx->checksums, (size_t)n_views * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!(flags & PM3D_NO_SYNC)) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PM3D_OK;
+}
+
+void *pm3d_last_frame_device(pm3d_ctx *ctx) { return ctx ? ctx->last_frame : nullptr; }
+
+// ------------------------------------------------------------------ LOS segments + bins
+
+static inline int64_t host_go_int(double v) {
+    if (!(v > -9223372036854775808.0 && v < 9223372036854775808.0)) return INT64_MIN;
+    return (int64_t)v;
+}
+
+int pm3d_upload_segments(pm3d_ctx *ctx, const double *xyxy, int n) {
+    if (!ctx) return PM3D_ERR_ARG;
+    if (n < 0 || (n > 0 && !xyxy)) return pm3d_fail(ctx, PM3D_ERR_ARG, "null segments");
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    // bounding box of all endpoints -> bin area dilated by one cell plus one spare
+    double minx = 0, miny = 0, maxx = 1, maxy = 1;
+    for (int i = 0; i < n; i++) {
+        for (int k = 0; k < 4; k++)
+            if (!isfinite(xyxy[i * 4 + k])) return pm3d_fail(ctx, PM3D_ERR_ARG, "segment %d is not finite", i);
+        const double *s = xyxy + (size_t)i * 4;
+        if (i == 0) { minx = std::min(s[0], s[2]); maxx = std::max(s[0], s[2]); miny = std::min(s[1], s[3]); maxy = std::max(s[1], s[3]); }
+        minx = std::min(minx, std::min(s[0], s[2])); maxx = std::max(maxx, std::max(s[0], s[2]));
+        miny = std::min(miny, std::min(s[1], s[3])); maxy = std::max(maxy, std::max(s[1], s[3]));
+    }
+    if (maxx - minx > 30000 || maxy - miny > 30000) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "segment extent too large to bin");
+    const int x0 = (int)floor(minx) - 2, y0 = (int)floor(miny) - 2;
+    const int bw = (int)floor(maxx) + 3 - x0, bh = (int)floor(maxy) + 3 - y0;
+    std::vector<int32_t> count((size_t)bw * bh + 1, 0);
+    std::vector<int4> irect(std::max(n, 1));
+    auto cell_range = [&](const double *s, int &cx0, int &cy0, int &cx1, int &cy1) {
+        cx0 = (int)floor(std::min(s[0], s[2])) - 1 - x0; cx1 = (int)floor(std::max(s[0], s[2])) + 1 - x0;
+        cy0 = (int)floor(std::min(s[1], s[3])) - 1 - y0; cy1 = (int)floor(std::max(s[1], s[3])) + 1 - y0;
+    };
+    for (int i = 0; i < n; i++) {
+        const double *s = xyxy + (size_t)i * 4;
+        int cx0, cy0, cx1, cy1;
+        cell_range(s, cx0, cy0, cx1, cy1);
+        for (int cy = cy0; cy <= cy1; cy++)
+            for (int cx = cx0; cx <= cx1; cx++) count[(size_t)cy * bw + cx + 1]++;
+        int64_t ax = host_go_int(s[0]), ay = host_go_int(s[1]), bx = host_go_int(s[2]), by = host_go_int(s[3]);
+        if (ax > bx) std::swap(ax, bx);
+        if (ay > by) std::swap(ay, by);
+        irect[i] = make_int4((int)ax, (int)ay, (int)bx, (int)by);
+    }
+    for (size_t c = 0; c < (size_t)bw * bh; c++) count[c + 1] += count[c];
+    std::vector<int32_t> items(std::max<size_t>(count.back(), 1));
+    std::vector<int32_t> fill(count.begin(), count.end() - 1);
+    for (int i = 0; i < n; i++) {
+        const double *s = xyxy + (size_t)i * 4;
+        int cx0, cy0, cx1, cy1;
+        cell_range(s, cx0, cy0, cx1, cy1);
+        for (int cy = cy0; cy <= cy1; cy++)
+            for (int cx = cx0; cx <= cx1; cx++) items[fill[(size_t)cy * bw + cx]++] = i;
+    }
+    int rc;
+    if ((rc = dev_realloc(ctx, &ctx->segs, (size_t)std::max(n, 1) * 4))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->seg_irect, (size_t)std::max(n, 1)))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->cell_start, count.size()))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->cell_items, items.size()))) return rc;
+    if (n) {
+        PM3D_CUDA(ctx, cudaMemcpy(ctx->segs, xyxy, (size_t)n * 32, cudaMemcpyHostToDevice));
+        PM3D_CUDA(ctx, cudaMemcpy(ctx->seg_irect, irect.data(), (size_t)n * sizeof(int4), cudaMemcpyHostToDevice));
+    }
+    PM3D_CUDA(ctx, cudaMemcpy(ctx->cell_start, count.data(), count.size() * 4, cudaMemcpyHostToDevice));
+    PM3D_CUDA(ctx, cudaMemcpy(ctx->cell_items, items.data(), items.size() * 4, cudaMemcpyHostToDevice));
+    ctx->n_segs = n; ctx->bin_x0 = x0; ctx->bin_y0 = y0; ctx->bin_w = bw; ctx->bin_h = bh;
+    return PM3D_OK;
+}
+
+// ------------------------------------------------------------------ memory + timing helpers
+
+int pm3d_device_alloc(pm3d_ctx *ctx, int64_t bytes, void **out) {
+    if (!ctx || !out || bytes < 0) return PM3D_ERR_ARG;
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    PM3D_CUDA(ctx, cudaMalloc(out, (size_t)std::max<int64_t>(bytes, 1)));
+    return PM3D_OK;
+}
+int pm3d_device_free(pm3d_ctx *ctx, void *ptr) {
+    if (!ctx) return PM3D_ERR_ARG;
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    PM3D_CUDA(ctx, cudaFree(ptr));
+    return PM3D_OK;
+}
+int pm3d_host_alloc(pm3d_ctx *ctx, int64_t bytes, void **out) {
+    if (!ctx || !out || bytes < 0) return PM3D_ERR_ARG;
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    PM3D_CUDA(ctx, cudaMallocHost(out, (size_t)std::max<int64_t>(bytes, 1)));
+    return PM3D_OK;
+}
+int pm3d_host_free(pm3d_ctx *ctx, void *ptr) {
+    if (!ctx) return PM3D_ERR_ARG;
+    PM3D_CUDA(ctx, cudaFreeHost(ptr));
+    return PM3D_OK;
+}
+int pm3d_memcpy_h2d(pm3d_ctx *ctx, void *dst, const void *src, int64_t bytes) {
+    if (!ctx) return PM3D_ERR_ARG;
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    PM3D_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+    PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PM3D_OK;
+}
+int pm3d_memcpy_d2h(pm3d_ctx *ctx, void *dst, const void *src, int64_t bytes) {
+    if (!ctx) return PM3D_ERR_ARG;
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    PM3D_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PM3D_OK;
+}
+
+int pm3d_timer_start(pm3d_ctx *ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 16) return PM3D_ERR_ARG;
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->ev_start[slot]) {
+        PM3D_CUDA(ctx, cudaEventCreate(&ctx->ev_start[slot]));
+        PM3D_CUDA(ctx, cudaEventCreate(&ctx->ev_stop[slot]));
+    }
+    PM3D_CUDA(ctx, cudaEventRecord(ctx->ev_start[slot], ctx->stream));
+    return PM3D_OK;
+}
+int pm3d_timer_stop(pm3d_ctx *ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 16 || !ctx->ev_stop[slot]) return PM3D_ERR_ARG;
+    PM3D_CUDA(ctx, cudaEventRecord(ctx->ev_stop[slot], ctx->stream));
+    return PM3D_OK;
+}
+int pm3d_timer_elapsed_ms(pm3d_ctx *ctx, int slot, float *ms) {
+    if (!ctx || slot < 0 || slot >= 16 || !ctx->ev_stop[slot] || !ms) return PM3D_ERR_ARG;
+    PM3D_CUDA(ctx, cudaEventSynchronize(ctx->ev_stop[slot]));
+    PM3D_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev_start[slot], ctx->ev_stop[slot]));
+    return PM3D_OK;
+}
+
+int64_t pm3d_launch_count(const pm3d_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int pm3d_flush_l2(pm3d_ctx *ctx) {
+    if (!ctx) return PM3D_ERR_ARG;
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->flush_buf) {
+        ctx->flush_bytes = (size_t)256 << 20;  // 256 MiB > 126 MB L2
+        PM3D_CUDA(ctx, cudaMalloc((void **)&ctx->flush_buf, ctx->flush_bytes));
+    }
+    PM3D_CUDA(ctx, cudaMemsetAsync(ctx->flush_buf, 0, ctx->flush_bytes, ctx->stream));
+    return PM3D_OK;
+}
+
+}  // extern "C"

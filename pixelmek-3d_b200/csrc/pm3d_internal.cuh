@@ -1,0 +1,188 @@
+// pm3d_internal.cuh — shared device helpers, HBM record layouts and the ctx of libpm3d.so.
+// sm_100a only.  Compiled with -fmad=false: the path's binary64 arithmetic must not be
+// contracted into FMAs (Go on amd64 never fuses), see DESIGN.md "numeric contract".
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "pm3d.h"
+
+// ------------------------------------------------------------------ HBM layouts
+
+// One (view, level, column) wall slice as the compose kernel consumes it.  32 B = 2 x uint4.
+struct __align__(16) ColRec {
+    int32_t ya, yb;        // visible rows [ya, yb) clipped to the screen; ya >= yb: nothing
+    uint32_t tile_texx;    // (tile << 16) | texX
+    uint32_t tint;         // R | G<<8 | B<<16 | 255<<24
+    uint64_t pos0, step2;  // texel row of screen row y = (pos0 + y*step2) >> 33 (mod 2^64 arithmetic)
+};
+static_assert(sizeof(ColRec) == 32, "ColRec");
+
+// Level-0 floor-cast parameters of one (view, column).  32 B.
+struct __align__(16) FloorRec {
+    double fxw, fyw;  // floorXWall, floorYWall
+    double dw;        // distWall
+    int32_t fs;       // first floor row (drawEnd + 1, or h when none)
+    int32_t _pad;
+};
+static_assert(sizeof(FloorRec) == 32, "FloorRec");
+
+// Per (view, screen row) values shared by every column.  16 B.
+struct __align__(16) RowRec {
+    double cd;       // currentDist of the floor cast
+    uint32_t tint;   // floor light tint of this row
+    uint32_t info;   // bit31: floor row valid (render distance); bits 0..15: sky/floor-box texel row
+};
+static_assert(sizeof(RowRec) == 16, "RowRec");
+
+// One visible sprite of a view, in paint order (far -> near).  96 B.
+struct __align__(16) DrawRec {
+    int32_t dsx, dex, dsy, dey;  // unclipped screen rect [dsx,dex) x [dsy,dey)
+    double transformY;           // depth for the z test
+    uint64_t ypos0, ystep2;      // sprite texel row of screen row y = (ypos0 + y*ystep2) >> 33
+    uint64_t xmagic;             // ceil(2^64 / spriteWidth): texX = mulhi(k*texW, xmagic)
+    uint64_t sheet_px;           // pixel index of the rect's (rx0, ry0) inside sheet_pixels (may wrap)
+    uint32_t tex_w, tex_h;       // TextureRect size
+    uint32_t sheet_w;            // sheet row pitch in pixels
+    uint32_t tint;
+    uint16_t tx_lo, tx_hi, ty_lo, ty_hi;  // texel ranges that fall inside the sheet
+    int32_t src;                 // index into the view's sprite list
+    int32_t _pad;
+};
+static_assert(sizeof(DrawRec) == 96, "DrawRec");
+
+struct SheetInfo {
+    int64_t px_offset;  // first pixel of the sheet inside sheet_pixels (in pixels)
+    int32_t w, h;
+};
+
+// ------------------------------------------------------------------ ctx
+
+struct pm3d_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int64_t launches = 0;
+    int sm_count = 148;
+
+    // mission data
+    uint16_t *grid = nullptr;
+    int stored_levels = 0, map_w = 0, map_h = 0, num_levels = 0;
+    int16_t *wall_lut = nullptr;  // [32768][2]
+    uint8_t *atlas = nullptr;
+    int n_tiles = 0, tex_size = 0, tex_shift = 0;
+    int16_t *floor_tiles = nullptr;  // [map_w][map_h]
+    int floor_w = 0, floor_h = 0;
+    int sky_tile = -1, floorbox_tile = -1;
+    uint8_t *sheet_pixels = nullptr;
+    SheetInfo *sheet_info = nullptr;
+    int n_sheets = 0;
+
+    // view configuration
+    int w = 0, h = 0, max_views = 0, max_sprites = 0, n_groups = 0;
+    int keep_columns = 0, force_painter = 0;
+    int last_views = 0;
+
+    // per-call device buffers
+    pm3d_view *views = nullptr;
+    ColRec *col_rec = nullptr;      // [views][levels][w]
+    FloorRec *floor_rec = nullptr;  // [views][w]
+    double *zbuf = nullptr;         // [views][w]
+    RowRec *row_rec = nullptr;      // [views][h]
+    pm3d_column *dbg_cols = nullptr;  // [views][levels][w] when keep_columns
+    int dbg_levels = 0, dbg_views = 0;
+    pm3d_sprite *sprites = nullptr;  // [max_sprites]
+    int32_t *sprite_offset = nullptr;  // [max_views + 1]
+    DrawRec *draw_rec = nullptr;     // [max_sprites], per view contiguous at sprite_offset[v]
+    int32_t *n_draw = nullptr;       // [max_views]
+    uint16_t *bin_list = nullptr;    // [max_sprites * n_groups]
+    int32_t *bin_count = nullptr;    // [max_views * n_groups]
+    pm3d_rect *rects = nullptr;      // [max_sprites]
+    pm3d_convergence *conv = nullptr;  // [max_views]
+    uint8_t *frame = nullptr;        // [max_views][h][w][4]
+    uint8_t *last_frame = nullptr;   // where the last render wrote (frame or caller memory)
+    uint64_t *checksums = nullptr;   // [max_views]
+
+    // pinned staging for host-side arguments
+    void *stage = nullptr;
+    size_t stage_bytes = 0;
+    cudaEvent_t stage_ev = nullptr;  // recorded after the last H2D out of `stage`
+
+    // LOS / collision
+    double *segs = nullptr;          // [n_segs][4]
+    int4 *seg_irect = nullptr;       // Go image.Rect of int-truncated endpoints
+    int n_segs = 0;
+    int32_t *cell_start = nullptr;   // CSR over bin cells
+    int32_t *cell_items = nullptr;
+    int bin_x0 = 0, bin_y0 = 0, bin_w = 0, bin_h = 0;
+    void *io_a = nullptr, *io_b = nullptr, *io_c = nullptr;  // batch staging on device
+    size_t io_a_bytes = 0, io_b_bytes = 0, io_c_bytes = 0;
+
+    // timers / L2 flush
+    cudaEvent_t ev_start[16] = {}, ev_stop[16] = {};
+    uint8_t *flush_buf = nullptr;
+    size_t flush_bytes = 0;
+};
+
+int pm3d_fail(pm3d_ctx *ctx, int code, const char *fmt, ...);
+#define PM3D_CUDA(ctx, call)                                                                         \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) return pm3d_fail((ctx), PM3D_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+// kernel launchers (one per .cu)
+int pm3d_launch_cast(pm3d_ctx *ctx, int n_views);
+int pm3d_launch_view_setup(pm3d_ctx *ctx, int n_views, int n_sprites_total);
+int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out);
+int pm3d_launch_checksum(pm3d_ctx *ctx, int n_views, const uint8_t *frames);
+
+// ------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+
+// Go int(float64) on amd64 (CVTTSD2SQ): truncation, NaN / out of range -> INT64_MIN.
+__device__ __forceinline__ int64_t go_int(double v) {
+    if (!(v > -9223372036854775808.0 && v < 9223372036854775808.0)) return INT64_MIN;
+    return (int64_t)v;  // cvt.rzi.s64.f64
+}
+// Go int arithmetic wraps silently.
+__device__ __forceinline__ int64_t wadd(int64_t a, int64_t b) { return (int64_t)((uint64_t)a + (uint64_t)b); }
+__device__ __forceinline__ int64_t wsub(int64_t a, int64_t b) { return (int64_t)((uint64_t)a - (uint64_t)b); }
+__device__ __forceinline__ int64_t wneg(int64_t a) { return (int64_t)(0ull - (uint64_t)a); }
+__device__ __forceinline__ int64_t wmul(int64_t a, int64_t b) { return (int64_t)((uint64_t)a * (uint64_t)b); }
+__device__ __forceinline__ int64_t clamp_i64(int64_t v, int64_t lo, int64_t hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// blit model: nearest sample of n texels over len pixels
+__device__ __forceinline__ uint64_t span_step(int64_t n_src, int64_t len_dst) {
+    return ((uint64_t)n_src << 32) / (uint64_t)len_dst;
+}
+
+// lighting: byte(ClampInt(int(base + sqrt(dist)*falloff + illumination (+ extra)), min, max)) per channel
+__device__ __forceinline__ uint32_t light_tint(const pm3d_view &c, double dist, int base, double extra, bool use_extra) {
+    double shadow = sqrt(dist) * c.light_falloff;
+    double v = (double)base + shadow + c.global_illumination;
+    if (use_extra) v = v + extra;
+    int64_t iv = go_int(v);
+    uint32_t r = (uint32_t)clamp_i64(iv, c.min_light[0], c.max_light[0]) & 255u;
+    uint32_t g = (uint32_t)clamp_i64(iv, c.min_light[1], c.max_light[1]) & 255u;
+    uint32_t b = (uint32_t)clamp_i64(iv, c.min_light[2], c.max_light[2]) & 255u;
+    return r | (g << 8) | (b << 16) | (255u << 24);
+}
+
+// out = (c*tint + dst*(255-a) + 127) / 255 per channel (nvcc lowers /255u to an exact mul.hi + shift)
+__device__ __forceinline__ uint32_t div255(uint32_t v) { return v / 255u; }
+__device__ __forceinline__ uint32_t blend_over(uint32_t dst, uint32_t src, uint32_t tint) {
+    uint32_t a = src >> 24;
+    if (a == 0) return dst;
+    uint32_t ia = 255u - a;
+    uint32_t r = div255((src & 255u) * (tint & 255u) + (dst & 255u) * ia + 127u);
+    uint32_t g = div255(((src >> 8) & 255u) * ((tint >> 8) & 255u) + ((dst >> 8) & 255u) * ia + 127u);
+    uint32_t b = div255(((src >> 16) & 255u) * ((tint >> 16) & 255u) + ((dst >> 16) & 255u) * ia + 127u);
+    uint32_t o = div255(a * 255u + (dst >> 24) * ia + 127u);
+    r = min(r, 255u); g = min(g, 255u); b = min(b, 255u); o = min(o, 255u);
+    return r | (g << 8) | (b << 16) | (o << 24);
+}
+#endif

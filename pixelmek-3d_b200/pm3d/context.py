@@ -1,0 +1,199 @@
+"""Context: one libpm3d ctx (one GPU, one stream).  Thin, typed wrapper over the C-ABI."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import COLUMN_DTYPE, CONV_DTYPE, SPRITE_DTYPE, VIEW_DTYPE, Pm3dError, ptr
+from .scene import SceneData
+
+
+class Context:
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.pm3d_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != 0:
+            raise Pm3dError(f"pm3d_create failed ({rc}): {self.lib.pm3d_last_error(None).decode()}")
+        self.h = h
+        self.device = device
+        self.scene: SceneData | None = None
+        self.w = self.h_px = 0
+        self._keep = []
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise Pm3dError(f"{what} failed ({rc}): {self.lib.pm3d_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pm3d_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._check(self.lib.pm3d_sync(self.h), "pm3d_sync")
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.pm3d_launch_count(self.h))
+
+    # ------------------------------------------------------------------ mission-time uploads
+    def upload_scene(self, s: SceneData):
+        grid = np.ascontiguousarray(s.grid, dtype=np.uint16)
+        ls, mw, mh = grid.shape
+        self._check(self.lib.pm3d_upload_grid(self.h, ptr(grid), ls, mw, mh, int(s.num_levels)), "pm3d_upload_grid")
+        ti = np.ascontiguousarray(s.wall_tex_index, dtype=np.int32)
+        t0 = np.ascontiguousarray(s.wall_tile_side0, dtype=np.int32)
+        t1 = np.ascontiguousarray(s.wall_tile_side1, dtype=np.int32)
+        self._check(self.lib.pm3d_upload_wall_textures(self.h, ptr(ti), ptr(t0), ptr(t1), len(ti)), "pm3d_upload_wall_textures")
+        atlas = np.ascontiguousarray(s.atlas, dtype=np.uint8)
+        self._check(self.lib.pm3d_upload_atlas(self.h, ptr(atlas), atlas.shape[0], atlas.shape[1]), "pm3d_upload_atlas")
+        ft = np.ascontiguousarray(s.floor_tiles, dtype=np.int16)
+        self._check(self.lib.pm3d_upload_floor_tiles(self.h, ptr(ft), ft.shape[0], ft.shape[1]), "pm3d_upload_floor_tiles")
+        self._check(self.lib.pm3d_set_box_tiles(self.h, int(s.sky_tile), int(s.floorbox_tile)), "pm3d_set_box_tiles")
+        sheets = [np.ascontiguousarray(x, dtype=np.uint8) for x in s.sheets]
+        if sheets:
+            sizes = np.array([x.size for x in sheets], dtype=np.int64)
+            off = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+            pix = np.concatenate([x.reshape(-1) for x in sheets])
+            sw = np.array([x.shape[1] for x in sheets], dtype=np.int32)
+            sh = np.array([x.shape[0] for x in sheets], dtype=np.int32)
+            self._check(self.lib.pm3d_upload_sprite_sheets(self.h, ptr(pix), ptr(off), ptr(sw), ptr(sh), len(sheets)),
+                        "pm3d_upload_sprite_sheets")
+        else:
+            self._check(self.lib.pm3d_upload_sprite_sheets(self.h, None, None, None, None, 0), "pm3d_upload_sprite_sheets")
+        self.scene = s
+
+    def set_view(self, w: int, h: int, max_views: int = 1, max_sprites_total: int = 2048):
+        self._check(self.lib.pm3d_set_view(self.h, w, h, max_views, max_sprites_total), "pm3d_set_view")
+        self.w, self.h_px = w, h
+
+    def set_option(self, option: int, value: int):
+        self._check(self.lib.pm3d_set_option(self.h, option, value), "pm3d_set_option")
+
+    # ------------------------------------------------------------------ frame path
+    def render(self, views: np.ndarray, sprites: np.ndarray | None = None, sprite_offset: np.ndarray | None = None,
+               want_frame: bool = True, out_device_ptr: int | None = None, no_sync: bool = False):
+        """Camera.Update + Draw for len(views) views.  Returns dict(rgba, rects, conv)."""
+        views = np.ascontiguousarray(views, dtype=VIEW_DTYPE).reshape(-1)
+        nv = len(views)
+        if sprites is None:
+            sprites = np.zeros(0, dtype=SPRITE_DTYPE)
+        sprites = np.ascontiguousarray(sprites, dtype=SPRITE_DTYPE).reshape(-1)
+        if sprite_offset is None:
+            if nv != 1:
+                raise Pm3dError("sprite_offset is required for more than one view")
+            sprite_offset = np.array([0, len(sprites)], dtype=np.int32)
+        sprite_offset = np.ascontiguousarray(sprite_offset, dtype=np.int32)
+        ns = int(sprite_offset[-1])
+        rects = np.zeros((max(ns, 1), 4), dtype=np.int32)
+        conv = np.zeros(nv, dtype=CONV_DTYPE)
+        flags = 0
+        rgba = None
+        out_p = None
+        if out_device_ptr is not None:
+            flags |= _lib.PM3D_OUT_DEVICE
+            out_p = C.c_void_p(out_device_ptr)
+        elif want_frame:
+            rgba = np.empty((nv, self.h_px, self.w, 4), dtype=np.uint8)
+            out_p = ptr(rgba)
+        if no_sync:
+            flags |= _lib.PM3D_NO_SYNC
+            self._keep = [views, sprites, sprite_offset, rects, conv, rgba]
+        self._check(
+            self.lib.pm3d_render(self.h, ptr(views), nv, ptr(sprites) if ns else None, ptr(sprite_offset), out_p,
+                                 ptr(rects), ptr(conv), flags),
+            "pm3d_render",
+        )
+        return {"rgba": rgba, "rects": rects[:ns], "conv": conv}
+
+    def download_columns(self, view: int = 0):
+        s = self.scene
+        cols = np.zeros((int(s.num_levels), self.w), dtype=COLUMN_DTYPE)
+        zbuf = np.zeros(self.w, dtype=np.float64)
+        self._check(self.lib.pm3d_download_columns(self.h, view, ptr(cols), ptr(zbuf)), "pm3d_download_columns")
+        return cols, zbuf
+
+    def frame_checksums(self, n_views: int) -> np.ndarray:
+        out = np.zeros(n_views, dtype=np.uint64)
+        self._check(self.lib.pm3d_frame_checksums(self.h, n_views, ptr(out), 0), "pm3d_frame_checksums")
+        return out
+
+    # ------------------------------------------------------------------ LOS / collision path
+    def upload_segments(self, segs: np.ndarray):
+        segs = np.ascontiguousarray(segs, dtype=np.float64).reshape(-1, 4)
+        self._check(self.lib.pm3d_upload_segments(self.h, ptr(segs), len(segs)), "pm3d_upload_segments")
+
+    def los_batch(self, rays: np.ndarray) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 4)
+        out = np.zeros(len(rays), dtype=np.uint8)
+        self._check(self.lib.pm3d_los_batch(self.h, ptr(rays), len(rays), ptr(out), 0), "pm3d_los_batch")
+        return out
+
+    def move_batch(self, moves: np.ndarray, clip: float):
+        moves = np.ascontiguousarray(moves, dtype=np.float64).reshape(-1, 4)
+        n = len(moves)
+        pos = np.zeros((n, 2), dtype=np.float64)
+        col = np.zeros(n, dtype=np.uint8)
+        self._check(self.lib.pm3d_move_batch(self.h, ptr(moves), n, float(clip), ptr(pos), ptr(col), 0), "pm3d_move_batch")
+        return pos, col
+
+    # ------------------------------------------------------------------ device memory + timers
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.pm3d_device_alloc(self.h, int(nbytes), C.byref(p)), "pm3d_device_alloc")
+        return int(p.value)
+
+    def device_free(self, p: int):
+        self._check(self.lib.pm3d_device_free(self.h, C.c_void_p(p)), "pm3d_device_free")
+
+    def host_alloc(self, nbytes: int, dtype=np.uint8, shape=None) -> np.ndarray:
+        """Pinned host buffer as a numpy array (kept alive by this ctx)."""
+        p = C.c_void_p()
+        self._check(self.lib.pm3d_host_alloc(self.h, int(nbytes), C.byref(p)), "pm3d_host_alloc")
+        buf = (C.c_uint8 * int(nbytes)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.uint8).view(dtype)
+        return arr.reshape(shape) if shape is not None else arr
+
+    def h2d(self, dst: int, src: np.ndarray):
+        src = np.ascontiguousarray(src)
+        self._check(self.lib.pm3d_memcpy_h2d(self.h, C.c_void_p(dst), ptr(src), src.nbytes), "pm3d_memcpy_h2d")
+
+    def d2h(self, dst: np.ndarray, src: int):
+        self._check(self.lib.pm3d_memcpy_d2h(self.h, ptr(dst), C.c_void_p(src), dst.nbytes), "pm3d_memcpy_d2h")
+
+    def timer_start(self, slot: int = 0):
+        self._check(self.lib.pm3d_timer_start(self.h, slot), "pm3d_timer_start")
+
+    def timer_stop(self, slot: int = 0):
+        self._check(self.lib.pm3d_timer_stop(self.h, slot), "pm3d_timer_stop")
+
+    def timer_ms(self, slot: int = 0) -> float:
+        ms = C.c_float()
+        self._check(self.lib.pm3d_timer_elapsed_ms(self.h, slot, C.byref(ms)), "pm3d_timer_elapsed_ms")
+        return float(ms.value)
+
+    def flush_l2(self):
+        self._check(self.lib.pm3d_flush_l2(self.h), "pm3d_flush_l2")
+
+
+def generate_wall_collision_lines(level0: np.ndarray, has_boundary_wall: bool, clip: float) -> np.ndarray:
+    """Host mirror of Map.GenerateWallCollisionLines (game/model/map.go:811-851); needs no GPU."""
+    lib = _lib.load()
+    level0 = np.ascontiguousarray(level0, dtype=np.uint16)
+    w, h = level0.shape
+    n = lib.pm3d_generate_wall_collision_lines(ptr(level0), w, h, int(bool(has_boundary_wall)), float(clip), None, 0)
+    if n < 0:
+        raise Pm3dError(f"pm3d_generate_wall_collision_lines failed ({n})")
+    out = np.zeros((max(n, 1), 4), dtype=np.float64)
+    lib.pm3d_generate_wall_collision_lines(ptr(level0), w, h, int(bool(has_boundary_wall)), float(clip), ptr(out), n)
+    return out[:n]

@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py — measurement of the B200-native PixelMek 3D raycasting hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+Headline workload (BASELINE.json configs[1], "c2"): single camera 1920x1080 on the bundled
+proving_grounds map with floor casting and 200 sprites.  One STEP = one frame = one pass of
+the hot path (column cast -> view setup -> compose).  A ring of RING distinct poses/output
+framebuffers (> L2) is cycled so successive frames never hit the previous frame's lines.
+With N GPUs every rank renders its own K frames of independent cameras (weak scaling; the path
+has no exchange step — the only collective is one all_gather of the per-frame checksums).
+
+  value        frames/s, inputs (views, sprites) and outputs resident in HBM, CUDA-event timed
+  e2e          frames/s through the public API (pm3d_render) with HOST buffers: H2D of the
+               view + sprite snapshot and D2H of the 8.3 MB frame + rects + convergence per step
+  roofline     compose kernel: algorithmic bytes (4*W*H per launch) / its mean CUDA-event
+               duration inside the timed region, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline the CPU oracle port (oracle/, all host cores) on a bounded sample of the same frames
+  extra        the batched sweeps: c4 (4096 views of 320x200) and c5 (16 Mi LOS rays), sharded
+
+--impl reference times the reference's CPU implementation of the path.  The Go binary cannot
+be built here (no Go toolchain, raycaster-go not vendored: DESIGN.md), so this arm runs the
+oracle port (kind "port") with all host threads on the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "pixelmek-3d_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+W_PX, H_PX, N_SPRITES, RING = 1920, 1080, 200, 24
+FRAME_BYTES = 4 * W_PX * H_PX  # algorithmic bytes of one frame
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.002):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.reason_bits = [], 0
+        self.sm_max = None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._halt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=1.0)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"]}
+        names = {
+            0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+            0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+            0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+        }
+        reasons = [n for b, n in names.items() if self.reason_bits & b and n != "gpu_idle"]
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def view_to_orc(O, v, w, h):
+    return O.make_camera(dict(
+        pos_x=v["pos_x"], pos_y=v["pos_y"], cam_z_px=v["cam_z_px"], dir_x=v["dir_x"], dir_y=v["dir_y"],
+        plane_x=v["plane_x"], plane_y=v["plane_y"], pitch_px=v["pitch_px"], w=w, h=h,
+        render_distance=v["render_distance"], light_falloff=v["light_falloff"],
+        global_illumination=v["global_illumination"], min_light=v["min_light"], max_light=v["max_light"]))
+
+
+def cpu_frames(cfg, budget_s: float, threads: int, max_frames: int | None = None, min_frames: int = 3):
+    """The oracle port on the same frames: returns (frames, seconds)."""
+    from oracle import oracle as O
+
+    scene = O.Scene(cfg["scene"])
+    off = cfg["offsets"]
+    n = 0
+    # one untimed frame: page in, spin up the OpenMP team
+    O.render(scene, view_to_orc(O, cfg["views"][0], cfg["w"], cfg["h"]), cfg["sprites"][off[0]:off[1]].astype(O.SPRITE_DTYPE), threads)
+    t0 = time.perf_counter()
+    while True:
+        r = n % len(cfg["views"])
+        O.render(scene, view_to_orc(O, cfg["views"][r], cfg["w"], cfg["h"]),
+                 cfg["sprites"][off[r]:off[r + 1]].astype(O.SPRITE_DTYPE), threads)
+        n += 1
+        el = time.perf_counter() - t0
+        if max_frames is not None:
+            if n >= max_frames:
+                break
+        elif n >= min_frames and el >= budget_s:
+            break
+    return n, time.perf_counter() - t0
+
+
+def base_line(args, world, value, ms_per_step):
+    return {
+        "metric": "frames/s at 1920x1080 (walls+floor+200 sprites, one camera per GPU)",
+        "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": "c2: proving_grounds 500x500x3, 1920x1080, floor cast, 200 sprites, fov 70, render distance 100 cells",
+            "rays_per_frame": W_PX * 3, "pixels_per_frame": W_PX * H_PX, "ring": RING,
+            "l2": f"ring of {RING} distinct poses and output framebuffers = {RING * FRAME_BYTES / 1e6:.0f} MB > 126 MB L2",
+            "parallelism": f"{world} independent camera(s), one per GPU; no data-path collective",
+        },
+    }
+
+
+# --------------------------------------------------------------------------------------- reference arm
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from pm3d import workloads as Wk
+
+    threads = os.cpu_count() or 1
+    cfg = Wk.config_c2(W_PX, H_PX, N_SPRITES, n_poses=RING)
+    cpu_frames(cfg, 0.0, threads, max_frames=max(args.warmup, 1))
+    n, sec = cpu_frames(cfg, 0.0, threads, max_frames=args.steps)
+    value = n / sec
+    line = base_line(args, world, value, 1e3 * sec / n)
+    line["impl"] = "reference"
+    line["n_gpus"] = world
+    line["config"]["parallelism"] = f"CPU oracle port, {threads} OpenMP threads (rank 0 only)"
+    line["cpu_baseline"] = {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
+                            "sample": f"{n} full 1920x1080 frames of the c2 ring; the Go reference cannot be built here (no Go toolchain), this is the C restatement in oracle/"}
+    line["e2e"] = {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    line["gpu_launches"] = 0
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- our arm
+
+
+def sweep_c4(ctx, rank, world, dist, torch, dev):
+    """4096 views of 320x200 sharded i % world; returns dict for 'extra'."""
+    from pm3d import shard, workloads as Wk
+
+    n_views, w, h = 4096, 320, 200
+    cfg = Wk.config_c4(n_views, w, h)
+    mine = shard.view_shard(n_views, rank, world)
+    views = cfg["views"][mine]
+    off_all = cfg["offsets"]
+    recs = [cfg["sprites"][off_all[i]:off_all[i + 1]] for i in mine]
+    offs = np.concatenate([[0], np.cumsum([len(r) for r in recs])]).astype(np.int32)
+    sprites = np.concatenate(recs)
+    nv, ns = len(views), len(sprites)
+    ctx.upload_scene(cfg["scene"])
+    ctx.set_view(w, h, nv, ns)
+    d_views, d_spr, d_off = ctx.device_alloc(views.nbytes), ctx.device_alloc(sprites.nbytes), ctx.device_alloc(offs.nbytes)
+    ctx.h2d(d_views, views); ctx.h2d(d_spr, sprites); ctx.h2d(d_off, offs)
+    fb = nv * w * h * 4
+    d_out = ctx.device_alloc(fb)
+    for _ in range(3):
+        ctx.render_resident(d_views, nv, d_spr, d_off, ns, d_out)
+    ctx.sync()
+    reps = 5
+    if world > 1:
+        dist.barrier()
+    ctx.flush_l2()
+    ctx.ktimer_begin(reps)
+    ctx.timer_start(2)
+    for _ in range(reps):
+        ctx.render_resident(d_views, nv, d_spr, d_off, ns, d_out)
+    ctx.timer_stop(2)
+    ms = ctx.timer_ms(2) / reps
+    kt = ctx.ktimer_collect(reps)
+    sums = ctx.frame_checksums(nv)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        g = shard.gather_views(torch.from_numpy(sums.view(np.int64)).to(dev), n_views, rank, world)
+        total = int(g.sum().item()) & 0xFFFFFFFFFFFFFFFF
+    else:
+        total = int(sums.view(np.int64).sum()) & 0xFFFFFFFFFFFFFFFF
+    for p in (d_views, d_spr, d_off, d_out):
+        ctx.device_free(p)
+    ms_max = float(t.item())
+    peak, _ = hbm_peak()
+    compose_ms = float(kt[:, 2].mean())
+    return {
+        "workload": "c4: 4096 views 320x200, 50 nearest sprites each, sharded i % n_gpus",
+        "views_per_s": n_views / (ms_max * 1e-3), "ms_per_sweep": ms_max, "views_per_gpu": nv,
+        "compose_ms": compose_ms, "cast_ms": float(kt[:, 0].mean()), "setup_ms": float(kt[:, 1].mean()),
+        "hbm_frac_compose": (fb / (compose_ms * 1e-3)) / 1e9 / peak,
+        "hbm_frac_sweep": (fb / (ms * 1e-3)) / 1e9 / peak,
+        "checksum_of_checksums": f"{total:016x}",
+    }
+
+
+def sweep_c5(ctx, rank, world, dist, torch, dev):
+    """16 Mi LOS rays on a 256x256 map, contiguous shards; returns dict for 'extra'."""
+    from pm3d import shard, workloads as Wk
+
+    n_rays = 1 << 24
+    lo, hi = shard.ray_shard(n_rays, rank, world)
+    grid = Wk.synthetic_levels(256, 256, 1, 0.10, 42)
+    from pm3d import generate_wall_collision_lines
+
+    segs = generate_wall_collision_lines(grid[0], True, Wk.CLIP_DISTANCE)
+    rays = Wk.los_rays(grid[0], n_rays, 43)[lo:hi]
+    n = len(rays)
+    ctx.upload_segments(segs)
+    d_rays, d_out = ctx.device_alloc(rays.nbytes), ctx.device_alloc(n)
+    ctx.h2d(d_rays, rays)
+    lib, C = ctx.lib, __import__("ctypes")
+    flags = 1 | 2 | 4  # OUT_DEVICE | IN_DEVICE | NO_SYNC
+    for _ in range(2):
+        ctx._check(lib.pm3d_los_batch(ctx.h, C.c_void_p(d_rays), n, C.c_void_p(d_out), flags), "pm3d_los_batch")
+    ctx.sync()
+    if world > 1:
+        dist.barrier()
+    reps = 3
+    ctx.timer_start(3)
+    for _ in range(reps):
+        ctx._check(lib.pm3d_los_batch(ctx.h, C.c_void_p(d_rays), n, C.c_void_p(d_out), flags), "pm3d_los_batch")
+    ctx.timer_stop(3)
+    ms = ctx.timer_ms(3) / reps
+    out = np.zeros(n, dtype=np.uint8)
+    ctx.d2h(out, d_out)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    visible = torch.tensor([int(out.sum())], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        g = shard.gather_rays(torch.from_numpy(out).to(dev), n_rays, rank, world)
+        visible = g.sum(dtype=torch.int64).reshape(1)
+    ctx.device_free(d_rays); ctx.device_free(d_out)
+    ms_max = float(t.item())
+    peak, _ = hbm_peak()
+    return {
+        "workload": f"c5: 16777216 LOS rays, 256x256 map 10% walls, {len(segs)} collision segments, contiguous shards",
+        "mrays_per_s": n_rays / (ms_max * 1e-3) / 1e6, "ms_per_batch": ms_max, "rays_per_gpu": n,
+        "hbm_frac": (33.0 * n / (ms * 1e-3)) / 1e9 / peak, "visible_rays": int(visible.item()),
+    }
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+
+    import pm3d
+    from pm3d import workloads as Wk
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    ctx = pm3d.Context(local_rank)
+
+    # ---- workload: every rank its own ring of cameras
+    cfg = Wk.config_c2(W_PX, H_PX, N_SPRITES, n_poses=RING, seed=12345 + 1000 * rank)
+    ctx.upload_scene(cfg["scene"])
+    ctx.set_view(W_PX, H_PX, 1, N_SPRITES)
+    views, sprites, off = cfg["views"], cfg["sprites"], cfg["offsets"]
+    slot_off = np.array([0, N_SPRITES], dtype=np.int32)
+    d_views = ctx.device_alloc(views.nbytes)
+    d_spr = ctx.device_alloc(sprites.nbytes)
+    d_off = ctx.device_alloc(slot_off.nbytes)
+    d_out = ctx.device_alloc(RING * FRAME_BYTES)
+    ctx.h2d(d_views, views); ctx.h2d(d_spr, sprites); ctx.h2d(d_off, slot_off)
+    vsz, ssz = views.dtype.itemsize, sprites.dtype.itemsize
+
+    def frame(i):
+        r = i % RING
+        ctx.render_resident(d_views + r * vsz, 1, d_spr + int(off[r]) * ssz, d_off, N_SPRITES, d_out + r * FRAME_BYTES)
+
+    for i in range(max(args.warmup, 3)):
+        frame(i)
+    ctx.sync()
+
+    # ---- timed region (device resident)
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = ctx.launches
+    kt_frames = min(args.steps, 2048)
+    sampler.start()
+    ctx.ktimer_begin(kt_frames)
+    ctx.timer_start(0)
+    for i in range(args.steps):
+        frame(i)
+    ctx.timer_stop(0)
+    elapsed_ms = ctx.timer_ms(0)
+    ctx.sync()
+    torch.cuda.synchronize()
+    sampler.stop()
+    launches = ctx.launches - launches0
+    kt = ctx.ktimer_collect(kt_frames)
+    sums = ctx.frame_checksums(1)  # last frame: compact result
+    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        allsum = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(allsum, torch.from_numpy(sums.view(np.int64)).to(dev))
+    elapsed_ms = float(t.item())
+    value = world * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- e2e through the public API with host buffers (pinned), synchronous per frame
+    host_out = ctx.host_alloc(FRAME_BYTES, np.uint8, (1, H_PX, W_PX, 4))
+    e2e_steps = max(3, min(args.steps, 200))
+    for i in range(3):
+        ctx.render(views[i % RING:i % RING + 1], sprites[off[i % RING]:off[i % RING + 1]], out=host_out)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        r = i % RING
+        ctx.render(views[r:r + 1], sprites[off[r]:off[r + 1]], out=host_out)
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps / float(te.item())
+
+    # ---- roofline of the dominant kernel (compose)
+    peak, peak_kind = hbm_peak()
+    compose_ms = float(kt[:, 2].mean()) if len(kt) else float("nan")
+    achieved = FRAME_BYTES / (compose_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get("k_compose_c2_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    line = base_line(args, world, value, elapsed_ms / args.steps)
+    line["clocks"] = sampler.summary()
+    line["e2e"] = {"value": e2e_value, "unit": "frames/s",
+                   "h2d_bytes_per_step": int(vsz + N_SPRITES * ssz + 8),
+                   "d2h_bytes_per_step": int(FRAME_BYTES + N_SPRITES * 16 + 32), "steps": e2e_steps,
+                   "note": "pm3d_render, pinned host buffers, one stream sync per frame"}
+    line["gpu_launches"] = int(launches * world)
+    line["roofline"] = {"bound": "hbm", "kernel": "k_compose", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650 GB/s",
+                        "algorithmic_bytes_per_launch": FRAME_BYTES, "kernel_ms": compose_ms,
+                        "other_kernels_ms": {"k_cast_columns": float(kt[:, 0].mean()) if len(kt) else None,
+                                             "k_view_setup": float(kt[:, 1].mean()) if len(kt) else None}}
+    line["mrays_per_s"] = value * W_PX * 3 / 1e6
+    line["mpixels_per_s"] = value * W_PX * H_PX / 1e6
+
+    # ---- batched sweeps (c4 views, c5 LOS rays), sharded over the same ranks
+    extra = {}
+    if not args.no_sweeps:
+        try:
+            extra["c4"] = sweep_c4(ctx, rank, world, dist, torch, dev)
+            extra["c5"] = sweep_c5(ctx, rank, world, dist, torch, dev)
+        except Exception as e:  # the headline line must still print
+            extra["error"] = repr(e)
+    line["extra"] = extra
+
+    # ---- CPU baseline beside it (rank 0, N=1 only)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        n, sec = cpu_frames(cfg, 10.0, threads)
+        n1, sec1 = cpu_frames(cfg, 3.0, 1)
+        line["cpu_baseline"] = {"value": n / sec, "unit": "frames/s", "cores": threads, "kind": "port",
+                                "sample": f"{n} full 1920x1080 frames of the same ring in {sec:.1f} s (oracle/ C restatement, OpenMP); single thread: {n1 / sec1:.2f} frames/s",
+                                "single_thread_value": n1 / sec1}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-sweeps", action="store_true", help="skip the c4/c5 batched sweeps")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -160,6 +160,14 @@ int pm3d_set_option(pm3d_ctx *ctx, int option, int value);
 int pm3d_render(pm3d_ctx *ctx, const pm3d_view *views, int n_views, const pm3d_sprite *sprites,
                 const int32_t *sprite_offset, uint8_t *out_rgba, pm3d_rect *out_rects,
                 pm3d_convergence *out_conv, uint32_t flags);
+/* Same frame path with every argument already resident in HBM (device pointers) and nothing
+ * copied or synchronised: the call only enqueues the kernels on the ctx stream.  Per-sprite
+ * rectangles and per-view convergence stay on the device until pm3d_download_results.
+ * n_sprites_total = d_sprite_offset[n_views] (the caller knows it; the host cannot read it). */
+int pm3d_render_resident(pm3d_ctx *ctx, const pm3d_view *d_views, int n_views, const pm3d_sprite *d_sprites,
+                         const int32_t *d_sprite_offset, int n_sprites_total, uint8_t *d_out_rgba);
+/* rects (n_sprites of the last render) and convergence (n_views) of the last render; either may be NULL */
+int pm3d_download_results(pm3d_ctx *ctx, pm3d_rect *out_rects, pm3d_convergence *out_conv);
 /* wall-cast records + z-buffer of one view of the last pm3d_render (parity/debug).
  * columns: [num_levels][w]; zbuf: [w] */
 int pm3d_download_columns(pm3d_ctx *ctx, int view, pm3d_column *columns, double *zbuf);
@@ -200,6 +208,13 @@ int pm3d_memcpy_d2h(pm3d_ctx *ctx, void *dst, const void *src, int64_t bytes);
 int pm3d_timer_start(pm3d_ctx *ctx, int slot);
 int pm3d_timer_stop(pm3d_ctx *ctx, int slot);
 int pm3d_timer_elapsed_ms(pm3d_ctx *ctx, int slot, float *ms); /* syncs on the stop event */
+/* Per-kernel CUDA-event timing of the frame path: after pm3d_ktimer_begin(ctx, max_frames) every
+ * render records an event pair around each of its kernels (0 = column cast, 1 = view setup,
+ * 2 = compose) until max_frames frames were sampled.  pm3d_ktimer_collect syncs, writes the
+ * per-frame durations in ms as out_ms[frame*3 + kernel], returns the number of frames sampled
+ * and stops the sampling. */
+int pm3d_ktimer_begin(pm3d_ctx *ctx, int max_frames);
+int pm3d_ktimer_collect(pm3d_ctx *ctx, float *out_ms, int cap_frames);
 /* kernels launched by this ctx since creation (bench.py "gpu_launches") */
 int64_t pm3d_launch_count(const pm3d_ctx *ctx);
 /* write `bytes` of a scratch buffer (> L2) to flush the L2 between timed iterations */

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(128) k_cast_columns(CastParams p) {
 
 int pm3d_launch_cast(pm3d_ctx *ctx, int n_views) {
     CastParams p;
-    p.views = ctx->views;
+    p.views = ctx->cur_views;
     p.grid = ctx->grid;
     p.wall_lut = ctx->wall_lut;
     p.col_rec = ctx->col_rec;
@@ -157,8 +157,10 @@ int pm3d_launch_cast(pm3d_ctx *ctx, int n_views) {
     p.w = ctx->w; p.h = ctx->h; p.map_w = ctx->map_w; p.map_h = ctx->map_h;
     p.stored_levels = ctx->stored_levels; p.num_levels = ctx->num_levels; p.tex_size = ctx->tex_size;
     dim3 block(128), grid((ctx->w + 127) / 128, ctx->num_levels, n_views);
+    pm3d_kt_mark(ctx, 0, 0);
     if (p.dbg) k_cast_columns<true><<<grid, block, 0, ctx->stream>>>(p);
     else k_cast_columns<false><<<grid, block, 0, ctx->stream>>>(p);
+    pm3d_kt_mark(ctx, 0, 1);
     ctx->launches++;
     PM3D_CUDA(ctx, cudaGetLastError());
     return PM3D_OK;

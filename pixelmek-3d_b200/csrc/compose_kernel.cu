@@ -302,13 +302,13 @@ __global__ void k_checksum(const uint32_t *frames, uint64_t *out, size_t words_p
 
 int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     ComposeParams p;
-    p.views = ctx->views;
+    p.views = ctx->cur_views;
     p.col_rec = ctx->col_rec;
     p.floor_rec = ctx->floor_rec;
     p.zbuf = ctx->zbuf;
     p.row_rec = ctx->row_rec;
     p.draw_rec = ctx->draw_rec;
-    p.sprite_offset = ctx->sprite_offset;
+    p.sprite_offset = ctx->cur_offset;
     p.bin_list = ctx->bin_list;
     p.bin_count = ctx->bin_count;
     p.atlas = reinterpret_cast<const uint32_t *>(ctx->atlas);
@@ -323,7 +323,9 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
         PM3D_CUDA(ctx, cudaFuncSetAttribute(k_compose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     dim3 block(COMPOSE_WARPS * 32), grid(ctx->n_groups, (ctx->h + COMPOSE_ROWS - 1) / COMPOSE_ROWS, n_views);
+    pm3d_kt_mark(ctx, 2, 0);
     k_compose<<<grid, block, smem, ctx->stream>>>(p);
+    pm3d_kt_mark(ctx, 2, 1);
     ctx->launches++;
     PM3D_CUDA(ctx, cudaGetLastError());
     return PM3D_OK;

@@ -98,6 +98,8 @@ void pm3d_destroy(pm3d_ctx *ctx) {
         if (ctx->ev_stop[i]) cudaEventDestroy(ctx->ev_stop[i]);
     }
     if (ctx->stage_ev) cudaEventDestroy(ctx->stage_ev);
+    for (int i = 0; i < ctx->kt_cap * 6; i++) cudaEventDestroy(ctx->kt_ev[i]);
+    delete[] ctx->kt_ev;
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -257,18 +259,93 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
 
 // ------------------------------------------------------------------ frame path
 
-int pm3d_render(pm3d_ctx *ctx, const pm3d_view *views, int n_views, const pm3d_sprite *sprites,
-                const int32_t *sprite_offset, uint8_t *out_rgba, pm3d_rect *out_rects, pm3d_convergence *out_conv,
-                uint32_t flags) {
-    if (!ctx) return PM3D_ERR_ARG;
+// the three kernels of one frame batch; inputs come from ctx->cur_*
+static int render_core(pm3d_ctx *ctx, int n_views, int n_sprites, uint8_t *target) {
+    int rc;
+    if ((rc = pm3d_launch_cast(ctx, n_views))) return rc;
+    if ((rc = pm3d_launch_view_setup(ctx, n_views, n_sprites))) return rc;
+    if ((rc = pm3d_launch_compose(ctx, n_views, target))) return rc;
+    if (ctx->kt_on && ctx->kt_n < ctx->kt_cap) ctx->kt_n++;
+    ctx->last_frame = target;
+    ctx->last_views = n_views;
+    ctx->last_sprites = n_sprites;
+    return PM3D_OK;
+}
+
+static int render_ready(pm3d_ctx *ctx, int n_views) {
     if (!ctx->grid || !ctx->wall_lut || !ctx->atlas || !ctx->floor_tiles || ctx->w < 1)
         return pm3d_fail(ctx, PM3D_ERR_ARG, "grid, wall textures, atlas, floor tiles and view size must be set first");
     if (ctx->floor_w != ctx->map_w || ctx->floor_h != ctx->map_h)
         return pm3d_fail(ctx, PM3D_ERR_ARG, "floor tile grid %dx%d does not match map %dx%d", ctx->floor_w, ctx->floor_h, ctx->map_w, ctx->map_h);
-    if (!views || n_views < 1) return pm3d_fail(ctx, PM3D_ERR_ARG, "no views");
+    if (n_views < 1) return pm3d_fail(ctx, PM3D_ERR_ARG, "no views");
     if (n_views > ctx->max_views) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "%d views > max_views %d", n_views, ctx->max_views);
     if (ctx->sky_tile >= ctx->n_tiles || ctx->floorbox_tile >= ctx->n_tiles)
         return pm3d_fail(ctx, PM3D_ERR_ARG, "sky/floor box tile outside the atlas");
+    return PM3D_OK;
+}
+
+int pm3d_render_resident(pm3d_ctx *ctx, const pm3d_view *d_views, int n_views, const pm3d_sprite *d_sprites,
+                         const int32_t *d_sprite_offset, int n_sprites_total, uint8_t *d_out_rgba) {
+    if (!ctx) return PM3D_ERR_ARG;
+    int rc = render_ready(ctx, n_views);
+    if (rc) return rc;
+    if (!d_views || !d_sprite_offset || !d_out_rgba || n_sprites_total < 0 || (n_sprites_total > 0 && !d_sprites))
+        return pm3d_fail(ctx, PM3D_ERR_ARG, "null device pointer");
+    if (n_sprites_total > ctx->max_sprites) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "%d sprites > max_sprites_total %d", n_sprites_total, ctx->max_sprites);
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->cur_views = d_views; ctx->cur_sprites = d_sprites; ctx->cur_offset = d_sprite_offset;
+    return render_core(ctx, n_views, n_sprites_total, d_out_rgba);
+}
+
+int pm3d_download_results(pm3d_ctx *ctx, pm3d_rect *out_rects, pm3d_convergence *out_conv) {
+    if (!ctx) return PM3D_ERR_ARG;
+    if (ctx->last_views < 1) return pm3d_fail(ctx, PM3D_ERR_ARG, "nothing rendered");
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (out_rects && ctx->last_sprites)
+        PM3D_CUDA(ctx, cudaMemcpyAsync(out_rects, ctx->rects, (size_t)ctx->last_sprites * sizeof(pm3d_rect), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_conv)
+        PM3D_CUDA(ctx, cudaMemcpyAsync(out_conv, ctx->conv, (size_t)ctx->last_views * sizeof(pm3d_convergence), cudaMemcpyDeviceToHost, ctx->stream));
+    PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PM3D_OK;
+}
+
+int pm3d_ktimer_begin(pm3d_ctx *ctx, int max_frames) {
+    if (!ctx || max_frames < 1 || max_frames > (1 << 20)) return PM3D_ERR_ARG;
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->kt_cap < max_frames) {
+        cudaEvent_t *ev = new cudaEvent_t[(size_t)max_frames * 6];
+        for (int i = 0; i < ctx->kt_cap * 6; i++) ev[i] = ctx->kt_ev[i];
+        for (int i = ctx->kt_cap * 6; i < max_frames * 6; i++) PM3D_CUDA(ctx, cudaEventCreate(&ev[i]));
+        delete[] ctx->kt_ev;
+        ctx->kt_ev = ev;
+        ctx->kt_cap = max_frames;
+    }
+    ctx->kt_n = 0;
+    ctx->kt_on = 1;
+    return PM3D_OK;
+}
+
+int pm3d_ktimer_collect(pm3d_ctx *ctx, float *out_ms, int cap_frames) {
+    if (!ctx || !out_ms) return PM3D_ERR_ARG;
+    ctx->kt_on = 0;
+    PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int n = ctx->kt_n < cap_frames ? ctx->kt_n : cap_frames;
+    for (int f = 0; f < n; f++)
+        for (int k = 0; k < 3; k++)
+            PM3D_CUDA(ctx, cudaEventElapsedTime(&out_ms[f * 3 + k], ctx->kt_ev[(f * 3 + k) * 2], ctx->kt_ev[(f * 3 + k) * 2 + 1]));
+    ctx->kt_n = 0;
+    return n;
+}
+
+int pm3d_render(pm3d_ctx *ctx, const pm3d_view *views, int n_views, const pm3d_sprite *sprites,
+                const int32_t *sprite_offset, uint8_t *out_rgba, pm3d_rect *out_rects, pm3d_convergence *out_conv,
+                uint32_t flags) {
+    if (!ctx) return PM3D_ERR_ARG;
+    if (!views) return pm3d_fail(ctx, PM3D_ERR_ARG, "no views");
+    {
+        int rdy = render_ready(ctx, n_views);
+        if (rdy) return rdy;
+    }
     std::vector<int32_t> zero_off;
     if (!sprite_offset) {
         zero_off.assign(n_views + 1, 0);
@@ -304,11 +381,8 @@ int pm3d_render(pm3d_ctx *ctx, const pm3d_view *views, int n_views, const pm3d_s
     PM3D_CUDA(ctx, cudaEventRecord(ctx->stage_ev, ctx->stream));
 
     uint8_t *target = (out_rgba && (flags & PM3D_OUT_DEVICE)) ? out_rgba : ctx->frame;
-    if ((rc = pm3d_launch_cast(ctx, n_views))) return rc;
-    if ((rc = pm3d_launch_view_setup(ctx, n_views, n_sprites))) return rc;
-    if ((rc = pm3d_launch_compose(ctx, n_views, target))) return rc;
-    ctx->last_frame = target;
-    ctx->last_views = n_views;
+    ctx->cur_views = ctx->views; ctx->cur_sprites = ctx->sprites; ctx->cur_offset = ctx->sprite_offset;
+    if ((rc = render_core(ctx, n_views, n_sprites, target))) return rc;
 
     const size_t fb = (size_t)n_views * ctx->w * ctx->h * 4;
     if (out_rgba && !(flags & PM3D_OUT_DEVICE))

@@ -106,6 +106,16 @@ struct pm3d_ctx {
     uint8_t *last_frame = nullptr;   // where the last render wrote (frame or caller memory)
     uint64_t *checksums = nullptr;   // [max_views]
 
+    // inputs the kernels read this call (ctx-owned copies, or caller device memory)
+    const pm3d_view *cur_views = nullptr;
+    const pm3d_sprite *cur_sprites = nullptr;
+    const int32_t *cur_offset = nullptr;
+    int last_sprites = 0;
+
+    // per-kernel event timing (pm3d_ktimer_*)
+    cudaEvent_t *kt_ev = nullptr;  // [kt_cap][3][2]
+    int kt_cap = 0, kt_n = 0, kt_on = 0;
+
     // pinned staging for host-side arguments
     void *stage = nullptr;
     size_t stage_bytes = 0;
@@ -128,6 +138,10 @@ struct pm3d_ctx {
 };
 
 int pm3d_fail(pm3d_ctx *ctx, int code, const char *fmt, ...);
+// event pair around kernel `k` (0 cast, 1 view setup, 2 compose) of the frame being sampled
+inline void pm3d_kt_mark(pm3d_ctx *ctx, int k, int end) {
+    if (ctx->kt_on && ctx->kt_n < ctx->kt_cap) cudaEventRecord(ctx->kt_ev[(ctx->kt_n * 3 + k) * 2 + end], ctx->stream);
+}
 #define PM3D_CUDA(ctx, call)                                                                         \
     do {                                                                                             \
         cudaError_t e__ = (call);                                                                    \

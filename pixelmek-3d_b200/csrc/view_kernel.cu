@@ -251,11 +251,11 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view_setup(ViewParams p) {
 int pm3d_launch_view_setup(pm3d_ctx *ctx, int n_views, int n_sprites_total) {
     (void)n_sprites_total;
     ViewParams p;
-    p.views = ctx->views;
+    p.views = ctx->cur_views;
     p.zbuf = ctx->zbuf;
     p.row_rec = ctx->row_rec;
-    p.sprites = ctx->sprites;
-    p.sprite_offset = ctx->sprite_offset;
+    p.sprites = ctx->cur_sprites;
+    p.sprite_offset = ctx->cur_offset;
     p.sheets = ctx->sheet_info;
     p.draw_rec = ctx->draw_rec;
     p.n_draw = ctx->n_draw;
@@ -265,7 +265,9 @@ int pm3d_launch_view_setup(pm3d_ctx *ctx, int n_views, int n_sprites_total) {
     p.conv = ctx->conv;
     p.w = ctx->w; p.h = ctx->h; p.tex_size = ctx->tex_size; p.n_sheets = ctx->n_sheets; p.n_groups = ctx->n_groups;
     p.sky_tile = ctx->sky_tile; p.floorbox_tile = ctx->floorbox_tile;
+    pm3d_kt_mark(ctx, 1, 0);
     k_view_setup<<<n_views, VIEW_THREADS, 0, ctx->stream>>>(p);
+    pm3d_kt_mark(ctx, 1, 1);
     ctx->launches++;
     PM3D_CUDA(ctx, cudaGetLastError());
     return PM3D_OK;

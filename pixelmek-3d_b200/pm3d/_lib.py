@@ -84,6 +84,8 @@ SYMBOLS = {
     "pm3d_set_view": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int]),
     "pm3d_set_option": (C.c_int, [_P, C.c_int, C.c_int]),
     "pm3d_render": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_uint32]),
+    "pm3d_render_resident": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P]),
+    "pm3d_download_results": (C.c_int, [_P, _P, _P]),
     "pm3d_download_columns": (C.c_int, [_P, C.c_int, _P, _P]),
     "pm3d_frame_checksums": (C.c_int, [_P, C.c_int, _P, C.c_uint32]),
     "pm3d_last_frame_device": (_P, [_P]),
@@ -100,6 +102,8 @@ SYMBOLS = {
     "pm3d_timer_start": (C.c_int, [_P, C.c_int]),
     "pm3d_timer_stop": (C.c_int, [_P, C.c_int]),
     "pm3d_timer_elapsed_ms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float)]),
+    "pm3d_ktimer_begin": (C.c_int, [_P, C.c_int]),
+    "pm3d_ktimer_collect": (C.c_int, [_P, _P, C.c_int]),
     "pm3d_launch_count": (C.c_int64, [_P]),
     "pm3d_flush_l2": (C.c_int, [_P]),
 }

@@ -82,8 +82,10 @@ class Context:
 
     # ------------------------------------------------------------------ frame path
     def render(self, views: np.ndarray, sprites: np.ndarray | None = None, sprite_offset: np.ndarray | None = None,
-               want_frame: bool = True, out_device_ptr: int | None = None, no_sync: bool = False):
-        """Camera.Update + Draw for len(views) views.  Returns dict(rgba, rects, conv)."""
+               want_frame: bool = True, out_device_ptr: int | None = None, no_sync: bool = False,
+               out: np.ndarray | None = None):
+        """Camera.Update + Draw for len(views) views.  Returns dict(rgba, rects, conv).
+        `out` (optional) is a host buffer for the frames, e.g. pinned memory from host_alloc."""
         views = np.ascontiguousarray(views, dtype=VIEW_DTYPE).reshape(-1)
         nv = len(views)
         if sprites is None:
@@ -104,7 +106,9 @@ class Context:
             flags |= _lib.PM3D_OUT_DEVICE
             out_p = C.c_void_p(out_device_ptr)
         elif want_frame:
-            rgba = np.empty((nv, self.h_px, self.w, 4), dtype=np.uint8)
+            rgba = out if out is not None else np.empty((nv, self.h_px, self.w, 4), dtype=np.uint8)
+            if rgba.nbytes < nv * self.h_px * self.w * 4:
+                raise Pm3dError("out buffer too small")
             out_p = ptr(rgba)
         if no_sync:
             flags |= _lib.PM3D_NO_SYNC
@@ -115,6 +119,32 @@ class Context:
             "pm3d_render",
         )
         return {"rgba": rgba, "rects": rects[:ns], "conv": conv}
+
+    def render_resident(self, d_views: int, n_views: int, d_sprites: int, d_offsets: int, n_sprites_total: int,
+                        d_out: int):
+        """Enqueue one frame batch whose inputs and output already live in HBM (device pointers)."""
+        self._check(
+            self.lib.pm3d_render_resident(self.h, C.c_void_p(d_views), n_views, C.c_void_p(d_sprites) if d_sprites else None,
+                                          C.c_void_p(d_offsets), n_sprites_total, C.c_void_p(d_out)),
+            "pm3d_render_resident",
+        )
+
+    def download_results(self, n_sprites: int, n_views: int):
+        rects = np.zeros((max(n_sprites, 1), 4), dtype=np.int32)
+        conv = np.zeros(n_views, dtype=CONV_DTYPE)
+        self._check(self.lib.pm3d_download_results(self.h, ptr(rects), ptr(conv)), "pm3d_download_results")
+        return rects[:n_sprites], conv
+
+    def ktimer_begin(self, max_frames: int):
+        self._check(self.lib.pm3d_ktimer_begin(self.h, int(max_frames)), "pm3d_ktimer_begin")
+
+    def ktimer_collect(self, cap_frames: int) -> np.ndarray:
+        """[frames][3] ms: column cast, view setup, compose."""
+        out = np.zeros((cap_frames, 3), dtype=np.float32)
+        n = self.lib.pm3d_ktimer_collect(self.h, ptr(out), int(cap_frames))
+        if n < 0:
+            self._check(n, "pm3d_ktimer_collect")
+        return out[:n]
 
     def download_columns(self, view: int = 0):
         s = self.scene

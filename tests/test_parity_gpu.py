@@ -1,0 +1,305 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle on the
+same seeded inputs.
+
+Bars (BASELINE.json north_star): DDA hit cells, wall sides and texture column indices
+bit-exact; distances bit-exact (binary64, no FMA contraction on either side); final RGBA
+pixels within <= 1 LSB on <= 0.1 % of pixels.  The integer blit model makes the pixels exact
+as well, so these tests assert ZERO differing pixels and only fall back to the stated
+tolerance in one place (test_frame_tolerance_statement) to document it.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import pm3d
+from conftest import assert_columns_equal, orc_camera
+from oracle import oracle as O
+from pm3d import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+def render_both(ctx, scene, w, h, views, sprites, offsets=None, keep_columns=True):
+    ctx.upload_scene(scene)
+    ctx.set_option(pm3d._lib.OPT_KEEP_COLUMNS, 1 if keep_columns else 0)
+    ctx.set_view(w, h, len(views), max(len(sprites), 1))
+    if offsets is None:
+        offsets = np.array([0, len(sprites)], dtype=np.int32)
+    got = ctx.render(views, sprites, offsets)
+    osc = O.Scene(scene)
+    want = []
+    for i, v in enumerate(views):
+        want.append(O.render(osc, orc_camera(v, w, h), sprites[offsets[i]:offsets[i + 1]].astype(O.SPRITE_DTYPE), threads=4))
+    return got, want
+
+
+def assert_frame_equal(got_rgba, want_rgba, what=""):
+    bad = (got_rgba != want_rgba).any(axis=-1)
+    n = int(bad.sum())
+    if n:
+        ys, xs = np.nonzero(bad)
+        first = [(int(x), int(y), got_rgba[y, x].tolist(), want_rgba[y, x].tolist()) for x, y in list(zip(xs, ys))[:5]]
+        raise AssertionError(f"{what}: {n} of {bad.size} pixels differ, first (x, y, gpu, oracle): {first}")
+
+
+def check_all(ctx, got, want, offsets, n_sprites):
+    for i, ref in enumerate(want):
+        cols, zbuf = ctx.download_columns(i)
+        assert_columns_equal(cols, ref["columns"])
+        assert np.array_equal(zbuf.view(np.uint64), ref["zbuf"].view(np.uint64)), "z-buffer bits"
+        assert_frame_equal(got["rgba"][i], ref["rgba"], f"view {i}")
+        lo, hi = int(offsets[i]), int(offsets[i + 1])
+        assert np.array_equal(got["rects"][lo:hi], ref["rects"]), f"view {i}: sprite screen rects"
+        c = got["conv"][i]
+        assert int(c["sprite"]) == ref["convergence"]["sprite"]
+        assert float(c["distance"]) == ref["convergence"]["distance"] or (math.isnan(float(c["distance"])) and math.isnan(ref["convergence"]["distance"]))
+        assert (float(c["point_x"]), float(c["point_y"])) == ref["convergence"]["point"] or math.isnan(float(c["point_x"]))
+
+
+# --------------------------------------------------------------------------- the five configs (reduced where the oracle would be slow)
+
+
+def test_c1_bundled_map_640x360(gpu_ctx):
+    c = W.config_c1()
+    off = np.array([0, len(c["sprites"])], dtype=np.int32)
+    got, want = render_both(gpu_ctx, c["scene"], 640, 360, c["views"], c["sprites"], off)
+    check_all(gpu_ctx, got, want, off, len(c["sprites"]))
+
+
+def test_c2_1080p_200_sprites(gpu_ctx):
+    c = W.config_c2(n_poses=3)
+    got, want = render_both(gpu_ctx, c["scene"], 1920, 1080, c["views"], c["sprites"], c["offsets"])
+    check_all(gpu_ctx, got, want, c["offsets"], len(c["sprites"]))
+
+
+@pytest.mark.parametrize("levels,pitch", [(3, 0.0), (8, math.pi / 4), (8, -math.pi / 8), (3, 0.2)])
+def test_c3_multilevel_infinite_distance(gpu_ctx, levels, pitch):
+    # the C3 scene at 960x540 (the 4K frame is covered by the checksum property test below)
+    c = W.config_c3(levels=levels, w=960, h=540, pitch=pitch)
+    off = np.array([0, 0], dtype=np.int32)
+    got, want = render_both(gpu_ctx, c["scene"], 960, 540, c["views"], c["sprites"], off)
+    check_all(gpu_ctx, got, want, off, 0)
+
+
+def test_c4_batched_views_320x200(gpu_ctx):
+    c = W.config_c4(n_views=48)
+    got, want = render_both(gpu_ctx, c["scene"], 320, 200, c["views"], c["sprites"], c["offsets"])
+    check_all(gpu_ctx, got, want, c["offsets"], len(c["sprites"]))
+
+
+# --------------------------------------------------------------------------- edge cases
+
+
+def edge_scene():
+    grid = W.synthetic_levels(24, 17, 3, 0.18, 77)
+    return W.scene_from_grid(grid, 4)  # one raycast level more than stored: top level repeats
+
+
+EDGE_POSES = [
+    (5.5, 5.5, 0.5, 0.0, 0.0),                 # ray direction exactly +x: deltaDistY = +Inf
+    (5.5, 5.5, 0.5, math.pi / 2, 0.0),         # exactly +y (cos = 6e-17)
+    (6.0, 5.0, 0.5, 0.3, 0.0),                 # standing exactly on a cell corner
+    (6.0, 5.5, 0.5, math.pi, 0.0),             # on a vertical cell border, looking along -x
+    (5.5, 5.5, 0.05, 1.1, -math.pi / 8),       # low camera, looking down
+    (5.5, 5.5, 2.9, 2.2, math.pi / 4),         # high camera (above level 2), max pitch up
+    (0.5, 0.5, 0.5, 0.7, 0.0),                 # inside the boundary wall cell
+    (-3.25, 8.5, 0.5, 0.0, 0.0),               # outside the map: first step leaves the grid (hit = 2)
+    (30.0, 30.0, 0.5, 4.0, 0.0),               # far outside, looking away
+    (12.5, 8.5, 0.5, 5.5, 0.1),
+]
+
+
+@pytest.mark.parametrize("rd", [-1.0, 6.0])
+def test_edge_poses(gpu_ctx, rd):
+    scene = edge_scene()
+    w, h = 200, 120
+    rng = W.SplitMix64(5)
+    u = rng.uniform(60 * 4).reshape(60, 4)
+    xyzs = np.stack([1 + 22 * u[:, 0], 1 + 15 * u[:, 1], 2.0 * u[:, 2] * (u[:, 3] > 0.5), 0.2 + u[:, 3]], axis=1)
+    sheet = (u[:, 2] * 4).astype(np.int32)
+    anchor = (u[:, 1] * 3).astype(np.uint8)
+    spr = W.sprite_records(xyzs, sheet, anchor, scene.sheets, illumination=25.0)
+    spr["focusable"][::3] = 0
+    views = W.make_views(scene, w, h, EDGE_POSES, fov_deg=70.0, render_distance=rd)
+    n = len(views)
+    offsets = (np.arange(n + 1) * len(spr)).astype(np.int32)
+    sprites = np.concatenate([spr] * n)
+    got, want = render_both(gpu_ctx, scene, w, h, views, sprites, offsets)
+    check_all(gpu_ctx, got, want, offsets, len(sprites))
+
+
+def test_zoom_fov_depth_2(gpu_ctx):
+    scene = edge_scene()
+    views = W.make_views(scene, 256, 144, [(5.5, 5.5, 0.5, 0.4, 0.05)], fov_deg=35.0, fov_depth=2.0, render_distance=50.0)
+    off = np.array([0, 0], dtype=np.int32)
+    got, want = render_both(gpu_ctx, scene, 256, 144, views, np.zeros(0, pm3d._lib.SPRITE_DTYPE), off)
+    check_all(gpu_ctx, got, want, off, 0)
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (3, 2), (63, 31), (65, 33), (130, 9), (322, 5)])
+def test_ragged_view_sizes(gpu_ctx, w, h):
+    """Widths that are not multiples of 4 / 64 and tiny frames (scalar-store and edge-group paths)."""
+    scene = edge_scene()
+    views = W.make_views(scene, w, h, [(5.5, 5.5, 0.5, 0.9, 0.0)])
+    xyzs = np.array([[8.5, 7.5, 0.0, 0.8], [7.0, 6.2, 0.3, 0.5]])
+    spr = W.sprite_records(xyzs, np.array([0, 2], np.int32), np.array([0, 1], np.uint8), scene.sheets)
+    off = np.array([0, 2], dtype=np.int32)
+    got, want = render_both(gpu_ctx, scene, w, h, views, spr, off)
+    check_all(gpu_ctx, got, want, off, 2)
+
+
+def test_no_sprites_no_floor_no_boxes(gpu_ctx):
+    """FloorTextureAt nil (floor texturing off, texture.go:120-122) and no sky / floor box."""
+    scene = edge_scene()
+    scene.floor_tiles = np.full_like(scene.floor_tiles, -1)
+    scene.sky_tile = scene.floorbox_tile = -1
+    views = W.make_views(scene, 160, 100, [(5.5, 5.5, 0.5, 0.9, 0.0)])
+    off = np.array([0, 0], dtype=np.int32)
+    got, want = render_both(gpu_ctx, scene, 160, 100, views, np.zeros(0, pm3d._lib.SPRITE_DTYPE), off)
+    check_all(gpu_ctx, got, want, off, 0)
+    assert (got["rgba"][0][..., 3] == 0).any()  # untouched pixels stay transparent
+
+
+def test_many_overlapping_sprites_and_duplicates(gpu_ctx):
+    """> 256 sprites in one band (band-list overflow path), exact duplicates (tie order), sprites behind
+    the camera, zero scale, bad sheet ids and rects hanging off the sheet."""
+    scene = edge_scene()
+    w, h = 192, 108
+    rng = W.SplitMix64(9)
+    n = 400
+    u = rng.uniform(n * 3).reshape(n, 3)
+    xyzs = np.stack([7.0 + 3.0 * u[:, 0], 5.0 + 2.0 * u[:, 1], np.zeros(n), 0.3 + 0.5 * u[:, 2]], axis=1)
+    xyzs[10:20] = xyzs[10]          # ten sprites at the same spot
+    xyzs[20, :2] = (2.0, 5.5)       # behind the camera
+    spr = W.sprite_records(xyzs, (u[:, 2] * 4).astype(np.int32), np.zeros(n, np.uint8), scene.sheets)
+    spr["scale"][21] = 0.0
+    spr["sheet"][22] = 99
+    spr["sheet"][23] = -1
+    spr["rx0"][24], spr["rx1"][24] = -20, 60   # rect partly outside the sheet
+    spr["ry0"][25], spr["ry1"][25] = 150, 400
+    spr["rx0"][26], spr["rx1"][26] = 50, 50    # empty rect
+    views = W.make_views(scene, w, h, [(5.5, 5.5, 0.5, 0.0, 0.0)], render_distance=-1.0)
+    off = np.array([0, n], dtype=np.int32)
+    got, want = render_both(gpu_ctx, scene, w, h, views, spr, off)
+    check_all(gpu_ctx, got, want, off, n)
+
+
+def test_painter_and_front_to_back_paths_agree(gpu_ctx):
+    """PM3D_OPT_FORCE_PAINTER runs the literal painter's loop on every pixel; the default
+    front-to-back shortcut must give identical bytes (translucent boundary tile + sprite rims)."""
+    c = W.config_c2(w=640, h=360, n_poses=2)
+    gpu_ctx.upload_scene(c["scene"])
+    gpu_ctx.set_view(640, 360, 2, len(c["sprites"]))
+    fast = gpu_ctx.render(c["views"], c["sprites"], c["offsets"])["rgba"].copy()
+    gpu_ctx.set_option(pm3d._lib.OPT_FORCE_PAINTER, 1)
+    try:
+        slow = gpu_ctx.render(c["views"], c["sprites"], c["offsets"])["rgba"].copy()
+    finally:
+        gpu_ctx.set_option(pm3d._lib.OPT_FORCE_PAINTER, 0)
+    assert np.array_equal(fast, slow)
+    assert ((fast[..., 3] > 0) & (fast[..., 3] < 255)).sum() == 0  # opaque sky/floor behind everything
+
+
+def test_frame_tolerance_statement(gpu_ctx):
+    """The stated tolerance: <= 1 LSB on <= 0.1 % of pixels.  (Measured: 0 pixels differ.)"""
+    c = W.config_c2(w=960, h=540, n_poses=1)
+    got, want = render_both(gpu_ctx, c["scene"], 960, 540, c["views"], c["sprites"], c["offsets"])
+    diff = np.abs(got["rgba"][0].astype(np.int32) - want[0]["rgba"].astype(np.int32))
+    assert diff.max() <= 1
+    assert (diff.max(axis=-1) > 0).mean() <= 0.001
+
+
+# --------------------------------------------------------------------------- API behaviour
+
+
+def test_batch_equals_single_and_resident_equals_host(gpu_ctx):
+    c = W.config_c4(n_views=12)
+    ctx = gpu_ctx
+    ctx.upload_scene(c["scene"])
+    ctx.set_view(320, 200, 12, len(c["sprites"]))
+    batch = ctx.render(c["views"], c["sprites"], c["offsets"])
+    sums = ctx.frame_checksums(12)
+    off = c["offsets"]
+    for i in (0, 5, 11):
+        one = ctx.render(c["views"][i:i + 1], c["sprites"][off[i]:off[i + 1]])
+        assert np.array_equal(one["rgba"][0], batch["rgba"][i])
+        assert ctx.frame_checksums(1)[0] == sums[i]
+    # device-resident entry point
+    views, sprites = c["views"], c["sprites"]
+    dv, ds, do = ctx.device_alloc(views.nbytes), ctx.device_alloc(sprites.nbytes), ctx.device_alloc(off.nbytes)
+    dout = ctx.device_alloc(12 * 320 * 200 * 4)
+    ctx.h2d(dv, views); ctx.h2d(ds, sprites); ctx.h2d(do, off)
+    ctx.render_resident(dv, 12, ds, do, len(sprites), dout)
+    back = np.empty((12, 200, 320, 4), dtype=np.uint8)
+    ctx.d2h(back, dout)
+    assert np.array_equal(back, batch["rgba"])
+    rects, conv = ctx.download_results(len(sprites), 12)
+    assert np.array_equal(rects, batch["rects"]) and np.array_equal(conv["sprite"], batch["conv"]["sprite"])
+    assert np.array_equal(ctx.frame_checksums(12), sums)
+    for p in (dv, ds, do, dout):
+        ctx.device_free(p)
+
+
+def test_full_size_4k_frame_properties(gpu_ctx):
+    """C3 at its full 3840x2160: the oracle renders this frame too (a few seconds on 4 threads)."""
+    c = W.config_c3(levels=8, pitch=0.15)
+    off = np.array([0, 0], dtype=np.int32)
+    got, want = render_both(gpu_ctx, c["scene"], 3840, 2160, c["views"], c["sprites"], off, keep_columns=True)
+    check_all(gpu_ctx, got, want, off, 0)
+    assert (got["rgba"][0][..., 3] == 255).all()
+
+
+def test_errors_are_reported_not_swallowed(gpu_ctx):
+    ctx = pm3d.Context(0)
+    v = np.zeros(1, dtype=pm3d._lib.VIEW_DTYPE)
+    with pytest.raises(pm3d.Pm3dError, match="must be set first|must precede"):
+        ctx.set_view(64, 64, 1, 0)
+    scene = edge_scene()
+    ctx.upload_scene(scene)
+    ctx.set_view(64, 64, 2, 10)
+    with pytest.raises(pm3d.Pm3dError, match="max_views"):
+        ctx.render(np.zeros(3, dtype=pm3d._lib.VIEW_DTYPE), None, np.zeros(4, np.int32))
+    with pytest.raises(pm3d.Pm3dError, match="max_sprites_total"):
+        ctx.render(v, np.zeros(11, dtype=pm3d._lib.SPRITE_DTYPE))
+    with pytest.raises(pm3d.Pm3dError, match="upload_segments"):
+        ctx.los_batch(np.zeros((1, 4)))
+    ctx.close()
+
+
+def test_camera_mirror_drives_the_path(gpu_ctx):
+    """The raycaster.Camera mirror: NewCamera + setters + Update/GetConvergenceSprite/Draw, with the
+    map / texture handler / sprites supplied through the callback interfaces."""
+    from pm3d import camera as cam
+
+    g = W.load_golden("debug_land")
+    atlas = W.standard_atlas()
+    level_map = cam.LevelMap(g["levels"], int(g["num_raycast_levels"]))
+    textures = {int(i): (atlas[int(i) % 4], None, None) for i in g["tex_index"] if int(i) > 0}
+    tex = cam.TextureHandler(level_map, textures, atlas[7], g["floor_grid"], [atlas[7], atlas[8], atlas[8], atlas[8]])
+    sheets = W.default_sheets()
+    c = cam.Camera(400, 240, 256, level_map, tex, ctx=gpu_ctx, sheets=sheets)
+    c.SetRenderDistance(100.0)
+    c.SetAlwaysSetSpriteScreenRect(True)
+    c.SetFloorTexture(atlas[10]); c.SetSkyTexture(atlas[9])
+    c.SetLightFalloff(float(g["light_falloff"])); c.SetGlobalIllumination(float(g["light_illumination"]))
+    c.SetLightRGB(tuple(g["min_light"]), tuple(g["max_light"]))
+    c.SetPosition((50.5, 50.5)); c.SetPositionZ(0.5); c.SetHeadingAngle(math.pi / 4); c.SetPitchAngle(0.0)
+    c.SetFovAngle(70.0, 1.0)
+    sprites = [cam.Sprite(x, y, z, s, cam.ANCHOR_BOTTOM, sheets[0]) for x, y, z, s in g["sprite_xyzs"][:60]]
+    c.Update(sprites)
+    frame = c.Draw()
+    assert frame.shape == (240, 400, 4)
+    # same numbers through the oracle
+    scene = cam.flatten_scene(level_map, tex, 256, atlas[9], atlas[10], sheets)
+    snap = cam.snapshot_sprites(sprites, {id(s): i for i, s in enumerate(sheets)})
+    ref = O.render(O.Scene(scene), orc_camera(c.state.view_record()[0], 400, 240), snap.astype(O.SPRITE_DTYPE))
+    assert_frame_equal(frame, ref["rgba"], "camera mirror")
+    conv = c.GetConvergenceSprite()
+    assert (conv is None and ref["convergence"]["sprite"] < 0) or conv is sprites[ref["convergence"]["sprite"]]
+    for s, rc in zip(sprites, ref["rects"]):
+        assert s.screen_rect == (None if rc[0] > rc[2] else tuple(int(v) for v in rc))
+    assert c.FovDepth() == 1.0 and c.FovRadians() == pytest.approx(math.radians(70))
+    c.SetViewSize(200, 120)
+    c.Update(sprites)
+    assert c.Draw().shape == (120, 200, 4)

@@ -209,8 +209,8 @@ int pm3d_timer_start(pm3d_ctx *ctx, int slot);
 int pm3d_timer_stop(pm3d_ctx *ctx, int slot);
 int pm3d_timer_elapsed_ms(pm3d_ctx *ctx, int slot, float *ms); /* syncs on the stop event */
 /* Per-kernel CUDA-event timing of the frame path: after pm3d_ktimer_begin(ctx, max_frames) every
- * render records an event pair around each of its kernels (0 = column cast, 1 = view setup,
- * 2 = compose) until max_frames frames were sampled.  pm3d_ktimer_collect syncs, writes the
+ * render records an event pair around each of its kernels (0 = front: column cast + view
+ * setup, 1 = unused (reads 0), 2 = compose) until max_frames frames were sampled.  pm3d_ktimer_collect syncs, writes the
  * per-frame durations in ms as out_ms[frame*3 + kernel], returns the number of frames sampled
  * and stops the sampling. */
 int pm3d_ktimer_begin(pm3d_ctx *ctx, int max_frames);

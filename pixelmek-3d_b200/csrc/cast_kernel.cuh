@@ -1,4 +1,4 @@
-// cast_kernel.cu — K2 wall cast: one thread per (view, level, screen column) ray.
+// cast_kernel.cuh — K2 wall cast: one thread per (view, level, screen column) ray.
 //
 // Replaces the per-column DDA inside raycaster.Camera.Update (call site
 // game/scene_game.go:161) together with the Map.Level / TextureHandler.TextureAt callbacks
@@ -7,25 +7,40 @@
 //
 // Arithmetic: IEEE binary64, no FMA contraction (-fmad=false), Go integer semantics via
 // go_int/wadd/...; the visited cell sequence is therefore identical to the CPU reference's.
+//
+// Empty-space skipping without changing that sequence: `dist` holds, per cell, the Chebyshev
+// distance D to the nearest wall cell or map edge.  Every DDA step moves one cell along one
+// axis, so the D-1 steps after a cell with distance D cannot reach a wall or leave the grid:
+// they are executed as pure register arithmetic (the same sideDist additions, in the same
+// order) with no memory access and no bounds test, and only every D-th step probes the grid.
+// On the bundled 500x500 map the upper levels are almost empty, which turns ~700 dependent
+// L2 loads per ray into 3-4.
+#pragma once
 #include "pm3d_internal.cuh"
 
 struct CastParams {
     const pm3d_view *views;
     const uint16_t *grid;
+    const uint8_t *dist;  // per stored level: Chebyshev distance to the nearest wall cell or map edge (0 = wall)
     const int16_t *wall_lut;
-    ColRec *col_rec;
-    FloorRec *floor_rec;
+    int2 *col_span;
+    uint2 *col_tt;
+    ulonglong2 *col_ps;
+    double *flo_xw, *flo_yw, *flo_dw;
+    int32_t *flo_fs;
+    int4 *agg;
     double *zbuf;
     pm3d_column *dbg;  // may be null
-    int w, h, map_w, map_h, stored_levels, num_levels, tex_size;
+    int w, h, map_w, map_h, stored_levels, num_levels, tex_size, n_groups;
 };
 
+// Called by all 64 threads of a (view, level, group) pair of warps; `x` may be >= w in the last group
+// (those lanes cast column w-1 again and store nothing) so that the warp-wide aggregate stays converged.
 template <bool DEBUG>
-__global__ void __launch_bounds__(128) k_cast_columns(CastParams p) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int level = blockIdx.y;
-    const int view = blockIdx.z;
-    if (x >= p.w) return;
+__device__ __forceinline__ void cast_ray(const CastParams &p, const int view, const int level, const int group,
+                                         const int x_in) {
+    const bool live = x_in < p.w;
+    const int x = live ? x_in : p.w - 1;
     const pm3d_view c = p.views[view];
     const int sl = level < p.stored_levels ? level : p.stored_levels - 1;  // Map.Level()
     const uint16_t *__restrict__ grid = p.grid + (size_t)sl * p.map_w * p.map_h;
@@ -55,11 +70,24 @@ __global__ void __launch_bounds__(128) k_cast_columns(CastParams p) {
         mapY = mapY < 0 ? 0 : (mapY > p.map_h - 1 ? p.map_h - 1 : mapY);
     }
     int mx = (int)mapX, my = (int)mapY;
+    const uint8_t *__restrict__ dist = p.dist + (size_t)sl * p.map_w * p.map_h;
+    // free-run length at the start cell; the reference never tests the start cell itself, so a
+    // camera inside a wall (D = 0) or outside the grid simply probes on its first step
+    int D = 1;
+    if (hit == 0 && (unsigned)mx < (unsigned)p.map_w && (unsigned)my < (unsigned)p.map_h) {
+        D = __ldg(dist + mx * p.map_h + my);
+        if (D == 0) D = 1;
+    }
     while (hit == 0) {
+        for (int k = D - 1; k > 0; --k) {  // blind steps: cannot hit, cannot leave
+            if (sideDistX < sideDistY) { sideDistX += deltaDistX; mx += stepX; side = 0; }
+            else                       { sideDistY += deltaDistY; my += stepY; side = 1; }
+        }
         if (sideDistX < sideDistY) { sideDistX += deltaDistX; mx += stepX; side = 0; }
         else                       { sideDistY += deltaDistY; my += stepY; side = 1; }
         if ((unsigned)mx < (unsigned)p.map_w && (unsigned)my < (unsigned)p.map_h) {
-            if (__ldg(grid + mx * p.map_h + my) > 0) hit = 1;
+            D = __ldg(dist + mx * p.map_h + my);
+            if (D == 0) hit = 1;
         } else {
             hit = 2;
             mx = mx < 0 ? 0 : (mx > p.map_w - 1 ? p.map_w - 1 : mx);
@@ -98,21 +126,28 @@ __global__ void __launch_bounds__(128) k_cast_columns(CastParams p) {
 
     const uint32_t tint = light_tint(c, perpWallDist, side == 0 ? 255 - 12 : 255, 0.0, false);
 
-    // ---- compose-side record
-    ColRec r;
-    r.ya = 0; r.yb = 0; r.tile_texx = 0; r.tint = tint; r.pos0 = 0; r.step2 = 0;
+    // ---- compose-side records
+    int ya = 0, yb = 0;
+    uint32_t tile_texx = 0;
+    uint64_t pos0 = 0, step2 = 0;
     if (tile >= 0 && lineHeight > 0 && drawEnd > drawStart) {
         const uint64_t step = span_step(p.tex_size, lineHeight);
-        r.ya = (int32_t)(drawStart < 0 ? 0 : (drawStart > h ? h : drawStart));
-        r.yb = (int32_t)(drawEnd > h ? h : (drawEnd < 0 ? 0 : drawEnd));
-        r.tile_texx = ((uint32_t)tile << 16) | (uint32_t)texX;
-        r.step2 = step * 2ull;
-        r.pos0 = (1ull - 2ull * (uint64_t)drawStart) * step;  // (2*(0 - drawStart) + 1) * step, mod 2^64
+        ya = (int32_t)(drawStart < 0 ? 0 : (drawStart > h ? h : drawStart));
+        yb = (int32_t)(drawEnd > h ? h : (drawEnd < 0 ? 0 : drawEnd));
+        tile_texx = ((uint32_t)tile << 16) | (uint32_t)texX;
+        step2 = step * 2ull;
+        pos0 = (1ull - 2ull * (uint64_t)drawStart) * step;  // (2*(0 - drawStart) + 1) * step, mod 2^64
     }
     const size_t ci = ((size_t)view * p.num_levels + level) * p.w + x;
-    p.col_rec[ci] = r;
+    if (live) {
+        p.col_span[ci] = make_int2(ya, yb);
+        p.col_tt[ci] = make_uint2(tile_texx, tint);
+        p.col_ps[ci] = make_ulonglong2(pos0, step2);
+    }
+    int agg_ya = (live && ya < yb) ? ya : 0x7fffffff;
+    int agg_fs_min = 0x7fffffff, agg_fs_max = 0;
 
-    if (DEBUG) {
+    if (DEBUG && live) {
         pm3d_column d;
         d.perp_dist = perpWallDist;
         d.line_height = lineHeight;
@@ -128,40 +163,32 @@ __global__ void __launch_bounds__(128) k_cast_columns(CastParams p) {
         p.dbg[ci] = d;
     }
 
-    if (level != 0) return;
-    p.zbuf[(size_t)view * p.w + x] = perpWallDist;
-
-    // ---- floor-cast parameters of this column
-    FloorRec f;
-    if (side == 0 && rayDirX > 0)      { f.fxw = (double)mx;         f.fyw = (double)my + wallX; }
-    else if (side == 0 && rayDirX < 0) { f.fxw = (double)mx + 1.0;   f.fyw = (double)my + wallX; }
-    else if (side == 1 && rayDirY > 0) { f.fxw = (double)mx + wallX; f.fyw = (double)my; }
-    else                               { f.fxw = (double)mx + wallX; f.fyw = (double)my + 1.0; }
-    f.dw = perpWallDist;
-    int64_t de = drawEnd;
-    if (de < 0) de = h;  // "becomes < 0 when the integer overflows"
-    f.fs = (int32_t)(de >= h ? h : de + 1);
-    f._pad = 0;
-    p.floor_rec[(size_t)view * p.w + x] = f;
-}
-
-int pm3d_launch_cast(pm3d_ctx *ctx, int n_views) {
-    CastParams p;
-    p.views = ctx->cur_views;
-    p.grid = ctx->grid;
-    p.wall_lut = ctx->wall_lut;
-    p.col_rec = ctx->col_rec;
-    p.floor_rec = ctx->floor_rec;
-    p.zbuf = ctx->zbuf;
-    p.dbg = ctx->keep_columns ? ctx->dbg_cols : nullptr;
-    p.w = ctx->w; p.h = ctx->h; p.map_w = ctx->map_w; p.map_h = ctx->map_h;
-    p.stored_levels = ctx->stored_levels; p.num_levels = ctx->num_levels; p.tex_size = ctx->tex_size;
-    dim3 block(128), grid((ctx->w + 127) / 128, ctx->num_levels, n_views);
-    pm3d_kt_mark(ctx, 0, 0);
-    if (p.dbg) k_cast_columns<true><<<grid, block, 0, ctx->stream>>>(p);
-    else k_cast_columns<false><<<grid, block, 0, ctx->stream>>>(p);
-    pm3d_kt_mark(ctx, 0, 1);
-    ctx->launches++;
-    PM3D_CUDA(ctx, cudaGetLastError());
-    return PM3D_OK;
+    if (level == 0) {
+        // ---- floor-cast parameters of this column
+        double fxw, fyw;
+        if (side == 0 && rayDirX > 0)      { fxw = (double)mx;         fyw = (double)my + wallX; }
+        else if (side == 0 && rayDirX < 0) { fxw = (double)mx + 1.0;   fyw = (double)my + wallX; }
+        else if (side == 1 && rayDirY > 0) { fxw = (double)mx + wallX; fyw = (double)my; }
+        else                               { fxw = (double)mx + wallX; fyw = (double)my + 1.0; }
+        int64_t de = drawEnd;
+        if (de < 0) de = h;  // "becomes < 0 when the integer overflows"
+        const int fs = (int32_t)(de >= h ? h : de + 1);
+        if (live) {
+            const size_t fi = (size_t)view * p.w + x;
+            p.zbuf[fi] = perpWallDist;
+            p.flo_xw[fi] = fxw; p.flo_yw[fi] = fyw; p.flo_dw[fi] = perpWallDist; p.flo_fs[fi] = fs;
+            agg_fs_min = fs; agg_fs_max = fs;
+        }
+    }
+    // ---- aggregate over this warp's 32 columns (half a group)
+    for (int o = 16; o > 0; o >>= 1) {
+        agg_ya = min(agg_ya, __shfl_xor_sync(0xffffffffu, agg_ya, o));
+        agg_fs_min = min(agg_fs_min, __shfl_xor_sync(0xffffffffu, agg_fs_min, o));
+        agg_fs_max = max(agg_fs_max, __shfl_xor_sync(0xffffffffu, agg_fs_max, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        const int half = (threadIdx.x >> 5) & 1;
+        p.agg[(((size_t)view * p.num_levels + level) * p.n_groups + group) * 2 + half] =
+            make_int4(agg_ya, agg_fs_min, agg_fs_max, 0);
+    }
 }

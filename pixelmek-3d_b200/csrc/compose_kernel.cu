@@ -1,50 +1,66 @@
 // compose_kernel.cu — K2 floor cast + K3 Camera.Draw: the per-pixel pass that writes the
 // RGBA8 framebuffer (call sites game/scene_game.go:161,167).
 //
-// Mapping: a warp covers one 64-column group x 2 rows (16 lanes x 4 adjacent pixels, so each
-// lane ends a row with ONE 128-bit store and a warp store covers two 256 B row segments);
-// a CTA = 4 warps = COMPOSE_ROWS consecutive rows of one group.  The group's wall-slice,
-// floor and z-buffer records and the CTA's row table are staged in shared memory once.
+// Mapping: a warp owns one 64-column group x WARP_ROWS consecutive rows and walks them two rows
+// at a time (16 lanes x 4 adjacent pixels per row, so every lane ends a row with ONE 128-bit
+// store and a warp store covers two 256 B row segments).  Warps are independent: nothing is
+// staged per CTA and there is no __syncthreads — the per-column records are read straight from
+// the struct-of-arrays the cast wrote (a lane's four columns are one contiguous 32/64 B load,
+// L1-resident after the first row pair), and the only shared memory is a warp-private list of
+// the sprites that touch the warp's rows.
 //
 // Layer order is the reference's painter's order (DESIGN.md "frame composition"):
 //   sky / floor box -> walls (top level .. 0) -> textured floor -> sprites far .. near.
-// Because every layer is premultiplied source-over with one rounding per layer, the result
-// after the last OPAQUE texel does not depend on anything behind it.  The fast path
-// therefore resolves layers front to back and stops at the first opaque texel; a pixel that
-// meets a translucent texel (0 < a < 255) on the way is re-done by the literal painter loop
-// (PM3D_OPT_FORCE_PAINTER forces that loop everywhere; tests require identical output).
+// Every layer is premultiplied source-over with one rounding per layer, so the colour after
+// the last OPAQUE texel does not depend on anything behind it.  The background (box, walls,
+// floor) is therefore resolved FRONT TO BACK and stops at the first opaque texel:
+//   * rows at or below every floor start of the group (agg.fs_max, from the cast) evaluate the
+//     four floor casts of a lane in straight line (4 independent binary64 chains);
+//   * rows above every wall slice and floor start of the group (agg) are sky only;
+//   * other rows resolve floor, then walls level by level for the four pixels together;
+//   * a pixel that meets a translucent texel (0 < a < 255) is redone by the literal painter loop.
+// Sprites are then blended over the background far -> near, exactly as the painter does.  Each
+// lane keeps a private bitmask of the warp's sprites that overlap ITS four columns, so lanes walk
+// different sprites concurrently (sprites pile up on the horizon rows).
+// PM3D_OPT_FORCE_PAINTER forces the literal loop everywhere; tests require identical bytes.
+// The warp that owns the screen-centre pixel also picks the convergence sprite
+// (Camera.GetConvergenceSprite, game/scene_game.go:164).
 #include "pm3d_internal.cuh"
 
-#define GROUP_COLS 64
 #define COMPOSE_WARPS 4
-#define COMPOSE_ROWS 32  // rows per CTA (8 per warp-pair-row slot: 4 warps x 2 rows x 4 iterations)
-#define MAX_BAND_SPRITES 256
+#define WARP_ROWS 8                               // rows per warp: 4 iterations x 2 rows
+#define COMPOSE_ROWS (COMPOSE_WARPS * WARP_ROWS)  // rows per CTA
+#define MAX_WARP_SPRITES 128
+#define WARP_WORDS (MAX_WARP_SPRITES / 32)
 
 struct ComposeParams {
     const pm3d_view *views;
-    const ColRec *col_rec;
-    const FloorRec *floor_rec;
+    const int2 *col_span;
+    const uint2 *col_tt;
+    const ulonglong2 *col_ps;
+    const double *flo_xw, *flo_yw, *flo_dw;
+    const int32_t *flo_fs;
+    const int4 *agg;
     const double *zbuf;
     const RowRec *row_rec;
     const DrawRec *draw_rec;
     const int32_t *sprite_offset;
     const uint16_t *bin_list;
-    const int32_t *bin_count;
+    const int4 *bin_rect;
+    const int4 *bin_count;
     const uint32_t *atlas;
     const int16_t *floor_tiles;
     const uint32_t *sheet_pixels;
+    const pm3d_sprite *sprites;
+    pm3d_convergence *conv;
     uint8_t *out;
+    uint64_t xstep;  // span_step(tex_size, w): box texel column of screen column x
     int w, h, num_levels, tex_size, tex_shift, map_w, map_h, n_groups, sky_tile, floorbox_tile, force_painter;
 };
 
-struct Smem {
-    FloorRec floor[GROUP_COLS];
-    double zbuf[GROUP_COLS];
-    RowRec rows[COMPOSE_ROWS];
-    uint16_t box_u[GROUP_COLS];
-    uint16_t band[MAX_BAND_SPRITES];
-    int n_band;
-    int band_overflow;
+struct WarpList {
+    int4 rect[MAX_WARP_SPRITES];  // dsx, dex, dsy, dey, paint order
+    uint16_t id[MAX_WARP_SPRITES];
 };
 
 // ---- one sprite layer at pixel (x, y); returns texel (premultiplied) or 0 when it does not cover
@@ -61,219 +77,383 @@ __device__ __forceinline__ uint32_t sprite_texel(const DrawRec &d, const uint32_
     return __ldg(sheet_pixels + d.sheet_px + (uint64_t)ty * d.sheet_w + tx);
 }
 
-// ---- floor layer at (column record f, row record r): returns texel already tinted (>>8), 0 if none
-__device__ __forceinline__ uint32_t floor_texel(const ComposeParams &p, const FloorRec &f, const RowRec &r,
-                                                double posx, double posy, int y) {
-    if (y < f.fs || !(r.info & 0x80000000u)) return 0u;
-    const double weight = r.cd / f.dw;
-    const double fx = weight * f.fxw + (1.0 - weight) * posx;
-    const double fy = weight * f.fyw + (1.0 - weight) * posy;
-    if (!(fx >= 0.0) || !(fy >= 0.0)) return 0u;
-    if (!(fx < (double)p.map_w) || !(fy < (double)p.map_h)) return 0u;  // int(fx) >= map_w  <=>  fx >= map_w
-    const int tx = (int)(fx * (double)p.tex_size), ty = (int)(fy * (double)p.tex_size);
-    const int cx = tx >> p.tex_shift, cy = ty >> p.tex_shift;
-    const int ft = __ldg(p.floor_tiles + cx * p.map_h + cy);
-    if (ft < 0) return 0u;
-    const int m = p.tex_size - 1;
-    const uint32_t px = __ldg(p.atlas + ((((size_t)ft << p.tex_shift) + (size_t)(ty & m)) << p.tex_shift) + (size_t)(tx & m));
-    if ((px >> 24) == 0) return 0u;
-    const uint32_t t = r.tint;
+__device__ __forceinline__ uint32_t floor_tint(uint32_t px, uint32_t t) {
+    // pixel.R = uint8(float64(pixel.R) * float64(pixelSt.R) / 256); alpha unchanged
     const uint32_t rr = ((px & 255u) * (t & 255u)) >> 8;
     const uint32_t gg = (((px >> 8) & 255u) * ((t >> 8) & 255u)) >> 8;
     const uint32_t bb = (((px >> 16) & 255u) * ((t >> 16) & 255u)) >> 8;
     return rr | (gg << 8) | (bb << 16) | (px & 0xff000000u);
 }
 
-__device__ __forceinline__ uint32_t wall_texel(const ComposeParams &p, const ColRec &c, int y) {
-    uint32_t ty = (uint32_t)((c.pos0 + (uint64_t)(int64_t)y * c.step2) >> 33);
+// ---- floor layer of one pixel given its column parameters: texel already tinted (>>8), 0 if none
+__device__ __forceinline__ uint32_t floor_texel(const ComposeParams &p, double fxw, double fyw, double dw, int fs,
+                                                const RowRec &r, double posx, double posy, int y) {
+    if (y < fs || !(r.info & 0x80000000u)) return 0u;
+    const double weight = r.cd / dw;
+    const double fx = weight * fxw + (1.0 - weight) * posx;
+    const double fy = weight * fyw + (1.0 - weight) * posy;
+    if (!(fx >= 0.0) || !(fy >= 0.0)) return 0u;
+    if (!(fx < (double)p.map_w) || !(fy < (double)p.map_h)) return 0u;  // int(fx) >= map_w  <=>  fx >= map_w
+    const int tx = (int)(fx * (double)p.tex_size), ty = (int)(fy * (double)p.tex_size);
+    const int ft = __ldg(p.floor_tiles + (tx >> p.tex_shift) * p.map_h + (ty >> p.tex_shift));
+    if (ft < 0) return 0u;
+    const int m = p.tex_size - 1;
+    const uint32_t px = __ldg(p.atlas + ((((size_t)ft << p.tex_shift) + (size_t)(ty & m)) << p.tex_shift) + (size_t)(tx & m));
+    if ((px >> 24) == 0) return 0u;
+    return floor_tint(px, r.tint);
+}
+
+__device__ __forceinline__ uint32_t wall_texel(const ComposeParams &p, uint32_t tile_texx, ulonglong2 ps, int y) {
+    uint32_t ty = (uint32_t)((ps.x + (uint64_t)(int64_t)y * ps.y) >> 33);
     if (ty > (uint32_t)p.tex_size - 1) ty = p.tex_size - 1;
-    const uint32_t tile = c.tile_texx >> 16, tx = c.tile_texx & 0xffffu;
+    const uint32_t tile = tile_texx >> 16, tx = tile_texx & 0xffffu;
     return __ldg(p.atlas + ((((size_t)tile << p.tex_shift) + ty) << p.tex_shift) + tx);
 }
 
-__device__ __forceinline__ uint32_t box_texel(const ComposeParams &p, const RowRec &r, uint32_t u) {
-    const int tile = (r.info & 0x40000000u) ? p.sky_tile : p.floorbox_tile;
+__device__ __forceinline__ uint32_t box_texel(const ComposeParams &p, uint32_t info, uint32_t u) {
+    const int tile = (info & 0x40000000u) ? p.sky_tile : p.floorbox_tile;
     if (tile < 0) return 0u;
-    const uint32_t v = r.info & 0xffffu;
+    const uint32_t v = info & 0xffffu;
     return __ldg(p.atlas + ((((size_t)tile << p.tex_shift) + v) << p.tex_shift) + u);
 }
 
-// literal painter's loop (the definition)
-__device__ __noinline__ uint32_t pixel_painter(const ComposeParams &p, const Smem &s, const ColRec *scol, int lc,
-                                               int x, int y, const RowRec &r, const DrawRec *draw, double posx,
-                                               double posy, uint32_t box_tint) {
+// tinted opaque texel over anything: (c*tint + 127)/255, alpha 255
+__device__ __forceinline__ uint32_t shade_opaque(uint32_t t, uint32_t tint) {
+    if (tint == 0xffffffffu) return t;  // (c*255 + 127)/255 == c
+    return blend_over(0u, t, tint);
+}
+
+// literal painter's loop over the BACKGROUND layers of pixel (x, y) — the definition
+__device__ __noinline__ uint32_t background_painter(const ComposeParams &p, int view, int x, int y, uint32_t u) {
+    const pm3d_view &c = p.views[view];
+    const uint32_t box_tint = (uint32_t)c.max_light[0] | ((uint32_t)c.max_light[1] << 8) |
+                              ((uint32_t)c.max_light[2] << 16) | 0xff000000u;
+    const RowRec r = p.row_rec[(size_t)view * p.h + y];
     uint32_t dst = 0u;
-    dst = blend_over(dst, box_texel(p, r, s.box_u[lc]), box_tint);
+    dst = blend_over(dst, box_texel(p, r.info, u), box_tint);
     for (int l = p.num_levels - 1; l >= 0; l--) {
-        const ColRec c = scol[l * GROUP_COLS + lc];
-        if (y >= c.ya && y < c.yb) dst = blend_over(dst, wall_texel(p, c, y), c.tint);
+        const size_t i = ((size_t)view * p.num_levels + l) * p.w + x;
+        const int2 span = p.col_span[i];
+        if (y >= span.x && y < span.y) {
+            const uint2 tt = p.col_tt[i];
+            dst = blend_over(dst, wall_texel(p, tt.x, p.col_ps[i], y), tt.y);
+        }
     }
-    dst = blend_over(dst, floor_texel(p, s.floor[lc], r, posx, posy, y), 0xffffffffu);
-    const double z = s.zbuf[lc];
-    for (int i = 0; i < s.n_band; i++) {
-        const DrawRec &d = draw[s.band[i]];
-        dst = blend_over(dst, sprite_texel(d, p.sheet_pixels, x, y, z), d.tint);
-    }
+    const size_t fi = (size_t)view * p.w + x;
+    dst = blend_over(dst, floor_texel(p, p.flo_xw[fi], p.flo_yw[fi], p.flo_dw[fi], p.flo_fs[fi], r, c.pos_x, c.pos_y, y),
+                     0xffffffffu);
     return dst;
 }
 
-// front-to-back resolve; sets *ok=false when a translucent texel was met
-__device__ __forceinline__ uint32_t pixel_fast(const ComposeParams &p, const Smem &s, const ColRec *scol, int lc, int x,
-                                               int y, const RowRec &r, const DrawRec *draw, double posx, double posy,
-                                               uint32_t box_tint, bool *ok) {
-    const double z = s.zbuf[lc];
-    for (int i = s.n_band - 1; i >= 0; i--) {
-        const DrawRec &d = draw[s.band[i]];
-        const uint32_t t = sprite_texel(d, p.sheet_pixels, x, y, z);
-        const uint32_t a = t >> 24;
-        if (a == 255u) return blend_over(0u, t, d.tint);
-        if (a != 0u) { *ok = false; return 0u; }
+// four consecutive array elements of a lane's columns; 16 B vector loads when the row pitch keeps
+// them aligned (w % 4 == 0) and all four columns exist
+__device__ __forceinline__ void load4(const double *base, size_t i, bool vec, int nvalid, double out[4]) {
+    if (vec) {
+        const double2 a = *reinterpret_cast<const double2 *>(base + i), b = *reinterpret_cast<const double2 *>(base + i + 2);
+        out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) out[j] = base[i + (j < nvalid ? j : 0)];
     }
-    {
-        const uint32_t t = floor_texel(p, s.floor[lc], r, posx, posy, y);
-        const uint32_t a = t >> 24;
-        if (a == 255u) return t;  // (t*255 + 127)/255 == t
-        if (a != 0u) { *ok = false; return 0u; }
+}
+__device__ __forceinline__ void load4(const int32_t *base, size_t i, bool vec, int nvalid, int out[4]) {
+    if (vec) {
+        const int4 a = *reinterpret_cast<const int4 *>(base + i);
+        out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) out[j] = base[i + (j < nvalid ? j : 0)];
     }
-    for (int l = 0; l < p.num_levels; l++) {
-        const ColRec c = scol[l * GROUP_COLS + lc];
-        if (y >= c.ya && y < c.yb) {
-            const uint32_t t = wall_texel(p, c, y);
-            const uint32_t a = t >> 24;
-            if (a == 255u) return blend_over(0u, t, c.tint);
-            if (a != 0u) { *ok = false; return 0u; }
-        }
+}
+__device__ __forceinline__ void load4(const int2 *base, size_t i, bool vec, int nvalid, int2 out[4]) {
+    if (vec) {
+        const int4 a = *reinterpret_cast<const int4 *>(base + i), b = *reinterpret_cast<const int4 *>(base + i + 2);
+        out[0] = make_int2(a.x, a.y); out[1] = make_int2(a.z, a.w); out[2] = make_int2(b.x, b.y); out[3] = make_int2(b.z, b.w);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) out[j] = base[i + (j < nvalid ? j : 0)];
     }
-    return blend_over(0u, box_texel(p, r, s.box_u[lc]), box_tint);
 }
 
-__global__ void __launch_bounds__(COMPOSE_WARPS * 32) k_compose(ComposeParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem &s = *reinterpret_cast<Smem *>(smem_raw);
-    ColRec *scol = reinterpret_cast<ColRec *>(smem_raw + ((sizeof(Smem) + 15) & ~(size_t)15));
+__global__ void __launch_bounds__(COMPOSE_WARPS * 32, 8) k_compose(const __grid_constant__ ComposeParams p) {
+    __shared__ WarpList s_list[COMPOSE_WARPS];
 
     const int group = blockIdx.x, view = blockIdx.z;
-    const int row0 = blockIdx.y * COMPOSE_ROWS;
-    const int tid = threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wrow0 = blockIdx.y * COMPOSE_ROWS + warp * WARP_ROWS;
+    if (wrow0 >= p.h) return;
+    const int wrow1 = min(wrow0 + WARP_ROWS, p.h);
     const int gx0 = group * GROUP_COLS;
     const pm3d_view &c = p.views[view];
     const double posx = c.pos_x, posy = c.pos_y;
     const uint32_t box_tint = (uint32_t)c.max_light[0] | ((uint32_t)c.max_light[1] << 8) |
                               ((uint32_t)c.max_light[2] << 16) | 0xff000000u;
+    WarpList &wl = s_list[warp];
 
-    // ---- stage the group's records
-    for (int i = tid; i < GROUP_COLS * p.num_levels; i += blockDim.x) {
-        const int l = i / GROUP_COLS, lc = i - l * GROUP_COLS;
-        ColRec r;
-        r.ya = 0; r.yb = 0; r.tile_texx = 0; r.tint = 0; r.pos0 = 0; r.step2 = 0;
-        if (gx0 + lc < p.w) r = p.col_rec[((size_t)view * p.num_levels + l) * p.w + gx0 + lc];
-        scol[i] = r;
-    }
-    if (tid < GROUP_COLS) {
-        const int x = gx0 + tid;
-        if (x < p.w) {
-            s.floor[tid] = p.floor_rec[(size_t)view * p.w + x];
-            s.zbuf[tid] = p.zbuf[(size_t)view * p.w + x];
-            uint32_t u = (uint32_t)((((uint64_t)(2 * (int64_t)x + 1)) * span_step(p.tex_size, p.w)) >> 33);
-            if (u > (uint32_t)p.tex_size - 1) u = p.tex_size - 1;
-            s.box_u[tid] = (uint16_t)u;
-        } else {
-            FloorRec f; f.fxw = 0; f.fyw = 0; f.dw = 1; f.fs = 0x7fffffff; f._pad = 0;
-            s.floor[tid] = f;
-            s.zbuf[tid] = 0.0;
-            s.box_u[tid] = 0;
+    // ---- group aggregates written by the cast: rows >= fs_max are floor candidates in every column,
+    //      rows < sky_below are above every wall slice and every floor start
+    int fs_max = 0, sky_below = 0x7fffffff;
+    {
+        const int n_agg = p.num_levels * 2;
+        for (int i = lane; i < n_agg; i += 32) {
+            const int4 a = p.agg[(((size_t)view * p.num_levels + (i >> 1)) * p.n_groups + group) * 2 + (i & 1)];
+            fs_max = max(fs_max, a.z);
+            sky_below = min(sky_below, min(a.x, a.y));
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            fs_max = max(fs_max, __shfl_xor_sync(0xffffffffu, fs_max, o));
+            sky_below = min(sky_below, __shfl_xor_sync(0xffffffffu, sky_below, o));
         }
     }
-    if (tid < COMPOSE_ROWS) {
-        const int y = row0 + tid;
-        RowRec r; r.cd = 0; r.tint = 0; r.info = 0;
-        if (y < p.h) r = p.row_rec[(size_t)view * p.h + y];
-        s.rows[tid] = r;
-    }
-    // ---- band sprite list: entries of the group list whose rows intersect this CTA (order kept)
+
+    // ---- warp-private sprite list: entries of the group list whose rows intersect this warp's rows
     const int s0 = p.sprite_offset[view];
     const int nv = p.sprite_offset[view + 1] - s0;
     const DrawRec *draw = p.draw_rec + s0;
-    if (tid < 32) {
-        const uint16_t *list = p.bin_list + (size_t)s0 * p.n_groups + (size_t)group * nv;
-        const int cnt = p.bin_count[view * p.n_groups + group];
-        int nb = 0, overflow = 0;
-        const int y0 = row0, y1 = min(row0 + COMPOSE_ROWS, p.h);
-        for (int base = 0; base < cnt; base += 32) {
-            const int i = base + tid;
+    const uint16_t *glist = p.bin_list + (size_t)s0 * p.n_groups + (size_t)group * nv;
+    const int4 *grect = p.bin_rect + (size_t)s0 * p.n_groups + (size_t)group * nv;
+    const int4 ginfo = p.bin_count[view * p.n_groups + group];  // entries, min dsy, max dey
+    const int gcnt = ginfo.x;
+    int n_list = 0;
+    bool overflow = false;
+    if (gcnt > 0 && ginfo.z > wrow0 && ginfo.y < wrow1) {
+        for (int base = 0; base < gcnt; base += 32) {
+            const int i = base + lane;
             bool keep = false;
             uint16_t id = 0;
-            if (i < cnt) {
-                id = list[i];
-                const DrawRec &d = draw[id];
-                keep = d.dey > y0 && d.dsy < y1;
+            int4 rc = make_int4(0, 0, 0, 0);
+            if (i < gcnt) {
+                id = glist[i];
+                rc = grect[i];  // dsx, dex, dsy, dey
+                keep = rc.w > wrow0 && rc.z < wrow1;
             }
             const unsigned m = __ballot_sync(0xffffffffu, keep);
-            const int pos = nb + __popc(m & ((1u << tid) - 1u));
-            if (keep) {
-                if (pos < MAX_BAND_SPRITES) s.band[pos] = id; else overflow = 1;
-            }
-            nb += __popc(m);
+            const int pos = n_list + __popc(m & ((1u << lane) - 1u));
+            if (keep && pos < MAX_WARP_SPRITES) { wl.id[pos] = id; wl.rect[pos] = rc; }
+            n_list += __popc(m);
         }
-        overflow = __any_sync(0xffffffffu, overflow);
-        if (tid == 0) { s.n_band = min(nb, MAX_BAND_SPRITES); s.band_overflow = overflow; }
+        if (n_list > MAX_WARP_SPRITES) { overflow = true; n_list = MAX_WARP_SPRITES; }
+        __syncwarp();
     }
-    __syncthreads();
 
-    // ---- pixels
-    const int warp = tid >> 5, lane = tid & 31;
+    // ---- convergence (one warp per view): wall hit of the centre ray, overridden by the nearest
+    //      focusable sprite covering the centre pixel in front of that wall; ties -> lower list index
+    {
+        const int cx = p.w / 2, cy = p.h / 2;
+        if (cx >= gx0 && cx < gx0 + GROUP_COLS && cy >= wrow0 && cy < wrow1) {
+            const double zc = p.zbuf[(size_t)view * p.w + cx];
+            int best = -1;
+            double best_d = 0.0;
+            const int cnt = overflow ? gcnt : n_list;
+            for (int i = lane; i < cnt; i += 32) {
+                const DrawRec &d = draw[overflow ? glist[i] : wl.id[i]];
+                if ((d.flags & 1u) && cx > 0 && cx >= d.dsx && cx < d.dex && cy >= d.dsy && cy < d.dey && d.transformY < zc) {
+                    if (best < 0 || d.dist < best_d || (d.dist == best_d && d.src < best)) { best = d.src; best_d = d.dist; }
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const double od = __shfl_xor_sync(0xffffffffu, best_d, o);
+                if (ob >= 0 && (best < 0 || od < best_d || (od == best_d && ob < best))) { best = ob; best_d = od; }
+            }
+            if (lane == 0) {
+                pm3d_convergence cv;
+                const double cameraX = 2.0 * (double)cx / (double)p.w - 1.0;
+                const double rdx = c.dir_x + c.plane_x * cameraX, rdy = c.dir_y + c.plane_y * cameraX;
+                cv.distance = zc;
+                cv.point_x = c.pos_x + zc * rdx;
+                cv.point_y = c.pos_y + zc * rdy;
+                cv.sprite = -1;
+                cv._pad = 0;
+                if (best >= 0) {
+                    const pm3d_sprite &sp = p.sprites[s0 + best];
+                    cv.sprite = best;
+                    cv.distance = best_d;
+                    cv.point_x = sp.x;
+                    cv.point_y = sp.y;
+                }
+                p.conv[view] = cv;
+            }
+        }
+    }
+
+    // ---- this lane's four columns
     const int lx = lane & 15, ly = lane >> 4;
-    const int lc0 = lx * 4;
-    const int x0 = gx0 + lc0;
+    const int x0 = gx0 + lx * 4;
     if (x0 >= p.w) return;
+    const int nvalid = min(4, p.w - x0);
+    const bool full4 = nvalid == 4;
+    const bool vec = ((p.w & 3) == 0) && full4;
+    const bool fast_ok = !p.force_painter && full4;
+    const int tmask = p.tex_size - 1;
+    const double mapw = (double)p.map_w, maph = (double)p.map_h, texd = (double)p.tex_size;
+    const size_t fi0 = (size_t)view * p.w + x0;
     uint32_t *out32 = reinterpret_cast<uint32_t *>(p.out) + (size_t)view * p.h * p.w;
-    const bool vec_ok = ((p.w & 3) == 0);
+
+    // per-lane mask of the warp's sprites that overlap this lane's four columns
+    uint32_t xm[WARP_WORDS];
+#pragma unroll
+    for (int wd = 0; wd < WARP_WORDS; wd++) {
+        uint32_t m = 0u;
+        const int lim = min(32, n_list - wd * 32);
+        for (int b = 0; b < lim; b++) {
+            const int4 rc = wl.rect[wd * 32 + b];
+            if (!(x0 + 3 < rc.x || x0 >= rc.y)) m |= 1u << b;
+        }
+        xm[wd] = m;
+    }
+
+    // z-buffer of this lane's columns (sprite depth test)
+    double zb[4] = {0.0, 0.0, 0.0, 0.0};
+    if (n_list > 0) load4(p.zbuf, fi0, vec, nvalid, zb);
+
+    // box texel column of each of this lane's pixels
+    uint32_t bu[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint32_t u = (uint32_t)((((uint64_t)(2 * (int64_t)(x0 + j) + 1)) * p.xstep) >> 33);
+        bu[j] = u > (uint32_t)tmask ? (uint32_t)tmask : u;
+    }
 
 #pragma unroll 1
-    for (int it = 0; it < COMPOSE_ROWS / (COMPOSE_WARPS * 2); it++) {
-        const int ry = (it * COMPOSE_WARPS + warp) * 2 + ly;
-        const int y = row0 + ry;
+    for (int it = 0; it < WARP_ROWS / 2; it++) {
+        const int y = wrow0 + it * 2 + ly;
         if (y >= p.h) break;
-        const RowRec r = s.rows[ry];
+        const RowRec r = p.row_rec[(size_t)view * p.h + y];
         uint32_t px[4];
+        bool done = false;
+
+        if (fast_ok && y >= fs_max && (r.info & 0x80000000u)) {
+            // ---------- every pixel of this lane is a floor candidate: four casts in straight line
+            double cw[4], cx[4], cy[4], fx[4], fy[4];
+            load4(p.flo_dw, fi0, vec, 4, cw);
+            load4(p.flo_xw, fi0, vec, 4, cx);
+            load4(p.flo_yw, fi0, vec, 4, cy);
+            bool inb = true;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int lc = lc0 + j, x = x0 + j;
-            uint32_t v = 0u;
-            if (x < p.w) {
-                bool ok = !p.force_painter && !s.band_overflow;
-                if (ok) v = pixel_fast(p, s, scol, lc, x, y, r, draw, posx, posy, box_tint, &ok);
-                if (!ok) {
-                    if (s.band_overflow) {
-                        // more sprites than the band list holds: walk the whole group list instead
-                        uint32_t dst = 0u;
-                        dst = blend_over(dst, box_texel(p, r, s.box_u[lc]), box_tint);
-                        for (int l = p.num_levels - 1; l >= 0; l--) {
-                            const ColRec cr = scol[l * GROUP_COLS + lc];
-                            if (y >= cr.ya && y < cr.yb) dst = blend_over(dst, wall_texel(p, cr, y), cr.tint);
-                        }
-                        dst = blend_over(dst, floor_texel(p, s.floor[lc], r, posx, posy, y), 0xffffffffu);
-                        const uint16_t *list = p.bin_list + (size_t)s0 * p.n_groups + (size_t)group * nv;
-                        const int cnt = p.bin_count[view * p.n_groups + group];
-                        const double z = s.zbuf[lc];
-                        for (int i = 0; i < cnt; i++) {
-                            const DrawRec &d = draw[list[i]];
-                            dst = blend_over(dst, sprite_texel(d, p.sheet_pixels, x, y, z), d.tint);
-                        }
-                        v = dst;
-                    } else {
-                        v = pixel_painter(p, s, scol, lc, x, y, r, draw, posx, posy, box_tint);
+            for (int j = 0; j < 4; j++) {
+                const double weight = r.cd / cw[j];
+                fx[j] = weight * cx[j] + (1.0 - weight) * posx;
+                fy[j] = weight * cy[j] + (1.0 - weight) * posy;
+                inb = inb && (fx[j] >= 0.0) && (fy[j] >= 0.0) && (fx[j] < mapw) && (fy[j] < maph);
+            }
+            if (inb) {
+                int tx[4], ty[4], ft[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    tx[j] = (int)(fx[j] * texd);
+                    ty[j] = (int)(fy[j] * texd);
+                    ft[j] = __ldg(p.floor_tiles + (tx[j] >> p.tex_shift) * p.map_h + (ty[j] >> p.tex_shift));
+                }
+                if ((ft[0] | ft[1] | ft[2] | ft[3]) >= 0) {
+                    uint32_t t[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        t[j] = __ldg(p.atlas + ((((size_t)ft[j] << p.tex_shift) + (size_t)(ty[j] & tmask)) << p.tex_shift) + (size_t)(tx[j] & tmask));
+                    if ((t[0] & t[1] & t[2] & t[3]) >= 0xff000000u) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) px[j] = floor_tint(t[j], r.tint);
+                        done = true;
                     }
                 }
             }
-            px[j] = v;
+        } else if (fast_ok && y < sky_below) {
+            // ---------- above every wall slice and floor start of the group: sky / floor box only
+            uint32_t t[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) t[j] = box_texel(p, r.info, bu[j]);
+            if ((t[0] & t[1] & t[2] & t[3]) >= 0xff000000u) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) px[j] = shade_opaque(t[j], box_tint);
+                done = true;
+            }
         }
+        if (!done) {
+            // ---------- mixed row: floor, then walls level by level, then the box — four pixels together
+            unsigned pending = (1u << nvalid) - 1u;         // pixels not resolved yet
+            unsigned slow = p.force_painter ? pending : 0u;  // pixels that met a translucent texel
+            pending &= ~slow;
+#pragma unroll
+            for (int j = 0; j < 4; j++) px[j] = 0u;
+            if (pending) {
+                int fs[4];
+                load4(p.flo_fs, fi0, vec, nvalid, fs);
+                bool any_floor = false;
+#pragma unroll
+                for (int j = 0; j < 4; j++) any_floor = any_floor || (((pending >> j) & 1u) && y >= fs[j]);
+                if (any_floor && (r.info & 0x80000000u)) {
+                    double cw[4], cx[4], cy[4];
+                    load4(p.flo_dw, fi0, vec, nvalid, cw);
+                    load4(p.flo_xw, fi0, vec, nvalid, cx);
+                    load4(p.flo_yw, fi0, vec, nvalid, cy);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (!((pending >> j) & 1u)) continue;
+                        const uint32_t t = floor_texel(p, cx[j], cy[j], cw[j], fs[j], r, posx, posy, y);
+                        const uint32_t a = t >> 24;
+                        if (a == 255u) { px[j] = t; pending &= ~(1u << j); }  // (t*255 + 127)/255 == t
+                        else if (a != 0u) { slow |= 1u << j; pending &= ~(1u << j); }
+                    }
+                }
+            }
+            for (int l = 0; l < p.num_levels && pending; l++) {
+                const size_t ci = ((size_t)view * p.num_levels + l) * p.w + x0;
+                int2 span[4];
+                load4(p.col_span, ci, vec, nvalid, span);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (!((pending >> j) & 1u) || y < span[j].x || y >= span[j].y) continue;
+                    const uint2 tt = p.col_tt[ci + j];
+                    const uint32_t t = wall_texel(p, tt.x, p.col_ps[ci + j], y);
+                    const uint32_t a = t >> 24;
+                    if (a == 255u) { px[j] = shade_opaque(t, tt.y); pending &= ~(1u << j); }
+                    else if (a != 0u) { slow |= 1u << j; pending &= ~(1u << j); }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if ((pending >> j) & 1u) px[j] = blend_over(0u, box_texel(p, r.info, bu[j]), box_tint);
+                if ((slow >> j) & 1u) px[j] = background_painter(p, view, x0 + j, y, bu[j]);
+            }
+        }
+
+        // ---------- sprites far -> near over the background
+        if (n_list > 0) {
+            if (!overflow) {
+#pragma unroll
+                for (int wd = 0; wd < WARP_WORDS; wd++) {
+                    uint32_t m = xm[wd];
+                    while (m) {
+                        const int i = wd * 32 + __ffs(m) - 1;
+                        m &= m - 1u;
+                        const int4 rc = wl.rect[i];
+                        if (y < rc.z || y >= rc.w) continue;
+                        const DrawRec &d = draw[wl.id[i]];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if (j >= nvalid) continue;
+                            px[j] = blend_over(px[j], sprite_texel(d, p.sheet_pixels, x0 + j, y, zb[j]), d.tint);
+                        }
+                    }
+                }
+            } else {
+                // more sprites than the warp list holds: walk the whole group list
+                for (int i = 0; i < gcnt; i++) {
+                    const DrawRec &d = draw[glist[i]];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (j >= nvalid) continue;
+                        px[j] = blend_over(px[j], sprite_texel(d, p.sheet_pixels, x0 + j, y, zb[j]), d.tint);
+                    }
+                }
+            }
+        }
+
         uint32_t *o = out32 + (size_t)y * p.w + x0;
-        if (vec_ok && x0 + 3 < p.w) {
+        if (vec) {
             *reinterpret_cast<uint4 *>(o) = make_uint4(px[0], px[1], px[2], px[3]);
         } else {
-            for (int j = 0; j < 4; j++)
-                if (x0 + j < p.w) o[j] = px[j];
+            for (int j = 0; j < nvalid; j++) o[j] = px[j];
         }
     }
 }
@@ -303,28 +483,29 @@ __global__ void k_checksum(const uint32_t *frames, uint64_t *out, size_t words_p
 int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     ComposeParams p;
     p.views = ctx->cur_views;
-    p.col_rec = ctx->col_rec;
-    p.floor_rec = ctx->floor_rec;
+    p.col_span = ctx->col_span; p.col_tt = ctx->col_tt; p.col_ps = ctx->col_ps;
+    p.flo_xw = ctx->flo_xw; p.flo_yw = ctx->flo_yw; p.flo_dw = ctx->flo_dw; p.flo_fs = ctx->flo_fs;
+    p.agg = ctx->agg;
     p.zbuf = ctx->zbuf;
     p.row_rec = ctx->row_rec;
     p.draw_rec = ctx->draw_rec;
     p.sprite_offset = ctx->cur_offset;
     p.bin_list = ctx->bin_list;
+    p.bin_rect = ctx->bin_rect;
     p.bin_count = ctx->bin_count;
     p.atlas = reinterpret_cast<const uint32_t *>(ctx->atlas);
     p.floor_tiles = ctx->floor_tiles;
     p.sheet_pixels = reinterpret_cast<const uint32_t *>(ctx->sheet_pixels);
+    p.sprites = ctx->cur_sprites;
+    p.conv = ctx->conv;
     p.out = out;
+    p.xstep = ((uint64_t)ctx->tex_size << 32) / (uint64_t)ctx->w;
     p.w = ctx->w; p.h = ctx->h; p.num_levels = ctx->num_levels; p.tex_size = ctx->tex_size; p.tex_shift = ctx->tex_shift;
     p.map_w = ctx->map_w; p.map_h = ctx->map_h; p.n_groups = ctx->n_groups;
     p.sky_tile = ctx->sky_tile; p.floorbox_tile = ctx->floorbox_tile; p.force_painter = ctx->force_painter;
-    const size_t smem = ((sizeof(Smem) + 15) & ~(size_t)15) + (size_t)GROUP_COLS * ctx->num_levels * sizeof(ColRec);
-    if (smem > 48 * 1024) {
-        PM3D_CUDA(ctx, cudaFuncSetAttribute(k_compose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
     dim3 block(COMPOSE_WARPS * 32), grid(ctx->n_groups, (ctx->h + COMPOSE_ROWS - 1) / COMPOSE_ROWS, n_views);
     pm3d_kt_mark(ctx, 2, 0);
-    k_compose<<<grid, block, smem, ctx->stream>>>(p);
+    k_compose<<<grid, block, 0, ctx->stream>>>(p);
     pm3d_kt_mark(ctx, 2, 1);
     ctx->launches++;
     PM3D_CUDA(ctx, cudaGetLastError());

@@ -1,0 +1,63 @@
+// front_kernel.cu — the frame path's first launch: the per-column wall cast (cast_kernel.cuh) and the
+// per-view setup (view_kernel.cuh) are independent of each other, so they run as CTAs of ONE grid:
+// CTAs [0, n_cast) cast four (view, level, 64-column group) units of 64 rays each,
+// CTAs [n_cast, n_cast + n_views) set up one view each.  The compose kernel consumes both.
+#include "cast_kernel.cuh"
+#include "view_kernel.cuh"
+
+template <bool DEBUG>
+__global__ void __launch_bounds__(VIEW_THREADS, 4) k_front(CastParams cp, ViewParams vp, int n_cast_blocks, long long n_pairs) {
+    if ((int)blockIdx.x < n_cast_blocks) {
+        // a pair of warps = the 64 columns of one (view, level, group)
+        const long long pair = (long long)blockIdx.x * (VIEW_THREADS / 64) + (threadIdx.x >> 6);
+        if (pair >= n_pairs) return;
+        const int group = (int)(pair % cp.n_groups);
+        const long long vl = pair / cp.n_groups;
+        cast_ray<DEBUG>(cp, (int)(vl / cp.num_levels), (int)(vl % cp.num_levels), group, group * GROUP_COLS + (threadIdx.x & 63));
+    } else {
+        view_setup(vp, (int)blockIdx.x - n_cast_blocks);
+    }
+}
+
+int pm3d_launch_front(pm3d_ctx *ctx, int n_views) {
+    CastParams p;
+    p.views = ctx->cur_views;
+    p.grid = ctx->grid;
+    p.dist = ctx->dist;
+    p.wall_lut = ctx->wall_lut;
+    p.col_span = ctx->col_span; p.col_tt = ctx->col_tt; p.col_ps = ctx->col_ps;
+    p.flo_xw = ctx->flo_xw; p.flo_yw = ctx->flo_yw; p.flo_dw = ctx->flo_dw; p.flo_fs = ctx->flo_fs;
+    p.agg = ctx->agg;
+    p.zbuf = ctx->zbuf;
+    p.dbg = ctx->keep_columns ? ctx->dbg_cols : nullptr;
+    p.w = ctx->w; p.h = ctx->h; p.map_w = ctx->map_w; p.map_h = ctx->map_h;
+    p.stored_levels = ctx->stored_levels; p.num_levels = ctx->num_levels; p.tex_size = ctx->tex_size; p.n_groups = ctx->n_groups;
+
+    ViewParams v;
+    v.views = ctx->cur_views;
+    v.row_rec = ctx->row_rec;
+    v.sprites = ctx->cur_sprites;
+    v.sprite_offset = ctx->cur_offset;
+    v.sheets = ctx->sheet_info;
+    v.draw_rec = ctx->draw_rec;
+    v.n_draw = ctx->n_draw;
+    v.bin_list = ctx->bin_list;
+    v.bin_rect = ctx->bin_rect;
+    v.bin_count = ctx->bin_count;
+    v.rects = ctx->rects;
+    v.conv = ctx->conv;
+    v.w = ctx->w; v.h = ctx->h; v.tex_size = ctx->tex_size; v.n_sheets = ctx->n_sheets; v.n_groups = ctx->n_groups;
+    v.sky_tile = ctx->sky_tile; v.floorbox_tile = ctx->floorbox_tile;
+
+    const long long n_pairs = (long long)n_views * ctx->num_levels * ctx->n_groups;
+    const long long n_cast = (n_pairs + VIEW_THREADS / 64 - 1) / (VIEW_THREADS / 64);
+    if (n_cast + n_views > 0x7fffffffll) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "too many rays for one launch");
+    const unsigned grid = (unsigned)(n_cast + n_views);
+    pm3d_kt_mark(ctx, 0, 0);
+    if (p.dbg) k_front<true><<<grid, VIEW_THREADS, 0, ctx->stream>>>(p, v, (int)n_cast, n_pairs);
+    else k_front<false><<<grid, VIEW_THREADS, 0, ctx->stream>>>(p, v, (int)n_cast, n_pairs);
+    pm3d_kt_mark(ctx, 0, 1);
+    ctx->launches++;
+    PM3D_CUDA(ctx, cudaGetLastError());
+    return PM3D_OK;
+}

@@ -85,9 +85,9 @@ void pm3d_destroy(pm3d_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    void *ptrs[] = {ctx->grid, ctx->wall_lut, ctx->atlas, ctx->floor_tiles, ctx->sheet_pixels, ctx->sheet_info,
-                    ctx->views, ctx->col_rec, ctx->floor_rec, ctx->zbuf, ctx->row_rec, ctx->dbg_cols, ctx->sprites,
-                    ctx->sprite_offset, ctx->draw_rec, ctx->n_draw, ctx->bin_list, ctx->bin_count, ctx->rects,
+    void *ptrs[] = {ctx->grid, ctx->dist, ctx->wall_lut, ctx->atlas, ctx->floor_tiles, ctx->sheet_pixels, ctx->sheet_info,
+                    ctx->views, ctx->col_span, ctx->col_tt, ctx->col_ps, ctx->flo_xw, ctx->flo_yw, ctx->flo_dw, ctx->flo_fs, ctx->agg, ctx->zbuf, ctx->row_rec, ctx->dbg_cols, ctx->sprites,
+                    ctx->sprite_offset, ctx->draw_rec, ctx->n_draw, ctx->bin_list, ctx->bin_rect, ctx->bin_count, ctx->rects,
                     ctx->conv, ctx->frame, ctx->checksums, ctx->segs, ctx->seg_irect, ctx->cell_start,
                     ctx->cell_items, ctx->io_a, ctx->io_b, ctx->io_c, ctx->flush_buf};
     for (void *p : ptrs)
@@ -124,6 +124,40 @@ int pm3d_upload_grid(pm3d_ctx *ctx, const uint16_t *grid, int stored_levels, int
     if (rc) return rc;
     PM3D_CUDA(ctx, cudaMemcpyAsync(ctx->grid, grid, count * 2, cudaMemcpyHostToDevice, ctx->stream));
     PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // free-run distance field (cast_kernel.cu): Chebyshev distance to the nearest wall cell or to the
+    // outside of the map, capped at 255; two-pass 8-neighbour chamfer, exact for the L-inf metric
+    {
+        std::vector<uint8_t> dist(count);
+        const int W = map_w, H = map_h;
+        for (int l = 0; l < stored_levels; l++) {
+            const uint16_t *g = grid + (size_t)l * W * H;
+            uint8_t *d = dist.data() + (size_t)l * W * H;
+            auto at = [&](int x, int y) -> int { return (x < 0 || y < 0 || x >= W || y >= H) ? 0 : d[(size_t)x * H + y]; };
+            for (int x = 0; x < W; x++)
+                for (int y = 0; y < H; y++) {
+                    int v = 255;
+                    if (g[(size_t)x * H + y] > 0) v = 0;
+                    else {
+                        v = std::min(v, at(x - 1, y - 1) + 1); v = std::min(v, at(x - 1, y) + 1);
+                        v = std::min(v, at(x - 1, y + 1) + 1); v = std::min(v, at(x, y - 1) + 1);
+                        // (x, y+1) and the x+1 column are not final yet: they may only be read as "outside"
+                        if (y + 1 >= H || x + 1 >= W) v = std::min(v, 1);
+                    }
+                    d[(size_t)x * H + y] = (uint8_t)v;
+                }
+            for (int x = W - 1; x >= 0; x--)
+                for (int y = H - 1; y >= 0; y--) {
+                    int v = d[(size_t)x * H + y];
+                    if (v == 0) continue;
+                    v = std::min(v, at(x + 1, y + 1) + 1); v = std::min(v, at(x + 1, y) + 1);
+                    v = std::min(v, at(x + 1, y - 1) + 1); v = std::min(v, at(x, y + 1) + 1);
+                    d[(size_t)x * H + y] = (uint8_t)v;
+                }
+        }
+        rc = dev_realloc(ctx, &ctx->dist, count);
+        if (rc) return rc;
+        PM3D_CUDA(ctx, cudaMemcpy(ctx->dist, dist.data(), count, cudaMemcpyHostToDevice));
+    }
     ctx->stored_levels = stored_levels; ctx->map_w = map_w; ctx->map_h = map_h;
     const bool levels_changed = ctx->num_levels != num_raycast_levels;
     ctx->num_levels = num_raycast_levels;
@@ -234,8 +268,14 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
     const size_t V = max_views, L = ctx->num_levels, W = width, H = height, S = std::max(max_sprites_total, 1);
     int rc;
     if ((rc = dev_realloc(ctx, &ctx->views, V))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->col_rec, V * L * W))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->floor_rec, V * W))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->col_span, V * L * W))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->col_tt, V * L * W))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->col_ps, V * L * W))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->flo_xw, V * W))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->flo_yw, V * W))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->flo_dw, V * W))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->flo_fs, V * W))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->agg, V * L * ctx->n_groups * 2))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->zbuf, V * W))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->row_rec, V * H))) return rc;
     if (ctx->keep_columns) {
@@ -247,6 +287,7 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
     if ((rc = dev_realloc(ctx, &ctx->draw_rec, S))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->n_draw, V))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->bin_list, S * ctx->n_groups))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->bin_rect, S * ctx->n_groups))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->bin_count, V * ctx->n_groups))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->rects, S))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->conv, V))) return rc;
@@ -262,8 +303,7 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
 // the three kernels of one frame batch; inputs come from ctx->cur_*
 static int render_core(pm3d_ctx *ctx, int n_views, int n_sprites, uint8_t *target) {
     int rc;
-    if ((rc = pm3d_launch_cast(ctx, n_views))) return rc;
-    if ((rc = pm3d_launch_view_setup(ctx, n_views, n_sprites))) return rc;
+    if ((rc = pm3d_launch_front(ctx, n_views))) return rc;
     if ((rc = pm3d_launch_compose(ctx, n_views, target))) return rc;
     if (ctx->kt_on && ctx->kt_n < ctx->kt_cap) ctx->kt_n++;
     ctx->last_frame = target;
@@ -331,8 +371,10 @@ int pm3d_ktimer_collect(pm3d_ctx *ctx, float *out_ms, int cap_frames) {
     PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const int n = ctx->kt_n < cap_frames ? ctx->kt_n : cap_frames;
     for (int f = 0; f < n; f++)
-        for (int k = 0; k < 3; k++)
-            PM3D_CUDA(ctx, cudaEventElapsedTime(&out_ms[f * 3 + k], ctx->kt_ev[(f * 3 + k) * 2], ctx->kt_ev[(f * 3 + k) * 2 + 1]));
+        for (int k = 0; k < 3; k++) {
+            out_ms[f * 3 + k] = 0.0f;  // slot 1 is unused since the cast and the view setup share one launch
+            if (k != 1) PM3D_CUDA(ctx, cudaEventElapsedTime(&out_ms[f * 3 + k], ctx->kt_ev[(f * 3 + k) * 2], ctx->kt_ev[(f * 3 + k) * 2 + 1]));
+        }
     ctx->kt_n = 0;
     return n;
 }

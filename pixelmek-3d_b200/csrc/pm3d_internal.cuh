@@ -11,23 +11,17 @@
 
 // ------------------------------------------------------------------ HBM layouts
 
-// One (view, level, column) wall slice as the compose kernel consumes it.  32 B = 2 x uint4.
-struct __align__(16) ColRec {
-    int32_t ya, yb;        // visible rows [ya, yb) clipped to the screen; ya >= yb: nothing
-    uint32_t tile_texx;    // (tile << 16) | texX
-    uint32_t tint;         // R | G<<8 | B<<16 | 255<<24
-    uint64_t pos0, step2;  // texel row of screen row y = (pos0 + y*step2) >> 33 (mod 2^64 arithmetic)
-};
-static_assert(sizeof(ColRec) == 32, "ColRec");
-
-// Level-0 floor-cast parameters of one (view, column).  32 B.
-struct __align__(16) FloorRec {
-    double fxw, fyw;  // floorXWall, floorYWall
-    double dw;        // distWall
-    int32_t fs;       // first floor row (drawEnd + 1, or h when none)
-    int32_t _pad;
-};
-static_assert(sizeof(FloorRec) == 32, "FloorRec");
+// The cast writes its per-column results as struct-of-arrays, [view][level][column] each, so that
+// the compose kernel reads a lane's four adjacent columns as one contiguous 32 B / 64 B load:
+//   col_span  int2        ya, yb     visible rows [ya, yb) of the slice, clipped to the screen; ya >= yb: nothing
+//   col_tt    uint2       (tile << 16 | texX), tint (R | G<<8 | B<<16 | 255<<24)
+//   col_ps    ulonglong2  pos0, step2: texel row of screen row y = (pos0 + y*step2) >> 33 (mod 2^64)
+// and the level-0 floor-cast parameters as [view][column]:
+//   flo_xw, flo_yw, flo_dw  double  floorXWall, floorYWall, distWall
+//   flo_fs                  int     first floor row (drawEnd + 1, or h when none)
+// plus one aggregate per (view, level, 64-column group, 32-column half):
+//   agg  int4  x: min ya over drawn slices (INT_MAX if none); y: min fs; z: max fs (level 0 only)
+#define GROUP_COLS 64
 
 // Per (view, screen row) values shared by every column.  16 B.
 struct __align__(16) RowRec {
@@ -37,7 +31,7 @@ struct __align__(16) RowRec {
 };
 static_assert(sizeof(RowRec) == 16, "RowRec");
 
-// One visible sprite of a view, in paint order (far -> near).  96 B.
+// One visible sprite of a view, in paint order (far -> near).  112 B.
 struct __align__(16) DrawRec {
     int32_t dsx, dex, dsy, dey;  // unclipped screen rect [dsx,dex) x [dsy,dey)
     double transformY;           // depth for the z test
@@ -48,10 +42,12 @@ struct __align__(16) DrawRec {
     uint32_t sheet_w;            // sheet row pitch in pixels
     uint32_t tint;
     uint16_t tx_lo, tx_hi, ty_lo, ty_hi;  // texel ranges that fall inside the sheet
+    double dist;                 // euclidean camera distance (convergence pick)
     int32_t src;                 // index into the view's sprite list
-    int32_t _pad;
+    uint32_t flags;              // bit0: IsFocusable()
+    uint64_t _pad0, _pad1;
 };
-static_assert(sizeof(DrawRec) == 96, "DrawRec");
+static_assert(sizeof(DrawRec) == 112, "DrawRec");
 
 struct SheetInfo {
     int64_t px_offset;  // first pixel of the sheet inside sheet_pixels (in pixels)
@@ -70,6 +66,7 @@ struct pm3d_ctx {
 
     // mission data
     uint16_t *grid = nullptr;
+    uint8_t *dist = nullptr;  // [stored_levels][map_w][map_h] free-run distance field of the grid
     int stored_levels = 0, map_w = 0, map_h = 0, num_levels = 0;
     int16_t *wall_lut = nullptr;  // [32768][2]
     uint8_t *atlas = nullptr;
@@ -88,9 +85,13 @@ struct pm3d_ctx {
 
     // per-call device buffers
     pm3d_view *views = nullptr;
-    ColRec *col_rec = nullptr;      // [views][levels][w]
-    FloorRec *floor_rec = nullptr;  // [views][w]
-    double *zbuf = nullptr;         // [views][w]
+    int2 *col_span = nullptr;        // [views][levels][w]
+    uint2 *col_tt = nullptr;
+    ulonglong2 *col_ps = nullptr;
+    double *flo_xw = nullptr, *flo_yw = nullptr, *flo_dw = nullptr;  // [views][w]
+    int32_t *flo_fs = nullptr;
+    int4 *agg = nullptr;             // [views][levels][n_groups][2]
+    double *zbuf = nullptr;          // [views][w]
     RowRec *row_rec = nullptr;      // [views][h]
     pm3d_column *dbg_cols = nullptr;  // [views][levels][w] when keep_columns
     int dbg_levels = 0, dbg_views = 0;
@@ -99,7 +100,8 @@ struct pm3d_ctx {
     DrawRec *draw_rec = nullptr;     // [max_sprites], per view contiguous at sprite_offset[v]
     int32_t *n_draw = nullptr;       // [max_views]
     uint16_t *bin_list = nullptr;    // [max_sprites * n_groups]
-    int32_t *bin_count = nullptr;    // [max_views * n_groups]
+    int4 *bin_rect = nullptr;        // [max_sprites * n_groups]
+    int4 *bin_count = nullptr;       // [max_views * n_groups]: entries, min dsy, max dey
     pm3d_rect *rects = nullptr;      // [max_sprites]
     pm3d_convergence *conv = nullptr;  // [max_views]
     uint8_t *frame = nullptr;        // [max_views][h][w][4]
@@ -149,8 +151,7 @@ inline void pm3d_kt_mark(pm3d_ctx *ctx, int k, int end) {
     } while (0)
 
 // kernel launchers (one per .cu)
-int pm3d_launch_cast(pm3d_ctx *ctx, int n_views);
-int pm3d_launch_view_setup(pm3d_ctx *ctx, int n_views, int n_sprites_total);
+int pm3d_launch_front(pm3d_ctx *ctx, int n_views);  // column cast + per-view setup, one launch
 int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out);
 int pm3d_launch_checksum(pm3d_ctx *ctx, int n_views, const uint8_t *frames);
 

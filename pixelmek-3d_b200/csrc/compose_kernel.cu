@@ -25,12 +25,15 @@
 // PM3D_OPT_FORCE_PAINTER forces the literal loop everywhere; tests require identical bytes.
 // The warp that owns the screen-centre pixel also picks the convergence sprite
 // (Camera.GetConvergenceSprite, game/scene_game.go:164).
+#include <stdlib.h>
+
 #include "pm3d_internal.cuh"
 
 #define COMPOSE_WARPS 4
-#define WARP_ROWS 8                               // rows per warp: 4 iterations x 2 rows
-#define COMPOSE_ROWS (COMPOSE_WARPS * WARP_ROWS)  // rows per CTA
-#define MAX_WARP_SPRITES 128
+// rows per warp (WARP_ROWS, a template parameter: 2, 4 or 8 = 1, 2 or 4 iterations of 2 rows) trades the
+// per-warp prologue against the length of the serial chain: single frames want many short warps, large
+// batches of views want few long ones.
+#define MAX_WARP_SPRITES 256
 #define WARP_WORDS (MAX_WARP_SPRITES / 32)
 
 struct ComposeParams {
@@ -58,8 +61,17 @@ struct ComposeParams {
     int w, h, num_levels, tex_size, tex_shift, map_w, map_h, n_groups, sky_tile, floorbox_tile, force_painter;
 };
 
+// screen rect of a listed sprite, clamped to int16 (screens are <= 16384 wide/high, so clamping never
+// changes a comparison against a screen coordinate)
+struct __align__(8) Rect16 { short x0, x1, y0, y1; };
+__device__ __forceinline__ Rect16 make_rect16(int4 r) {
+    Rect16 o;
+    o.x0 = (short)max(-32768, min(32767, r.x)); o.x1 = (short)max(-32768, min(32767, r.y));
+    o.y0 = (short)max(-32768, min(32767, r.z)); o.y1 = (short)max(-32768, min(32767, r.w));
+    return o;
+}
 struct WarpList {
-    int4 rect[MAX_WARP_SPRITES];  // dsx, dex, dsy, dey, paint order
+    Rect16 rect[MAX_WARP_SPRITES];  // dsx, dex, dsy, dey, paint order
     uint16_t id[MAX_WARP_SPRITES];
 };
 
@@ -175,7 +187,9 @@ __device__ __forceinline__ void load4(const int2 *base, size_t i, bool vec, int 
     }
 }
 
-__global__ void __launch_bounds__(COMPOSE_WARPS * 32, 8) k_compose(const __grid_constant__ ComposeParams p) {
+template <int WARP_ROWS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS) k_compose(const __grid_constant__ ComposeParams p) {
+    constexpr int COMPOSE_ROWS = COMPOSE_WARPS * WARP_ROWS;
     __shared__ WarpList s_list[COMPOSE_WARPS];
 
     const int group = blockIdx.x, view = blockIdx.z;
@@ -229,7 +243,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, 8) k_compose(const __grid_
             }
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             const int pos = n_list + __popc(m & ((1u << lane) - 1u));
-            if (keep && pos < MAX_WARP_SPRITES) { wl.id[pos] = id; wl.rect[pos] = rc; }
+            if (keep && pos < MAX_WARP_SPRITES) { wl.id[pos] = id; wl.rect[pos] = make_rect16(rc); }
             n_list += __popc(m);
         }
         if (n_list > MAX_WARP_SPRITES) { overflow = true; n_list = MAX_WARP_SPRITES; }
@@ -290,22 +304,19 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, 8) k_compose(const __grid_
     const size_t fi0 = (size_t)view * p.w + x0;
     uint32_t *out32 = reinterpret_cast<uint32_t *>(p.out) + (size_t)view * p.h * p.w;
 
-    // per-lane mask of the warp's sprites that overlap this lane's four columns
+    // per-lane mask of the warp's sprites that overlap this lane's four columns (lanes then walk
+    // different sprites concurrently instead of every lane scanning the whole list)
     uint32_t xm[WARP_WORDS];
 #pragma unroll
     for (int wd = 0; wd < WARP_WORDS; wd++) {
         uint32_t m = 0u;
         const int lim = min(32, n_list - wd * 32);
         for (int b = 0; b < lim; b++) {
-            const int4 rc = wl.rect[wd * 32 + b];
-            if (!(x0 + 3 < rc.x || x0 >= rc.y)) m |= 1u << b;
+            const Rect16 rc = wl.rect[wd * 32 + b];
+            if (!(x0 + 3 < rc.x0 || x0 >= rc.x1)) m |= 1u << b;
         }
         xm[wd] = m;
     }
-
-    // z-buffer of this lane's columns (sprite depth test)
-    double zb[4] = {0.0, 0.0, 0.0, 0.0};
-    if (n_list > 0) load4(p.zbuf, fi0, vec, nvalid, zb);
 
     // box texel column of each of this lane's pixels
     uint32_t bu[4];
@@ -322,8 +333,59 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, 8) k_compose(const __grid_
         const RowRec r = p.row_rec[(size_t)view * p.h + y];
         uint32_t px[4];
         bool done = false;
+        const unsigned full = (1u << nvalid) - 1u;
 
-        if (fast_ok && y >= fs_max && (r.info & 0x80000000u)) {
+        // ---------- sprites, front to back: the nearest opaque texel of a pixel hides everything behind it
+        unsigned s_got = 0u;    // pixels whose nearest opaque sprite texel is in s_top
+        unsigned s_trans = 0u;  // pixels that met a translucent sprite texel in front of it
+        uint32_t s_top[4] = {0u, 0u, 0u, 0u};
+        const bool sprite_f2b = n_list > 0 && !overflow && !p.force_painter;
+        double zb[4] = {0.0, 0.0, 0.0, 0.0};
+        if (n_list > 0) load4(p.zbuf, fi0, vec, nvalid, zb);
+        if (sprite_f2b) {
+#pragma unroll
+            for (int wd = WARP_WORDS - 1; wd >= 0; wd--) {
+                uint32_t m = xm[wd];
+                while (m && s_got != full) {
+                    const int bit = 31 - __clz(m);
+                    m &= ~(1u << bit);
+                    const int i = wd * 32 + bit;
+                    const Rect16 rc = wl.rect[i];
+                    if (y < rc.y0 || y >= rc.y1) continue;
+                    const DrawRec &d = draw[wl.id[i]];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (j >= nvalid || ((s_got >> j) & 1u)) continue;
+                        const uint32_t t = sprite_texel(d, p.sheet_pixels, x0 + j, y, zb[j]);
+                        const uint32_t a = t >> 24;
+                        if (a == 255u) { s_top[j] = blend_over(0u, t, d.tint); s_got |= 1u << j; }
+                        else if (a != 0u) s_trans |= 1u << j;
+                    }
+                }
+            }
+        }
+        if (overflow && !p.force_painter) {
+            // more sprites than the warp list holds: walk the group list itself, nearest first
+            for (int i = gcnt - 1; i >= 0 && s_got != full; i--) {
+                const int4 rc = grect[i];
+                if (y < rc.z || y >= rc.w || x0 + 3 < rc.x || x0 >= rc.y) continue;
+                const DrawRec &d = draw[glist[i]];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (j >= nvalid || ((s_got >> j) & 1u)) continue;
+                    const uint32_t t = sprite_texel(d, p.sheet_pixels, x0 + j, y, zb[j]);
+                    const uint32_t a = t >> 24;
+                    if (a == 255u) { s_top[j] = blend_over(0u, t, d.tint); s_got |= 1u << j; }
+                    else if (a != 0u) s_trans |= 1u << j;
+                }
+            }
+        }
+        const bool need_bg = (s_got & ~s_trans) != full;  // some pixel still shows (or blends with) the background
+        if (!need_bg) done = true;
+
+        if (done) {
+            // every pixel of this lane is covered by an opaque sprite texel
+        } else if (fast_ok && y >= fs_max && (r.info & 0x80000000u)) {
             // ---------- every pixel of this lane is a floor candidate: four casts in straight line
             double cw[4], cx[4], cy[4], fx[4], fy[4];
             load4(p.flo_dw, fi0, vec, 4, cw);
@@ -417,8 +479,13 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, 8) k_compose(const __grid_
             }
         }
 
-        // ---------- sprites far -> near over the background
-        if (n_list > 0) {
+        // ---------- combine: opaque sprite texels win; pixels that met a translucent texel (and every pixel
+        //            when the list overflowed or the painter is forced) are repainted far -> near
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (((s_got & ~s_trans) >> j) & 1u) px[j] = s_top[j];
+        const unsigned repaint = p.force_painter ? (n_list > 0 ? full : 0u) : s_trans;
+        if (repaint) {
             if (!overflow) {
 #pragma unroll
                 for (int wd = 0; wd < WARP_WORDS; wd++) {
@@ -426,12 +493,12 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, 8) k_compose(const __grid_
                     while (m) {
                         const int i = wd * 32 + __ffs(m) - 1;
                         m &= m - 1u;
-                        const int4 rc = wl.rect[i];
-                        if (y < rc.z || y >= rc.w) continue;
+                        const Rect16 rc = wl.rect[i];
+                        if (y < rc.y0 || y >= rc.y1) continue;
                         const DrawRec &d = draw[wl.id[i]];
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            if (j >= nvalid) continue;
+                            if (!((repaint >> j) & 1u)) continue;
                             px[j] = blend_over(px[j], sprite_texel(d, p.sheet_pixels, x0 + j, y, zb[j]), d.tint);
                         }
                     }
@@ -439,10 +506,12 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, 8) k_compose(const __grid_
             } else {
                 // more sprites than the warp list holds: walk the whole group list
                 for (int i = 0; i < gcnt; i++) {
+                    const int4 rc = grect[i];
+                    if (y < rc.z || y >= rc.w || x0 + 3 < rc.x || x0 >= rc.y) continue;
                     const DrawRec &d = draw[glist[i]];
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        if (j >= nvalid) continue;
+                        if (!((repaint >> j) & 1u)) continue;
                         px[j] = blend_over(px[j], sprite_texel(d, p.sheet_pixels, x0 + j, y, zb[j]), d.tint);
                     }
                 }
@@ -503,9 +572,21 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     p.w = ctx->w; p.h = ctx->h; p.num_levels = ctx->num_levels; p.tex_size = ctx->tex_size; p.tex_shift = ctx->tex_shift;
     p.map_w = ctx->map_w; p.map_h = ctx->map_h; p.n_groups = ctx->n_groups;
     p.sky_tile = ctx->sky_tile; p.floorbox_tile = ctx->floorbox_tile; p.force_painter = ctx->force_painter;
-    dim3 block(COMPOSE_WARPS * 32), grid(ctx->n_groups, (ctx->h + COMPOSE_ROWS - 1) / COMPOSE_ROWS, n_views);
+    // rows per warp: enough warps to fill the chip a few times over, otherwise as long as possible
+    const long long warps8 = (long long)ctx->n_groups * ((ctx->h + 7) / 8) * n_views;
+    const long long resident = (long long)ctx->sm_count * 24;
+    int rows = warps8 >= 8 * resident ? 8 : (warps8 >= 2 * resident ? 4 : 2);
+    int minb = rows == 8 ? 8 : 6;
+    if (const char *e = getenv("PM3D_COMPOSE_ROWS")) rows = atoi(e);      // tuning overrides (tools/)
+    if (const char *e = getenv("PM3D_COMPOSE_MINB")) minb = atoi(e);
+    dim3 block(COMPOSE_WARPS * 32), grid(ctx->n_groups, (ctx->h + COMPOSE_WARPS * rows - 1) / (COMPOSE_WARPS * rows), n_views);
     pm3d_kt_mark(ctx, 2, 0);
-    k_compose<<<grid, block, 0, ctx->stream>>>(p);
+    if (rows == 8 && minb == 8) k_compose<8, 8><<<grid, block, 0, ctx->stream>>>(p);
+    else if (rows == 8) k_compose<8, 6><<<grid, block, 0, ctx->stream>>>(p);
+    else if (rows == 4 && minb == 8) k_compose<4, 8><<<grid, block, 0, ctx->stream>>>(p);
+    else if (rows == 4) k_compose<4, 6><<<grid, block, 0, ctx->stream>>>(p);
+    else if (minb == 8) k_compose<2, 8><<<grid, block, 0, ctx->stream>>>(p);
+    else k_compose<2, 6><<<grid, block, 0, ctx->stream>>>(p);
     pm3d_kt_mark(ctx, 2, 1);
     ctx->launches++;
     PM3D_CUDA(ctx, cudaGetLastError());

@@ -146,8 +146,11 @@ int pm3d_upload_sprite_sheets(pm3d_ctx *ctx, const uint8_t *pixels, const int64_
 int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_sprites_total);
 /* options: PM3D_OPT_KEEP_COLUMNS (default 0) keeps the pm3d_column records of every view for
  * pm3d_download_columns; PM3D_OPT_FORCE_PAINTER (default 0) disables the front-to-back
- * shortcut of the compose kernel (A/B check: output must not change). */
-enum { PM3D_OPT_KEEP_COLUMNS = 1, PM3D_OPT_FORCE_PAINTER = 2 };
+ * shortcut of the compose kernel (A/B check: output must not change); PM3D_OPT_PIPELINE = n
+ * (1..4, default 1) keeps n internal frame slots so that, for PM3D_NO_SYNC renders into HOST
+ * memory, the device-to-host copy of frame i (on a second stream) overlaps the kernels of frame
+ * i+1; results are valid after pm3d_sync.  Call it after pm3d_set_view. */
+enum { PM3D_OPT_KEEP_COLUMNS = 1, PM3D_OPT_FORCE_PAINTER = 2, PM3D_OPT_PIPELINE = 3 };
 int pm3d_set_option(pm3d_ctx *ctx, int option, int value);
 
 /* ------------------------------------------------------------------ frame path

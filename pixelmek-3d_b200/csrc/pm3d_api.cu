@@ -98,6 +98,12 @@ void pm3d_destroy(pm3d_ctx *ctx) {
         if (ctx->ev_stop[i]) cudaEventDestroy(ctx->ev_stop[i]);
     }
     if (ctx->stage_ev) cudaEventDestroy(ctx->stage_ev);
+    for (int i = 0; i < 4; i++) {
+        if (ctx->frame_ring[i]) cudaFree(ctx->frame_ring[i]);
+        if (ctx->ev_rendered[i]) cudaEventDestroy(ctx->ev_rendered[i]);
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < ctx->kt_cap * 6; i++) cudaEventDestroy(ctx->kt_ev[i]);
     delete[] ctx->kt_ev;
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -107,6 +113,7 @@ void pm3d_destroy(pm3d_ctx *ctx) {
 int pm3d_sync(pm3d_ctx *ctx) {
     if (!ctx) return PM3D_ERR_ARG;
     PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     return PM3D_OK;
 }
 
@@ -251,6 +258,28 @@ int pm3d_set_option(pm3d_ctx *ctx, int option, int value) {
     case PM3D_OPT_FORCE_PAINTER:
         ctx->force_painter = value ? 1 : 0;
         return PM3D_OK;
+    case PM3D_OPT_PIPELINE: {
+        if (value < 1 || value > 4) return pm3d_fail(ctx, PM3D_ERR_ARG, "pipeline depth must be 1..4");
+        if (ctx->w < 1) return pm3d_fail(ctx, PM3D_ERR_ARG, "pm3d_set_view must precede PM3D_OPT_PIPELINE");
+        PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+        PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->copy_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        for (int i = 0; i < 4; i++)
+            if (ctx->frame_ring[i]) { PM3D_CUDA(ctx, cudaFree(ctx->frame_ring[i])); ctx->frame_ring[i] = nullptr; }
+        ctx->ring_n = value; ctx->ring_pos = 0;
+        if (value > 1) {
+            if (!ctx->copy_stream) PM3D_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            const size_t fb = (size_t)ctx->max_views * ctx->w * ctx->h * 4;
+            for (int i = 0; i < value; i++) {
+                PM3D_CUDA(ctx, cudaMalloc((void **)&ctx->frame_ring[i], fb));
+                if (!ctx->ev_rendered[i]) {
+                    PM3D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_rendered[i], cudaEventDisableTiming));
+                    PM3D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+                }
+            }
+        }
+        return PM3D_OK;
+    }
     }
     return pm3d_fail(ctx, PM3D_ERR_ARG, "unknown option %d", option);
 }
@@ -295,6 +324,7 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
     if ((rc = dev_realloc(ctx, &ctx->checksums, V))) return rc;
     ctx->last_frame = nullptr;
     ctx->last_views = 0;
+    if (ctx->ring_n > 1) return pm3d_set_option(ctx, PM3D_OPT_PIPELINE, ctx->ring_n);  // re-size the slots
     return PM3D_OK;
 }
 
@@ -422,13 +452,24 @@ int pm3d_render(pm3d_ctx *ctx, const pm3d_view *views, int n_views, const pm3d_s
     if (sb) PM3D_CUDA(ctx, cudaMemcpyAsync(ctx->sprites, st + vb + ob_pad, sb, cudaMemcpyHostToDevice, ctx->stream));
     PM3D_CUDA(ctx, cudaEventRecord(ctx->stage_ev, ctx->stream));
 
-    uint8_t *target = (out_rgba && (flags & PM3D_OUT_DEVICE)) ? out_rgba : ctx->frame;
+    const bool piped = ctx->ring_n > 1 && out_rgba && !(flags & PM3D_OUT_DEVICE) && (flags & PM3D_NO_SYNC);
+    const int slot = ctx->ring_pos;
+    uint8_t *target = (out_rgba && (flags & PM3D_OUT_DEVICE)) ? out_rgba : (piped ? ctx->frame_ring[slot] : ctx->frame);
+    // the slot's previous frame must have left the device before the compose kernel overwrites it
+    if (piped) PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0));
     ctx->cur_views = ctx->views; ctx->cur_sprites = ctx->sprites; ctx->cur_offset = ctx->sprite_offset;
     if ((rc = render_core(ctx, n_views, n_sprites, target))) return rc;
 
     const size_t fb = (size_t)n_views * ctx->w * ctx->h * 4;
-    if (out_rgba && !(flags & PM3D_OUT_DEVICE))
+    if (piped) {
+        PM3D_CUDA(ctx, cudaEventRecord(ctx->ev_rendered[slot], ctx->stream));
+        PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[slot], 0));
+        PM3D_CUDA(ctx, cudaMemcpyAsync(out_rgba, target, fb, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        PM3D_CUDA(ctx, cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
+        ctx->ring_pos = (slot + 1) % ctx->ring_n;
+    } else if (out_rgba && !(flags & PM3D_OUT_DEVICE)) {
         PM3D_CUDA(ctx, cudaMemcpyAsync(out_rgba, ctx->frame, fb, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     if (out_rects && n_sprites)
         PM3D_CUDA(ctx, cudaMemcpyAsync(out_rects, ctx->rects, (size_t)n_sprites * sizeof(pm3d_rect), cudaMemcpyDeviceToHost, ctx->stream));
     if (out_conv)

@@ -106,6 +106,12 @@ struct pm3d_ctx {
     pm3d_convergence *conv = nullptr;  // [max_views]
     uint8_t *frame = nullptr;        // [max_views][h][w][4]
     uint8_t *last_frame = nullptr;   // where the last render wrote (frame or caller memory)
+    // PM3D_OPT_PIPELINE: ring of internal frame slots so the D2H of frame i (copy stream) overlaps
+    // the kernels of frame i+1 (compute stream)
+    cudaStream_t copy_stream = nullptr;
+    int ring_n = 1, ring_pos = 0;
+    uint8_t *frame_ring[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_rendered[4] = {}, ev_copied[4] = {};
     uint64_t *checksums = nullptr;   // [max_views]
 
     // inputs the kernels read this call (ctx-owned copies, or caller device memory)

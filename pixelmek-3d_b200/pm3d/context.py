@@ -41,6 +41,7 @@ class Context:
 
     def sync(self):
         self._check(self.lib.pm3d_sync(self.h), "pm3d_sync")
+        self._keep = []
 
     @property
     def launches(self) -> int:
@@ -112,7 +113,7 @@ class Context:
             out_p = ptr(rgba)
         if no_sync:
             flags |= _lib.PM3D_NO_SYNC
-            self._keep = [views, sprites, sprite_offset, rects, conv, rgba]
+            self._keep.append((views, sprites, sprite_offset, rects, conv, rgba))  # alive until sync()
         self._check(
             self.lib.pm3d_render(self.h, ptr(views), nv, ptr(sprites) if ns else None, ptr(sprite_offset), out_p,
                                  ptr(rects), ptr(conv), flags),

@@ -76,7 +76,8 @@ struct WarpList {
 };
 
 // ---- one sprite layer at pixel (x, y); returns texel (premultiplied) or 0 when it does not cover
-__device__ __forceinline__ uint32_t sprite_texel(const DrawRec &d, const uint32_t *__restrict__ sheet_pixels, int x,
+// (not inlined: it has ~16 call sites and the kernel is instruction-fetch sensitive)
+__device__ __noinline__ uint32_t sprite_texel(const DrawRec &d, const uint32_t *__restrict__ sheet_pixels, int x,
                                                  int y, double z) {
     if (x < d.dsx || x >= d.dex || x <= 0 || y < d.dsy || y >= d.dey) return 0u;
     if (!(d.transformY < z)) return 0u;
@@ -191,6 +192,7 @@ template <int WARP_ROWS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS) k_compose(const __grid_constant__ ComposeParams p) {
     constexpr int COMPOSE_ROWS = COMPOSE_WARPS * WARP_ROWS;
     __shared__ WarpList s_list[COMPOSE_WARPS];
+    __shared__ uint32_t s_xm[COMPOSE_WARPS][WARP_WORDS][32];  // per-lane sprite masks (kept out of registers and out of unrolled code)
 
     const int group = blockIdx.x, view = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -306,16 +308,16 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS) k_compose(cons
 
     // per-lane mask of the warp's sprites that overlap this lane's four columns (lanes then walk
     // different sprites concurrently instead of every lane scanning the whole list)
-    uint32_t xm[WARP_WORDS];
-#pragma unroll
-    for (int wd = 0; wd < WARP_WORDS; wd++) {
+    const int n_words = (n_list + 31) >> 5;
+#pragma unroll 1
+    for (int wd = 0; wd < n_words; wd++) {
         uint32_t m = 0u;
         const int lim = min(32, n_list - wd * 32);
         for (int b = 0; b < lim; b++) {
             const Rect16 rc = wl.rect[wd * 32 + b];
             if (!(x0 + 3 < rc.x0 || x0 >= rc.x1)) m |= 1u << b;
         }
-        xm[wd] = m;
+        s_xm[warp][wd][lane] = m;
     }
 
     // box texel column of each of this lane's pixels
@@ -343,9 +345,9 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS) k_compose(cons
         double zb[4] = {0.0, 0.0, 0.0, 0.0};
         if (n_list > 0) load4(p.zbuf, fi0, vec, nvalid, zb);
         if (sprite_f2b) {
-#pragma unroll
-            for (int wd = WARP_WORDS - 1; wd >= 0; wd--) {
-                uint32_t m = xm[wd];
+#pragma unroll 1
+            for (int wd = n_words - 1; wd >= 0; wd--) {
+                uint32_t m = s_xm[warp][wd][lane];
                 while (m && s_got != full) {
                     const int bit = 31 - __clz(m);
                     m &= ~(1u << bit);
@@ -487,9 +489,9 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS) k_compose(cons
         const unsigned repaint = p.force_painter ? (n_list > 0 ? full : 0u) : s_trans;
         if (repaint) {
             if (!overflow) {
-#pragma unroll
-                for (int wd = 0; wd < WARP_WORDS; wd++) {
-                    uint32_t m = xm[wd];
+#pragma unroll 1
+                for (int wd = 0; wd < n_words; wd++) {
+                    uint32_t m = s_xm[warp][wd][lane];
                     while (m) {
                         const int i = wd * 32 + __ffs(m) - 1;
                         m &= m - 1u;

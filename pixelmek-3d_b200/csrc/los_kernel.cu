@@ -17,6 +17,7 @@ struct LosParams {
     const int4 *seg_irect;  // image.Rect(int(x1),int(y1),int(x2),int(y2)) canonicalised: minx,miny,maxx,maxy
     const int32_t *cell_start;
     const int32_t *cell_items;
+    const int4 *cell_rec;  // per bin cell: x = count, y/z/w = the first three candidate ids (count <= 3) or y = offset into cell_items
     int64_t n;
     int n_segs, bin_x0, bin_y0, bin_w, bin_h;
     // move queries
@@ -43,6 +44,38 @@ __device__ __forceinline__ bool line_intersection(const double4 &a, const double
     return true;
 }
 
+// Same boolean as line_intersection(..., nullptr, nullptr) without the two divisions.
+// With denom, tNum, uNum finite and their exponents within 2^+-500 the quotients cannot overflow or
+// underflow, so for t = RN(tNum/denom):  t < 0  <=>  tNum != 0 and the signs differ;
+// t > 1  <=>  |tNum| > |denom|  (two doubles a > b satisfy a/b >= 1 + ulp(b)/b > 1 + 2^-53, which rounds to at
+// least 1 + 2^-52; a <= b gives a quotient <= 1).  Anything else (zero / tiny / huge / inf / NaN operands,
+// where Go's comparisons with NaN all read false) takes the reference arithmetic.
+__device__ __forceinline__ bool exp_mid(double v) {
+    const unsigned e = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu;
+    return e - 523u <= 1000u;
+}
+__device__ __forceinline__ bool segments_intersect(const double4 &a, const double4 &b) {
+    const double x1 = a.x, y1 = a.y, x2 = a.z, y2 = a.w;
+    const double x3 = b.x, y3 = b.y, x4 = b.z, y4 = b.w;
+    const double denom = (x1 - x2) * (y3 - y4) - (y1 - y2) * (x3 - x4);
+    const double tNum = (x1 - x3) * (y3 - y4) - (y1 - y3) * (x3 - x4);
+    const double uNum = -((x1 - x2) * (y1 - y3) - (y1 - y2) * (x1 - x3));
+    if (exp_mid(denom) && (tNum == 0 || exp_mid(tNum)) && (uNum == 0 || exp_mid(uNum))) {
+        const double ad = fabs(denom);
+        if (tNum != 0 && ((tNum < 0) != (denom < 0))) return false;
+        if (fabs(tNum) > ad) return false;
+        if (uNum != 0 && ((uNum < 0) != (denom < 0))) return false;
+        if (fabs(uNum) > ad) return false;
+        return true;
+    }
+    if (denom == 0) return false;
+    const double t = tNum / denom;
+    if (t > 1 || t < 0) return false;
+    const double u = uNum / denom;
+    if (u > 1 || u < 0) return false;
+    return true;
+}
+
 __device__ __forceinline__ int4 go_rect(int64_t x0, int64_t y0, int64_t x1, int64_t y1) {
     if (x0 > x1) { int64_t t = x0; x0 = x1; x1 = t; }
     if (y0 > y1) { int64_t t = y0; y0 = y1; y1 = t; }
@@ -65,7 +98,7 @@ __device__ bool any_hit(const LosParams &p, const double4 &ray) {
         const double2 s01 = __ldg(reinterpret_cast<const double2 *>(p.segs + id));
         const double2 s23 = __ldg(reinterpret_cast<const double2 *>(p.segs + id) + 1);
         const double4 sg = make_double4(s01.x, s01.y, s23.x, s23.y);
-        return line_intersection(ray, sg, nullptr, nullptr);
+        return segments_intersect(ray, sg);
     };
 
     // rays that are not finite or leave the binned area by more than a cell: brute force
@@ -107,11 +140,124 @@ __device__ bool any_hit(const LosParams &p, const double4 &ray) {
     return false;
 }
 
-__global__ void __launch_bounds__(256) k_los(LosParams p) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.n) return;
-    const double4 ray = p.rays[i];
-    p.out_flag[i] = any_hit<true>(p, ray) ? 0 : 1;
+// Persistent line-of-sight kernel.  Rays end after very different numbers of cells (most are blocked
+// within a few cells, the visible ones cross the whole map), so a warp owns a contiguous range of rays
+// and a lane that finishes its ray takes the next one of the range (refill once >= 8 lanes are idle)
+// instead of idling until the slowest ray of a fixed group of 32 is done.  One loop iteration = one bin cell.
+#define LOS_THREADS 256
+__global__ void __launch_bounds__(LOS_THREADS) k_los(LosParams p, long long rays_per_warp) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_id = (long long)blockIdx.x * (LOS_THREADS / 32) + (threadIdx.x >> 5);
+    long long next = warp_id * rays_per_warp;                      // warp-uniform: next unassigned ray
+    const long long end = min(next + rays_per_warp, (long long)p.n);
+    if (next >= end) return;
+
+    const double gx0 = (double)p.bin_x0, gy0 = (double)p.bin_y0;
+    const double gx1 = (double)(p.bin_x0 + p.bin_w), gy1 = (double)(p.bin_y0 + p.bin_h);
+
+    bool active = false;
+    long long idx = 0;
+    double4 ray = make_double4(0, 0, 0, 0);
+    int4 lr = make_int4(0, 0, 0, 0);
+    int cx = 0, cy = 0, ex = 0, ey = 0, sx = 1, sy = 1, steps = 0;
+    int4 cur = make_int4(0, -1, -1, -1);  // record of the current cell
+    double tx = 0, ty = 0, inv_dx = 0, inv_dy = 0;
+
+    auto test = [&](int id) -> bool {
+        const int4 br = __ldg(p.seg_irect + id);  // lineOfSight's integer bounding-rect pre-filter, as written
+        if ((br.x > lr.z && br.y > lr.w) || (br.z < lr.x && br.w < lr.y)) return false;
+        const double2 s01 = __ldg(reinterpret_cast<const double2 *>(p.segs + id));
+        const double2 s23 = __ldg(reinterpret_cast<const double2 *>(p.segs + id) + 1);
+        return segments_intersect(ray, make_double4(s01.x, s01.y, s23.x, s23.y));
+    };
+
+    for (;;) {
+        // ---- refill idle lanes from the warp's range
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle && next < end && (__popc(idle) >= 8 || idle == 0xffffffffu)) {
+            const long long mine = next + __popc(idle & ((1u << lane) - 1u));
+            next += __popc(idle);
+            if (!active && mine < end) {
+                idx = mine;
+                ray = p.rays[idx];
+                lr = go_rect(go_int(ray.x), go_int(ray.y), go_int(ray.z), go_int(ray.w));
+                const bool inside = ray.x >= gx0 && ray.x < gx1 && ray.z >= gx0 && ray.z < gx1 && ray.y >= gy0 &&
+                                    ray.y < gy1 && ray.w >= gy0 && ray.w < gy1;
+                if (!inside) {
+                    // not finite, or leaves the binned area: every segment is a candidate
+                    bool hit = false;
+                    for (int id = 0; id < p.n_segs && !hit; id++) hit = test(id);
+                    p.out_flag[idx] = hit ? 0 : 1;
+                } else {
+                    const double fx = floor(ray.x), fy = floor(ray.y);
+                    cx = (int)fx - p.bin_x0; cy = (int)fy - p.bin_y0;
+                    ex = (int)floor(ray.z) - p.bin_x0; ey = (int)floor(ray.w) - p.bin_y0;
+                    const double dx = ray.z - ray.x, dy = ray.w - ray.y;
+                    sx = dx > 0 ? 1 : -1; sy = dy > 0 ? 1 : -1;
+                    inv_dx = dx != 0 ? 1.0 / fabs(dx) : 0.0;
+                    inv_dy = dy != 0 ? 1.0 / fabs(dy) : 0.0;
+                    tx = dx != 0 ? (dx > 0 ? (fx + 1.0 - ray.x) : (ray.x - fx)) * inv_dx : 1e300;
+                    ty = dy != 0 ? (dy > 0 ? (fy + 1.0 - ray.y) : (ray.y - fy)) * inv_dy : 1e300;
+                    steps = abs(ex - cx) + abs(ey - cy);
+                    cur = __ldg(p.cell_rec + cy * p.bin_w + cx);
+                    active = true;
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) {
+            if (next >= end) break;
+            continue;
+        }
+        // ---- one bin cell of every active ray
+        if (active) {
+            // the step decision needs only tx/ty, so the NEXT cell's record is requested before this
+            // cell's candidates are tested; candidates are fetched three at a time (independent loads)
+            const bool more = steps > 0;
+            int ncx = cx, ncy = cy;
+            double ntx = tx, nty = ty;
+            if (more) {
+                // never step past the target cell on either axis: keeps the walk inside the bins
+                if ((tx < ty && cx != ex) || cy == ey) { ntx += inv_dx; ncx += sx; }
+                else { nty += inv_dy; ncy += sy; }
+            }
+            const int4 rec = cur;
+            int4 nrec = make_int4(0, -1, -1, -1);
+            if (more) nrec = __ldg(p.cell_rec + ncy * p.bin_w + ncx);
+            bool hit = false;
+            for (int base = 0; base < rec.x && !hit; base += 3) {
+                int ids[3];
+                if (rec.x <= 3) { ids[0] = rec.y; ids[1] = rec.z; ids[2] = rec.w; }
+                else {
+#pragma unroll
+                    for (int k = 0; k < 3; k++) ids[k] = base + k < rec.x ? __ldg(p.cell_items + rec.y + base + k) : -1;
+                }
+                int4 br[3];
+                double2 s01[3], s23[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const int id = ids[k] < 0 ? 0 : ids[k];
+                    br[k] = __ldg(p.seg_irect + id);
+                    s01[k] = __ldg(reinterpret_cast<const double2 *>(p.segs + id));
+                    s23[k] = __ldg(reinterpret_cast<const double2 *>(p.segs + id) + 1);
+                }
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    if (hit || ids[k] < 0 || base + k >= rec.x) continue;
+                    // lineOfSight's integer bounding-rect pre-filter, as written
+                    if ((br[k].x > lr.z && br[k].y > lr.w) || (br[k].z < lr.x && br[k].w < lr.y)) continue;
+                    hit = segments_intersect(ray, make_double4(s01[k].x, s01[k].y, s23[k].x, s23[k].y));
+                }
+            }
+            if (hit || !more) {
+                p.out_flag[idx] = hit ? 0 : 1;
+                active = false;
+            } else {
+                steps--;
+                cx = ncx; cy = ncy; tx = ntx; ty = nty;
+                cur = nrec;
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) k_move(LosParams p) {
@@ -188,6 +334,7 @@ static int run_batch(pm3d_ctx *ctx, bool is_move, const double *rays, int64_t n,
     p.seg_irect = ctx->seg_irect;
     p.cell_start = ctx->cell_start;
     p.cell_items = ctx->cell_items;
+    p.cell_rec = ctx->cell_rec;
     p.n = n;
     p.n_segs = ctx->n_segs; p.bin_x0 = ctx->bin_x0; p.bin_y0 = ctx->bin_y0; p.bin_w = ctx->bin_w; p.bin_h = ctx->bin_h;
     p.grid0 = ctx->grid; p.map_w = ctx->map_w; p.map_h = ctx->map_h; p.clip = clip;
@@ -195,8 +342,17 @@ static int run_batch(pm3d_ctx *ctx, bool is_move, const double *rays, int64_t n,
     p.out_pos = (double2 *)d_pos;
     const int64_t blocks = (n + 255) / 256;
     if (blocks > 0x7fffffffll) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "batch too large");
-    if (is_move) k_move<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p);
-    else k_los<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p);
+    if (is_move) {
+        k_move<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p);
+    } else {
+        // persistent: 8 CTAs per SM, every warp owns a contiguous range of rays (at least 32)
+        long long warps = (long long)ctx->sm_count * 8 * (LOS_THREADS / 32);
+        long long per_warp = (n + warps - 1) / warps;
+        if (per_warp < 32) per_warp = 32;
+        warps = (n + per_warp - 1) / per_warp;
+        const unsigned los_blocks = (unsigned)((warps + LOS_THREADS / 32 - 1) / (LOS_THREADS / 32));
+        k_los<<<los_blocks, LOS_THREADS, 0, ctx->stream>>>(p, per_warp);
+    }
     ctx->launches++;
     PM3D_CUDA(ctx, cudaGetLastError());
     if (!out_dev) {

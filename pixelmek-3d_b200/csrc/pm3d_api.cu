@@ -89,7 +89,7 @@ void pm3d_destroy(pm3d_ctx *ctx) {
                     ctx->views, ctx->col_span, ctx->col_tt, ctx->col_ps, ctx->flo_xw, ctx->flo_yw, ctx->flo_dw, ctx->flo_fs, ctx->agg, ctx->zbuf, ctx->row_rec, ctx->dbg_cols, ctx->sprites,
                     ctx->sprite_offset, ctx->draw_rec, ctx->n_draw, ctx->bin_list, ctx->bin_rect, ctx->bin_count, ctx->rects,
                     ctx->conv, ctx->frame, ctx->checksums, ctx->segs, ctx->seg_irect, ctx->cell_start,
-                    ctx->cell_items, ctx->io_a, ctx->io_b, ctx->io_c, ctx->flush_buf};
+                    ctx->cell_items, ctx->cell_rec, ctx->io_a, ctx->io_b, ctx->io_c, ctx->flush_buf};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (ctx->stage) cudaFreeHost(ctx->stage);
@@ -535,16 +535,38 @@ int pm3d_upload_segments(pm3d_ctx *ctx, const double *xyxy, int n) {
     const int bw = (int)floor(maxx) + 3 - x0, bh = (int)floor(maxy) + 3 - y0;
     std::vector<int32_t> count((size_t)bw * bh + 1, 0);
     std::vector<int4> irect(std::max(n, 1));
+    // A segment is registered in every 1x1 cell whose box, grown by BIN_EPS on each side, it touches.
+    // BIN_EPS is ~8 orders of magnitude above the rounding error of the device's cell walk and of the
+    // predicate at map-scale coordinates, so any segment the exact predicate could report against a ray
+    // is listed in a cell that ray's walk visits (k_los); it is far below a cell, so lists stay short.
+    const double BIN_EPS = 1e-3;
     auto cell_range = [&](const double *s, int &cx0, int &cy0, int &cx1, int &cy1) {
-        cx0 = (int)floor(std::min(s[0], s[2])) - 1 - x0; cx1 = (int)floor(std::max(s[0], s[2])) + 1 - x0;
-        cy0 = (int)floor(std::min(s[1], s[3])) - 1 - y0; cy1 = (int)floor(std::max(s[1], s[3])) + 1 - y0;
+        cx0 = (int)floor(std::min(s[0], s[2]) - BIN_EPS) - x0; cx1 = (int)floor(std::max(s[0], s[2]) + BIN_EPS) - x0;
+        cy0 = (int)floor(std::min(s[1], s[3]) - BIN_EPS) - y0; cy1 = (int)floor(std::max(s[1], s[3]) + BIN_EPS) - y0;
+    };
+    // conservative segment-vs-grown-box overlap (Liang-Barsky on the infinite precision-free side: any doubt keeps it)
+    auto touches = [&](const double *s, int cx, int cy) -> bool {
+        const double bx0 = (double)(cx + x0) - 2 * BIN_EPS, bx1 = (double)(cx + x0) + 1.0 + 2 * BIN_EPS;
+        const double by0 = (double)(cy + y0) - 2 * BIN_EPS, by1 = (double)(cy + y0) + 1.0 + 2 * BIN_EPS;
+        double t0 = 0.0, t1 = 1.0;
+        const double dx = s[2] - s[0], dy = s[3] - s[1];
+        const double pq[4][2] = {{-dx, s[0] - bx0}, {dx, bx1 - s[0]}, {-dy, s[1] - by0}, {dy, by1 - s[1]}};
+        for (int k = 0; k < 4; k++) {
+            const double pp = pq[k][0], q = pq[k][1];
+            if (pp == 0) { if (q < 0) return false; continue; }
+            const double r = q / pp;
+            if (pp < 0) { if (r > t1 + 1e-9) return false; if (r > t0) t0 = r; }
+            else { if (r < t0 - 1e-9) return false; if (r < t1) t1 = r; }
+        }
+        return true;
     };
     for (int i = 0; i < n; i++) {
         const double *s = xyxy + (size_t)i * 4;
         int cx0, cy0, cx1, cy1;
         cell_range(s, cx0, cy0, cx1, cy1);
         for (int cy = cy0; cy <= cy1; cy++)
-            for (int cx = cx0; cx <= cx1; cx++) count[(size_t)cy * bw + cx + 1]++;
+            for (int cx = cx0; cx <= cx1; cx++)
+                if (touches(s, cx, cy)) count[(size_t)cy * bw + cx + 1]++;
         int64_t ax = host_go_int(s[0]), ay = host_go_int(s[1]), bx = host_go_int(s[2]), by = host_go_int(s[3]);
         if (ax > bx) std::swap(ax, bx);
         if (ay > by) std::swap(ay, by);
@@ -558,13 +580,22 @@ int pm3d_upload_segments(pm3d_ctx *ctx, const double *xyxy, int n) {
         int cx0, cy0, cx1, cy1;
         cell_range(s, cx0, cy0, cx1, cy1);
         for (int cy = cy0; cy <= cy1; cy++)
-            for (int cx = cx0; cx <= cx1; cx++) items[fill[(size_t)cy * bw + cx]++] = i;
+            for (int cx = cx0; cx <= cx1; cx++)
+                if (touches(s, cx, cy)) items[fill[(size_t)cy * bw + cx]++] = i;
     }
     int rc;
     if ((rc = dev_realloc(ctx, &ctx->segs, (size_t)std::max(n, 1) * 4))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->seg_irect, (size_t)std::max(n, 1)))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->cell_start, count.size()))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->cell_items, items.size()))) return rc;
+    std::vector<int4> recs((size_t)bw * bh);
+    for (size_t c = 0; c < (size_t)bw * bh; c++) {
+        const int b = count[c], e = count[c + 1], k = e - b;
+        recs[c] = k <= 3 ? make_int4(k, k > 0 ? items[b] : -1, k > 1 ? items[b + 1] : -1, k > 2 ? items[b + 2] : -1)
+                         : make_int4(k, b, 0, 0);
+    }
+    if ((rc = dev_realloc(ctx, &ctx->cell_rec, recs.size()))) return rc;
+    PM3D_CUDA(ctx, cudaMemcpy(ctx->cell_rec, recs.data(), recs.size() * sizeof(int4), cudaMemcpyHostToDevice));
     if (n) {
         PM3D_CUDA(ctx, cudaMemcpy(ctx->segs, xyxy, (size_t)n * 32, cudaMemcpyHostToDevice));
         PM3D_CUDA(ctx, cudaMemcpy(ctx->seg_irect, irect.data(), (size_t)n * sizeof(int4), cudaMemcpyHostToDevice));

@@ -135,6 +135,7 @@ struct pm3d_ctx {
     int n_segs = 0;
     int32_t *cell_start = nullptr;   // CSR over bin cells
     int32_t *cell_items = nullptr;
+    int4 *cell_rec = nullptr;        // count + first three candidate ids (or offset) per bin cell
     int bin_x0 = 0, bin_y0 = 0, bin_w = 0, bin_h = 0;
     void *io_a = nullptr, *io_b = nullptr, *io_c = nullptr;  // batch staging on device
     size_t io_a_bytes = 0, io_b_bytes = 0, io_c_bytes = 0;

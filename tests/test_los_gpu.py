@@ -135,3 +135,46 @@ def test_full_size_16m_rays_properties(gpu_ctx):
     assert np.array_equal(gpu_ctx.los_batch(rays[:half]), full[:half])
     assert np.array_equal(gpu_ctx.los_batch(rays[half:]), full[half:])
     assert abs(float(full.mean()) - float(full[::256].mean())) < 0.01
+
+
+def test_division_free_predicate_matches_reference_arithmetic(gpu_ctx):
+    """The device decides t,u in [0,1] from signs and magnitudes instead of dividing (los_kernel.cu
+    segments_intersect).  Adversarial inputs: endpoints exactly on segments (t or u == 0 or 1), collinear and
+    parallel rays, one-ulp perturbations around touching configurations, huge / tiny / zero / non-finite
+    coordinates (where it must fall back to the reference arithmetic, including Go's NaN comparisons)."""
+    segs = np.array([
+        [2.0, 1.0, 2.0, 5.0],          # vertical
+        [1.0, 3.0, 6.0, 3.0],          # horizontal
+        [0.5, 0.5, 4.5, 6.5],          # diagonal
+        [3.0, 3.0, 3.0, 3.0],          # degenerate point segment
+        [7.25, 0.125, 7.25, 0.375],    # tiny
+    ])
+    rng = W.SplitMix64(2024)
+    rays = []
+    for sg in segs:
+        x3, y3, x4, y4 = sg
+        for a in (0.0, 1.0, 0.5, 0.25, 1.0 / 3.0):
+            px, py = x3 + a * (x4 - x3), y3 + a * (y4 - y3)    # a point on the segment
+            for dxy in ((1.0, 0.0), (0.0, 1.0), (1.0, 1.0), (-2.5, 0.75), (1e-9, 1.0)):
+                for k in (1.0, 1e-3, 1e3):
+                    ex, ey = px + k * dxy[0], py + k * dxy[1]
+                    rays += [[px, py, ex, ey], [ex, ey, px, py]]                     # starts / ends exactly on it
+                    rays += [[np.nextafter(px, 9), py, ex, ey], [np.nextafter(px, -9), py, ex, ey],
+                             [px, np.nextafter(py, 9), ex, ey], [ex, ey, px, np.nextafter(py, -9)]]
+                    rays += [[2 * px - ex, 2 * py - ey, ex, ey]]                     # passes through it
+        rays += [[x3, y3, x4, y4], [x4, y4, x3, y3], [x3 - 1, y3 - 1, x3 - 1, y3 - 1]]  # collinear / identical / point
+    u = rng.uniform(4 * 4000).reshape(-1, 4)
+    rays += (u * 8.0).tolist()
+    rays += (np.round(u[:1000] * 16) / 2.0).tolist()                              # lattice points: many exact touches
+    big = [1e200, -1e200, 1e-200, -1e-200, 1e308, 5e-324, 0.0, -0.0, float("inf"), -float("inf"), float("nan")]
+    for i, bx in enumerate(big):
+        for by in big[i::3]:
+            rays += [[bx, by, 3.0, 3.0], [3.0, 2.0, bx, by], [bx, 2.0, by, 4.0], [2.0, bx, 2.0, by]]
+    rays = np.array(rays, dtype=np.float64)
+    gpu_ctx.upload_segments(segs)
+    got = gpu_ctx.los_batch(rays)
+    with np.errstate(all="ignore"):
+        want = O.los_batch(segs, rays)
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, f"{len(bad)} mismatches, first: {rays[bad[:5]].tolist()} gpu {got[bad[:5]].tolist()} oracle {want[bad[:5]].tolist()}"
+    assert 0 < int(want.sum()) < len(want)

@@ -9,6 +9,8 @@
 // binary64) on the candidates.  The boolean per ray is therefore the brute-force answer:
 // an intersection point lies on the query segment, hence inside a crossed cell (or, at a
 // lattice corner, a neighbour of one), and the dilation covers that neighbour.
+#include <stdlib.h>
+
 #include "pm3d_internal.cuh"
 
 struct LosParams {
@@ -145,7 +147,7 @@ __device__ bool any_hit(const LosParams &p, const double4 &ray) {
 // and a lane that finishes its ray takes the next one of the range (refill once >= 8 lanes are idle)
 // instead of idling until the slowest ray of a fixed group of 32 is done.  One loop iteration = one bin cell.
 #define LOS_THREADS 256
-__global__ void __launch_bounds__(LOS_THREADS) k_los(LosParams p, long long rays_per_warp) {
+__global__ void __launch_bounds__(LOS_THREADS, 3) k_los(LosParams p, long long rays_per_warp) {
     const int lane = threadIdx.x & 31;
     const long long warp_id = (long long)blockIdx.x * (LOS_THREADS / 32) + (threadIdx.x >> 5);
     long long next = warp_id * rays_per_warp;                      // warp-uniform: next unassigned ray
@@ -346,7 +348,11 @@ static int run_batch(pm3d_ctx *ctx, bool is_move, const double *rays, int64_t n,
         k_move<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p);
     } else {
         // persistent: 8 CTAs per SM, every warp owns a contiguous range of rays (at least 32)
-        long long warps = (long long)ctx->sm_count * 8 * (LOS_THREADS / 32);
+        int per_sm = 2;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_los, LOS_THREADS, 0);
+        if (per_sm < 1) per_sm = 1;
+        if (const char *e = getenv("PM3D_LOS_WAVES")) per_sm *= atoi(e);  // tuning override (tools/)
+        long long warps = (long long)ctx->sm_count * per_sm * (LOS_THREADS / 32);
         long long per_warp = (n + warps - 1) / warps;
         if (per_warp < 32) per_warp = 32;
         warps = (n + per_warp - 1) / per_warp;

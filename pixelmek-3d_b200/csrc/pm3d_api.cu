@@ -89,7 +89,7 @@ void pm3d_destroy(pm3d_ctx *ctx) {
                     ctx->views, ctx->col_span, ctx->col_tt, ctx->col_ps, ctx->flo_xw, ctx->flo_yw, ctx->flo_dw, ctx->flo_fs, ctx->agg, ctx->zbuf, ctx->row_rec, ctx->dbg_cols, ctx->sprites,
                     ctx->sprite_offset, ctx->draw_rec, ctx->n_draw, ctx->bin_list, ctx->bin_rect, ctx->bin_count, ctx->rects,
                     ctx->conv, ctx->frame, ctx->checksums, ctx->segs, ctx->seg_irect, ctx->cell_start,
-                    ctx->cell_items, ctx->cell_rec, ctx->io_a, ctx->io_b, ctx->io_c, ctx->flush_buf};
+                    ctx->cell_items, ctx->cell_rec, ctx->inbuf, ctx->io_a, ctx->io_b, ctx->io_c, ctx->flush_buf};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (ctx->stage) cudaFreeHost(ctx->stage);
@@ -447,9 +447,14 @@ int pm3d_render(pm3d_ctx *ctx, const pm3d_view *views, int n_views, const pm3d_s
     memcpy(st, views, vb);
     memcpy(st + vb, sprite_offset, ob);
     if (sb) memcpy(st + vb + ob_pad, sprites, sb);
-    PM3D_CUDA(ctx, cudaMemcpyAsync(ctx->views, st, vb, cudaMemcpyHostToDevice, ctx->stream));
-    PM3D_CUDA(ctx, cudaMemcpyAsync(ctx->sprite_offset, st + vb, ob, cudaMemcpyHostToDevice, ctx->stream));
-    if (sb) PM3D_CUDA(ctx, cudaMemcpyAsync(ctx->sprites, st + vb + ob_pad, sb, cudaMemcpyHostToDevice, ctx->stream));
+    // one H2D for the whole per-frame input block: [views | sprite_offset | sprites]
+    if (ctx->inbuf_bytes < vb + ob_pad + sb) {
+        if (ctx->inbuf) PM3D_CUDA(ctx, cudaFree(ctx->inbuf));
+        ctx->inbuf = nullptr;
+        ctx->inbuf_bytes = std::max<size_t>(vb + ob_pad + sb, (size_t)1 << 16) * 2;
+        PM3D_CUDA(ctx, cudaMalloc((void **)&ctx->inbuf, ctx->inbuf_bytes));
+    }
+    PM3D_CUDA(ctx, cudaMemcpyAsync(ctx->inbuf, st, vb + ob_pad + sb, cudaMemcpyHostToDevice, ctx->stream));
     PM3D_CUDA(ctx, cudaEventRecord(ctx->stage_ev, ctx->stream));
 
     const bool piped = ctx->ring_n > 1 && out_rgba && !(flags & PM3D_OUT_DEVICE) && (flags & PM3D_NO_SYNC);
@@ -457,9 +462,16 @@ int pm3d_render(pm3d_ctx *ctx, const pm3d_view *views, int n_views, const pm3d_s
     uint8_t *target = (out_rgba && (flags & PM3D_OUT_DEVICE)) ? out_rgba : (piped ? ctx->frame_ring[slot] : ctx->frame);
     // the slot's previous frame must have left the device before the compose kernel overwrites it
     if (piped) PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0));
-    ctx->cur_views = ctx->views; ctx->cur_sprites = ctx->sprites; ctx->cur_offset = ctx->sprite_offset;
+    ctx->cur_views = (const pm3d_view *)ctx->inbuf;
+    ctx->cur_offset = (const int32_t *)(ctx->inbuf + vb);
+    ctx->cur_sprites = (const pm3d_sprite *)(ctx->inbuf + vb + ob_pad);
     if ((rc = render_core(ctx, n_views, n_sprites, target))) return rc;
 
+    // the small results first: they must not queue behind the frame on the D2H copy engine
+    if (out_rects && n_sprites)
+        PM3D_CUDA(ctx, cudaMemcpyAsync(out_rects, ctx->rects, (size_t)n_sprites * sizeof(pm3d_rect), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_conv)
+        PM3D_CUDA(ctx, cudaMemcpyAsync(out_conv, ctx->conv, (size_t)n_views * sizeof(pm3d_convergence), cudaMemcpyDeviceToHost, ctx->stream));
     const size_t fb = (size_t)n_views * ctx->w * ctx->h * 4;
     if (piped) {
         PM3D_CUDA(ctx, cudaEventRecord(ctx->ev_rendered[slot], ctx->stream));
@@ -470,10 +482,6 @@ int pm3d_render(pm3d_ctx *ctx, const pm3d_view *views, int n_views, const pm3d_s
     } else if (out_rgba && !(flags & PM3D_OUT_DEVICE)) {
         PM3D_CUDA(ctx, cudaMemcpyAsync(out_rgba, ctx->frame, fb, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    if (out_rects && n_sprites)
-        PM3D_CUDA(ctx, cudaMemcpyAsync(out_rects, ctx->rects, (size_t)n_sprites * sizeof(pm3d_rect), cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_conv)
-        PM3D_CUDA(ctx, cudaMemcpyAsync(out_conv, ctx->conv, (size_t)n_views * sizeof(pm3d_convergence), cudaMemcpyDeviceToHost, ctx->stream));
     if (!(flags & PM3D_NO_SYNC)) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PM3D_OK;
 }

@@ -124,6 +124,9 @@ struct pm3d_ctx {
     cudaEvent_t *kt_ev = nullptr;  // [kt_cap][3][2]
     int kt_cap = 0, kt_n = 0, kt_on = 0;
 
+    uint8_t *inbuf = nullptr;        // device copy of one call's [views | sprite_offset | sprites]
+    size_t inbuf_bytes = 0;
+
     // pinned staging for host-side arguments
     void *stage = nullptr;
     size_t stage_bytes = 0;

@@ -22,6 +22,7 @@ class Context:
         self.scene: SceneData | None = None
         self.w = self.h_px = 0
         self._keep = []
+        self._no_sprites = np.zeros(0, dtype=SPRITE_DTYPE)
 
     # ------------------------------------------------------------------ plumbing
     def _check(self, rc: int, what: str):
@@ -87,19 +88,23 @@ class Context:
                out: np.ndarray | None = None):
         """Camera.Update + Draw for len(views) views.  Returns dict(rgba, rects, conv).
         `out` (optional) is a host buffer for the frames, e.g. pinned memory from host_alloc."""
-        views = np.ascontiguousarray(views, dtype=VIEW_DTYPE).reshape(-1)
+        if not (isinstance(views, np.ndarray) and views.dtype == VIEW_DTYPE and views.flags.c_contiguous):
+            views = np.ascontiguousarray(views, dtype=VIEW_DTYPE)
+        views = views.reshape(-1)
         nv = len(views)
         if sprites is None:
-            sprites = np.zeros(0, dtype=SPRITE_DTYPE)
-        sprites = np.ascontiguousarray(sprites, dtype=SPRITE_DTYPE).reshape(-1)
+            sprites = self._no_sprites
+        elif not (isinstance(sprites, np.ndarray) and sprites.dtype == SPRITE_DTYPE and sprites.flags.c_contiguous):
+            sprites = np.ascontiguousarray(sprites, dtype=SPRITE_DTYPE).reshape(-1)
         if sprite_offset is None:
             if nv != 1:
                 raise Pm3dError("sprite_offset is required for more than one view")
             sprite_offset = np.array([0, len(sprites)], dtype=np.int32)
-        sprite_offset = np.ascontiguousarray(sprite_offset, dtype=np.int32)
+        elif not (isinstance(sprite_offset, np.ndarray) and sprite_offset.dtype == np.int32 and sprite_offset.flags.c_contiguous):
+            sprite_offset = np.ascontiguousarray(sprite_offset, dtype=np.int32)
         ns = int(sprite_offset[-1])
-        rects = np.zeros((max(ns, 1), 4), dtype=np.int32)
-        conv = np.zeros(nv, dtype=CONV_DTYPE)
+        rects = np.empty((max(ns, 1), 4), dtype=np.int32)
+        conv = np.empty(nv, dtype=CONV_DTYPE)
         flags = 0
         rgba = None
         out_p = None

@@ -303,3 +303,26 @@ def test_camera_mirror_drives_the_path(gpu_ctx):
     c.SetViewSize(200, 120)
     c.Update(sprites)
     assert c.Draw().shape == (120, 200, 4)
+
+
+def test_pipelined_frames_equal_synchronous_frames(gpu_ctx):
+    """PM3D_OPT_PIPELINE: NO_SYNC renders into host memory overlap the frame's D2H with the next
+    frame's kernels; after pm3d_sync every frame, rect and convergence must equal the synchronous result."""
+    c = W.config_c2(w=640, h=360, n_poses=7)
+    ctx = gpu_ctx
+    ctx.upload_scene(c["scene"])
+    ctx.set_view(640, 360, 1, 200)
+    off = c["offsets"]
+    want = [ctx.render(c["views"][i:i + 1], c["sprites"][off[i]:off[i + 1]]) for i in range(7)]
+    want = [{k: v.copy() for k, v in r.items()} for r in want]
+    ctx.set_option(pm3d._lib.OPT_PIPELINE, 3)
+    try:
+        bufs = [ctx.host_alloc(640 * 360 * 4, np.uint8, (1, 360, 640, 4)) for _ in range(7)]
+        got = [ctx.render(c["views"][i:i + 1], c["sprites"][off[i]:off[i + 1]], out=bufs[i], no_sync=True) for i in range(7)]
+        ctx.sync()
+        for i in range(7):
+            assert np.array_equal(got[i]["rgba"], want[i]["rgba"]), f"frame {i}"
+            assert np.array_equal(got[i]["rects"], want[i]["rects"])
+            assert np.array_equal(got[i]["conv"]["sprite"], want[i]["conv"]["sprite"])
+    finally:
+        ctx.set_option(pm3d._lib.OPT_PIPELINE, 1)

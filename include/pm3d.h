@@ -222,6 +222,11 @@ int pm3d_ktimer_collect(pm3d_ctx *ctx, float *out_ms, int cap_frames);
 int64_t pm3d_launch_count(const pm3d_ctx *ctx);
 /* write `bytes` of a scratch buffer (> L2) to flush the L2 between timed iterations */
 int pm3d_flush_l2(pm3d_ctx *ctx);
+/* Device self-check of the division-free quotient the floor cast uses for weight = currentDist / distWall
+ * (Go: one float64 division per floor pixel): blocks*256 threads each compare `iters` operand pairs
+ * (random, adversarial and path-range) bit for bit against the IEEE division.  out_mismatches must read 0. */
+int pm3d_selfcheck_division(pm3d_ctx *ctx, uint64_t seed, int blocks, int iters, uint64_t *out_mismatches,
+                            uint64_t *out_tested);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ struct CastParams {
     int2 *col_span;
     uint2 *col_tt;
     ulonglong2 *col_ps;
-    double *flo_xw, *flo_yw, *flo_dw;
+    double *flo_xw, *flo_yw, *flo_dw, *flo_rc;
     int32_t *flo_fs;
     int4 *agg;
     double *zbuf;
@@ -177,6 +177,7 @@ __device__ __forceinline__ void cast_ray(const CastParams &p, const int view, co
             const size_t fi = (size_t)view * p.w + x;
             p.zbuf[fi] = perpWallDist;
             p.flo_xw[fi] = fxw; p.flo_yw[fi] = fyw; p.flo_dw[fi] = perpWallDist; p.flo_fs[fi] = fs;
+            p.flo_rc[fi] = exp_mid(perpWallDist) ? 1.0 / perpWallDist : 0.0;
             agg_fs_min = fs; agg_fs_max = fs;
         }
     }

@@ -41,7 +41,7 @@ struct ComposeParams {
     const int2 *col_span;
     const uint2 *col_tt;
     const ulonglong2 *col_ps;
-    const double *flo_xw, *flo_yw, *flo_dw;
+    const double *flo_xw, *flo_yw, *flo_dw, *flo_rc;
     const int32_t *flo_fs;
     const int4 *agg;
     const double *zbuf;
@@ -99,10 +99,15 @@ __device__ __forceinline__ uint32_t floor_tint(uint32_t px, uint32_t t) {
 }
 
 // ---- floor layer of one pixel given its column parameters: texel already tinted (>>8), 0 if none
-__device__ __forceinline__ uint32_t floor_texel(const ComposeParams &p, double fxw, double fyw, double dw, int fs,
+// weight := currentDist / distWall, correctly rounded either way
+__device__ __forceinline__ double floor_weight(const RowRec &r, double dw, double rc) {
+    return ((r.info & 0x20000000u) && rc != 0.0) ? div_by_rcp(r.cd, dw, rc) : r.cd / dw;
+}
+
+__device__ __forceinline__ uint32_t floor_texel(const ComposeParams &p, double fxw, double fyw, double dw, double rc, int fs,
                                                 const RowRec &r, double posx, double posy, int y) {
     if (y < fs || !(r.info & 0x80000000u)) return 0u;
-    const double weight = r.cd / dw;
+    const double weight = floor_weight(r, dw, rc);
     const double fx = weight * fxw + (1.0 - weight) * posx;
     const double fy = weight * fyw + (1.0 - weight) * posy;
     if (!(fx >= 0.0) || !(fy >= 0.0)) return 0u;
@@ -153,7 +158,7 @@ __device__ __noinline__ uint32_t background_painter(const ComposeParams &p, int 
         }
     }
     const size_t fi = (size_t)view * p.w + x;
-    dst = blend_over(dst, floor_texel(p, p.flo_xw[fi], p.flo_yw[fi], p.flo_dw[fi], p.flo_fs[fi], r, c.pos_x, c.pos_y, y),
+    dst = blend_over(dst, floor_texel(p, p.flo_xw[fi], p.flo_yw[fi], p.flo_dw[fi], p.flo_rc[fi], p.flo_fs[fi], r, c.pos_x, c.pos_y, y),
                      0xffffffffu);
     return dst;
 }
@@ -389,14 +394,15 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS) k_compose(cons
             // every pixel of this lane is covered by an opaque sprite texel
         } else if (fast_ok && y >= fs_max && (r.info & 0x80000000u)) {
             // ---------- every pixel of this lane is a floor candidate: four casts in straight line
-            double cw[4], cx[4], cy[4], fx[4], fy[4];
+            double cw[4], cr[4], cx[4], cy[4], fx[4], fy[4];
             load4(p.flo_dw, fi0, vec, 4, cw);
+            load4(p.flo_rc, fi0, vec, 4, cr);
             load4(p.flo_xw, fi0, vec, 4, cx);
             load4(p.flo_yw, fi0, vec, 4, cy);
             bool inb = true;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const double weight = r.cd / cw[j];
+                const double weight = floor_weight(r, cw[j], cr[j]);
                 fx[j] = weight * cx[j] + (1.0 - weight) * posx;
                 fy[j] = weight * cy[j] + (1.0 - weight) * posy;
                 inb = inb && (fx[j] >= 0.0) && (fy[j] >= 0.0) && (fx[j] < mapw) && (fy[j] < maph);
@@ -446,14 +452,15 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS) k_compose(cons
 #pragma unroll
                 for (int j = 0; j < 4; j++) any_floor = any_floor || (((pending >> j) & 1u) && y >= fs[j]);
                 if (any_floor && (r.info & 0x80000000u)) {
-                    double cw[4], cx[4], cy[4];
+                    double cw[4], cr[4], cx[4], cy[4];
                     load4(p.flo_dw, fi0, vec, nvalid, cw);
+                    load4(p.flo_rc, fi0, vec, nvalid, cr);
                     load4(p.flo_xw, fi0, vec, nvalid, cx);
                     load4(p.flo_yw, fi0, vec, nvalid, cy);
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         if (!((pending >> j) & 1u)) continue;
-                        const uint32_t t = floor_texel(p, cx[j], cy[j], cw[j], fs[j], r, posx, posy, y);
+                        const uint32_t t = floor_texel(p, cx[j], cy[j], cw[j], cr[j], fs[j], r, posx, posy, y);
                         const uint32_t a = t >> 24;
                         if (a == 255u) { px[j] = t; pending &= ~(1u << j); }  // (t*255 + 127)/255 == t
                         else if (a != 0u) { slow |= 1u << j; pending &= ~(1u << j); }
@@ -555,7 +562,7 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     ComposeParams p;
     p.views = ctx->cur_views;
     p.col_span = ctx->col_span; p.col_tt = ctx->col_tt; p.col_ps = ctx->col_ps;
-    p.flo_xw = ctx->flo_xw; p.flo_yw = ctx->flo_yw; p.flo_dw = ctx->flo_dw; p.flo_fs = ctx->flo_fs;
+    p.flo_xw = ctx->flo_xw; p.flo_yw = ctx->flo_yw; p.flo_dw = ctx->flo_dw; p.flo_rc = ctx->flo_rc; p.flo_fs = ctx->flo_fs;
     p.agg = ctx->agg;
     p.zbuf = ctx->zbuf;
     p.row_rec = ctx->row_rec;

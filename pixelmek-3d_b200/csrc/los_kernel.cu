@@ -52,10 +52,6 @@ __device__ __forceinline__ bool line_intersection(const double4 &a, const double
 // t > 1  <=>  |tNum| > |denom|  (two doubles a > b satisfy a/b >= 1 + ulp(b)/b > 1 + 2^-53, which rounds to at
 // least 1 + 2^-52; a <= b gives a quotient <= 1).  Anything else (zero / tiny / huge / inf / NaN operands,
 // where Go's comparisons with NaN all read false) takes the reference arithmetic.
-__device__ __forceinline__ bool exp_mid(double v) {
-    const unsigned e = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu;
-    return e - 523u <= 1000u;
-}
 __device__ __forceinline__ bool segments_intersect(const double4 &a, const double4 &b) {
     const double x1 = a.x, y1 = a.y, x2 = a.z, y2 = a.w;
     const double x3 = b.x, y3 = b.y, x4 = b.z, y4 = b.w;

@@ -86,7 +86,7 @@ void pm3d_destroy(pm3d_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     void *ptrs[] = {ctx->grid, ctx->dist, ctx->wall_lut, ctx->atlas, ctx->floor_tiles, ctx->sheet_pixels, ctx->sheet_info,
-                    ctx->views, ctx->col_span, ctx->col_tt, ctx->col_ps, ctx->flo_xw, ctx->flo_yw, ctx->flo_dw, ctx->flo_fs, ctx->agg, ctx->zbuf, ctx->row_rec, ctx->dbg_cols, ctx->sprites,
+                    ctx->views, ctx->col_span, ctx->col_tt, ctx->col_ps, ctx->flo_xw, ctx->flo_yw, ctx->flo_dw, ctx->flo_rc, ctx->flo_fs, ctx->agg, ctx->zbuf, ctx->row_rec, ctx->dbg_cols, ctx->sprites,
                     ctx->sprite_offset, ctx->draw_rec, ctx->n_draw, ctx->bin_list, ctx->bin_rect, ctx->bin_count, ctx->rects,
                     ctx->conv, ctx->frame, ctx->checksums, ctx->segs, ctx->seg_irect, ctx->cell_start,
                     ctx->cell_items, ctx->cell_rec, ctx->inbuf, ctx->io_a, ctx->io_b, ctx->io_c, ctx->flush_buf};
@@ -125,8 +125,10 @@ int pm3d_upload_grid(pm3d_ctx *ctx, const uint16_t *grid, int stored_levels, int
     if (!grid || stored_levels < 1 || map_w < 1 || map_h < 1 || num_raycast_levels < 1 || map_w > 32768 ||
         map_h > 32768 || num_raycast_levels > 64)
         return pm3d_fail(ctx, PM3D_ERR_ARG, "bad grid dimensions");
-    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
     size_t count = (size_t)stored_levels * map_w * map_h;
+    for (size_t i = 0; i < count; i++)
+        if (grid[i] > 32767) return pm3d_fail(ctx, PM3D_ERR_ARG, "grid cell %zu holds texture index %u > 32767 (math.MaxInt16 is the largest the reference uses)", i, (unsigned)grid[i]);
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = dev_realloc(ctx, &ctx->grid, count);
     if (rc) return rc;
     PM3D_CUDA(ctx, cudaMemcpyAsync(ctx->grid, grid, count * 2, cudaMemcpyHostToDevice, ctx->stream));
@@ -178,12 +180,14 @@ int pm3d_upload_wall_textures(pm3d_ctx *ctx, const int32_t *tex_index, const int
     if (n < 0 || (n > 0 && (!tex_index || !tile_side0 || !tile_side1))) return pm3d_fail(ctx, PM3D_ERR_ARG, "null LUT");
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<int16_t> lut(32768 * 2, (int16_t)-1);
+    ctx->max_wall_tile = -1;
     for (int i = 0; i < n; i++) {
         if (tex_index[i] < 0 || tex_index[i] > 32767) return pm3d_fail(ctx, PM3D_ERR_ARG, "texture index %d out of [0,32767]", tex_index[i]);
         if (tile_side0[i] < -1 || tile_side0[i] > 32767 || tile_side1[i] < -1 || tile_side1[i] > 32767)
             return pm3d_fail(ctx, PM3D_ERR_ARG, "tile out of range");
         lut[tex_index[i] * 2 + 0] = (int16_t)tile_side0[i];
         lut[tex_index[i] * 2 + 1] = (int16_t)tile_side1[i];
+        ctx->max_wall_tile = std::max(ctx->max_wall_tile, std::max(tile_side0[i], tile_side1[i]));
     }
     int rc = dev_realloc(ctx, &ctx->wall_lut, lut.size());
     if (rc) return rc;
@@ -209,6 +213,8 @@ int pm3d_upload_atlas(pm3d_ctx *ctx, const uint8_t *rgba, int n_tiles, int tex_s
 int pm3d_upload_floor_tiles(pm3d_ctx *ctx, const int16_t *tiles, int map_w, int map_h) {
     if (!ctx) return PM3D_ERR_ARG;
     if (!tiles || map_w < 1 || map_h < 1) return pm3d_fail(ctx, PM3D_ERR_ARG, "bad floor grid");
+    ctx->max_floor_tile = -1;
+    for (size_t i = 0; i < (size_t)map_w * map_h; i++) ctx->max_floor_tile = std::max(ctx->max_floor_tile, (int)tiles[i]);
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = dev_realloc(ctx, &ctx->floor_tiles, (size_t)map_w * map_h);
     if (rc) return rc;
@@ -303,6 +309,7 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
     if ((rc = dev_realloc(ctx, &ctx->flo_xw, V * W))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->flo_yw, V * W))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->flo_dw, V * W))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->flo_rc, V * W))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->flo_fs, V * W))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->agg, V * L * ctx->n_groups * 2))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->zbuf, V * W))) return rc;
@@ -351,6 +358,8 @@ static int render_ready(pm3d_ctx *ctx, int n_views) {
     if (n_views > ctx->max_views) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "%d views > max_views %d", n_views, ctx->max_views);
     if (ctx->sky_tile >= ctx->n_tiles || ctx->floorbox_tile >= ctx->n_tiles)
         return pm3d_fail(ctx, PM3D_ERR_ARG, "sky/floor box tile outside the atlas");
+    if (ctx->max_wall_tile >= ctx->n_tiles || ctx->max_floor_tile >= ctx->n_tiles)
+        return pm3d_fail(ctx, PM3D_ERR_ARG, "a wall (%d) or floor (%d) tile index lies outside the %d-tile atlas", ctx->max_wall_tile, ctx->max_floor_tile, ctx->n_tiles);
     return PM3D_OK;
 }
 

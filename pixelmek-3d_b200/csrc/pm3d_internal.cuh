@@ -18,6 +18,7 @@
 //   col_ps    ulonglong2  pos0, step2: texel row of screen row y = (pos0 + y*step2) >> 33 (mod 2^64)
 // and the level-0 floor-cast parameters as [view][column]:
 //   flo_xw, flo_yw, flo_dw  double  floorXWall, floorYWall, distWall
+//   flo_rc                  double  RN(1/distWall) when exp_mid(distWall), else 0 (compose then divides)
 //   flo_fs                  int     first floor row (drawEnd + 1, or h when none)
 // plus one aggregate per (view, level, 64-column group, 32-column half):
 //   agg  int4  x: min ya over drawn slices (INT_MAX if none); y: min fs; z: max fs (level 0 only)
@@ -74,6 +75,7 @@ struct pm3d_ctx {
     int16_t *floor_tiles = nullptr;  // [map_w][map_h]
     int floor_w = 0, floor_h = 0;
     int sky_tile = -1, floorbox_tile = -1;
+    int max_wall_tile = -1, max_floor_tile = -1;  // validated against n_tiles before every render
     uint8_t *sheet_pixels = nullptr;
     SheetInfo *sheet_info = nullptr;
     int n_sheets = 0;
@@ -88,7 +90,7 @@ struct pm3d_ctx {
     int2 *col_span = nullptr;        // [views][levels][w]
     uint2 *col_tt = nullptr;
     ulonglong2 *col_ps = nullptr;
-    double *flo_xw = nullptr, *flo_yw = nullptr, *flo_dw = nullptr;  // [views][w]
+    double *flo_xw = nullptr, *flo_yw = nullptr, *flo_dw = nullptr, *flo_rc = nullptr;  // [views][w]
     int32_t *flo_fs = nullptr;
     int4 *agg = nullptr;             // [views][levels][n_groups][2]
     double *zbuf = nullptr;          // [views][w]
@@ -183,6 +185,26 @@ __device__ __forceinline__ int64_t clamp_i64(int64_t v, int64_t lo, int64_t hi) 
 // blit model: nearest sample of n texels over len pixels
 __device__ __forceinline__ uint64_t span_step(int64_t n_src, int64_t len_dst) {
     return ((uint64_t)n_src << 32) / (uint64_t)len_dst;
+}
+
+// true when v is finite, non-zero and its exponent lies in [2^-500, 2^500]: quotients and products of
+// such values can neither overflow nor underflow
+__device__ __forceinline__ bool exp_mid(double v) {
+    const unsigned e = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu;
+    return e - 523u <= 1000u;
+}
+
+// RN(a / b) from r = RN(1 / b) without a division: two Newton corrections with exact FMA residuals
+// (Markstein's sequence: q1 is within an ulp of a/b, and a correction q1 + r*(a - b*q1) of a faithful
+// quotient by the correctly rounded reciprocal rounds correctly).  Requires exp_mid(a) && exp_mid(b);
+// callers fall back to the plain division otherwise.  pm3d_selfcheck_division compares it with `/`
+// on billions of random and adversarial operand pairs (tests/test_parity_gpu.py).
+__device__ __forceinline__ double div_by_rcp(double a, double b, double r) {
+    const double q0 = a * r;
+    const double e0 = __fma_rn(-b, q0, a);
+    const double q1 = __fma_rn(e0, r, q0);
+    const double e1 = __fma_rn(-b, q1, a);
+    return __fma_rn(e1, r, q1);
 }
 
 // lighting: byte(ClampInt(int(base + sqrt(dist)*falloff + illumination (+ extra)), min, max)) per channel

@@ -1,0 +1,79 @@
+// selfcheck.cu — device self-checks of arithmetic shortcuts the kernels rely on for bit-exactness.
+//
+// pm3d_selfcheck_division: div_by_rcp(a, b, RN(1/b)) (pm3d_internal.cuh; the floor cast's
+// weight = currentDist / distWall) against the IEEE division on random and adversarial operands:
+// uniform mantissas over a wide exponent range, divisors with all-ones / all-zero / single-bit mantissas,
+// quotients engineered to sit next to rounding boundaries (a = b * m with m +- a few ulps, and
+// a = RN(b * (m + 1/2 ulp))), and operands drawn from the path's own value range.
+#include "pm3d_internal.cuh"
+
+__device__ __forceinline__ uint64_t sm64(uint64_t &s) {
+    s += 0x9E3779B97F4A7C15ull;
+    uint64_t z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ double make_double(uint64_t mant52, int exp, bool neg) {
+    const uint64_t bits = ((uint64_t)neg << 63) | ((uint64_t)(exp + 1023) << 52) | (mant52 & 0xFFFFFFFFFFFFFull);
+    return __longlong_as_double((long long)bits);
+}
+
+__global__ void k_selfcheck_division(uint64_t seed, int iters, unsigned long long *mismatches, unsigned long long *tested) {
+    uint64_t s = seed ^ ((uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * 0xD1342543DE82EF95ull);
+    unsigned long long bad = 0, n = 0;
+    for (int it = 0; it < iters; it++) {
+        const uint64_t r0 = sm64(s), r1 = sm64(s), r2 = sm64(s);
+        const int mode = (int)(r2 & 7);
+        double a, b;
+        const int eb = (int)((r2 >> 8) % 61) - 30, ea = (int)((r2 >> 16) % 61) - 30;
+        b = make_double(r1, eb, (r2 >> 30) & 1);
+        a = make_double(r0, ea, (r2 >> 31) & 1);
+        if (mode == 1) b = make_double(0xFFFFFFFFFFFFFull, eb, false);                  // all-ones divisor
+        else if (mode == 2) b = make_double(0, eb, false);                              // power of two
+        else if (mode == 3) b = make_double(1ull << ((r2 >> 40) % 52), eb, false);      // single mantissa bit
+        else if (mode == 4 || mode == 5) {
+            // a = b * m rounded, nudged by up to 3 ulps: quotients beside representable values / midpoints
+            const double m = make_double(r0, ea, false);
+            a = b * m;
+            long long ab = __double_as_longlong(a) + (long long)((r2 >> 44) % 7) - 3;
+            a = __longlong_as_double(ab);
+        } else if (mode == 7) {
+            // the whole exp_mid range: exponents up to +-400 on either side
+            b = make_double(r1, (int)((r2 >> 8) % 801) - 400, (r2 >> 30) & 1);
+            a = make_double(r0, (int)((r2 >> 20) % 801) - 400, (r2 >> 31) & 1);
+        } else if (mode == 6) {
+            // the path's own range: row distances 1e-3 .. 1e3, wall distances 1e-2 .. 1e3
+            a = 1e-3 + (double)(r0 >> 11) * (1.0 / 9007199254740992.0) * 1e3;
+            b = 1e-2 + (double)(r1 >> 11) * (1.0 / 9007199254740992.0) * 1e3;
+        }
+        if (!exp_mid(a) || !exp_mid(b)) continue;
+        const double r = 1.0 / b;
+        const double want = a / b;
+        const double got = div_by_rcp(a, b, r);
+        n++;
+        if (__double_as_longlong(want) != __double_as_longlong(got)) bad++;
+    }
+    atomicAdd(mismatches, bad);
+    atomicAdd(tested, n);
+}
+
+extern "C" int pm3d_selfcheck_division(pm3d_ctx *ctx, uint64_t seed, int blocks, int iters, uint64_t *out_mismatches,
+                                       uint64_t *out_tested) {
+    if (!ctx || blocks < 1 || iters < 1 || !out_mismatches || !out_tested) return PM3D_ERR_ARG;
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned long long *d = nullptr;
+    PM3D_CUDA(ctx, cudaMalloc((void **)&d, 16));
+    PM3D_CUDA(ctx, cudaMemsetAsync(d, 0, 16, ctx->stream));
+    k_selfcheck_division<<<blocks, 256, 0, ctx->stream>>>(seed, iters, d, d + 1);
+    ctx->launches++;
+    PM3D_CUDA(ctx, cudaGetLastError());
+    unsigned long long h[2] = {0, 0};
+    PM3D_CUDA(ctx, cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PM3D_CUDA(ctx, cudaFree(d));
+    *out_mismatches = h[0];
+    *out_tested = h[1];
+    return PM3D_OK;
+}

@@ -107,6 +107,7 @@ SYMBOLS = {
     "pm3d_ktimer_collect": (C.c_int, [_P, _P, C.c_int]),
     "pm3d_launch_count": (C.c_int64, [_P]),
     "pm3d_flush_l2": (C.c_int, [_P]),
+    "pm3d_selfcheck_division": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 }
 
 _lib = None

@@ -221,6 +221,13 @@ class Context:
     def flush_l2(self):
         self._check(self.lib.pm3d_flush_l2(self.h), "pm3d_flush_l2")
 
+    def selfcheck_division(self, seed: int, blocks: int, iters: int) -> tuple[int, int]:
+        """(mismatches, pairs tested) of the division-free floor-cast quotient against `/` on the device."""
+        bad, n = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.pm3d_selfcheck_division(self.h, int(seed), int(blocks), int(iters), C.byref(bad), C.byref(n)),
+                    "pm3d_selfcheck_division")
+        return int(bad.value), int(n.value)
+
 
 def generate_wall_collision_lines(level0: np.ndarray, has_boundary_wall: bool, clip: float) -> np.ndarray:
     """Host mirror of Map.GenerateWallCollisionLines (game/model/map.go:811-851); needs no GPU."""

@@ -185,6 +185,16 @@ def test_many_overlapping_sprites_and_duplicates(gpu_ctx):
     check_all(gpu_ctx, got, want, off, n)
 
 
+def test_division_free_floor_weight_is_correctly_rounded(gpu_ctx):
+    """The floor cast's weight = currentDist / distWall is evaluated as a Newton sequence on RN(1/distWall)
+    (pm3d_internal.cuh div_by_rcp).  It must equal the IEEE quotient bit for bit: 2.1e9 operand pairs
+    (random mantissas, all-ones / power-of-two / single-bit divisors, quotients beside rounding
+    boundaries, the path's own value range, exponents to +-400)."""
+    bad, n = gpu_ctx.selfcheck_division(20261019, 148 * 8, 7000)
+    assert n > 2_000_000_000
+    assert bad == 0, f"{bad} of {n} quotients differ from a / b"
+
+
 def test_painter_and_front_to_back_paths_agree(gpu_ctx):
     """PM3D_OPT_FORCE_PAINTER runs the literal painter's loop on every pixel; the default
     front-to-back shortcut must give identical bytes (translucent boundary tile + sprite rims)."""
@@ -264,6 +274,17 @@ def test_errors_are_reported_not_swallowed(gpu_ctx):
         ctx.render(v, np.zeros(11, dtype=pm3d._lib.SPRITE_DTYPE))
     with pytest.raises(pm3d.Pm3dError, match="upload_segments"):
         ctx.los_batch(np.zeros((1, 4)))
+    bad = edge_scene()
+    bad.floor_tiles = bad.floor_tiles.copy()
+    bad.floor_tiles[3, 3] = 99          # tile outside the atlas: refused, not read out of bounds
+    ctx.upload_scene(bad)
+    with pytest.raises(pm3d.Pm3dError, match="outside the"):
+        ctx.render(v)
+    bad = edge_scene()
+    bad.grid = bad.grid.copy()
+    bad.grid[0, 2, 2] = 40000           # texture index beyond math.MaxInt16
+    with pytest.raises(pm3d.Pm3dError, match="32767"):
+        ctx.upload_scene(bad)
     ctx.close()
 
 

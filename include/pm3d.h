@@ -193,6 +193,49 @@ int pm3d_los_batch(pm3d_ctx *ctx, const double *rays, int64_t n, uint8_t *out, u
 int pm3d_move_batch(pm3d_ctx *ctx, const double *moves, int64_t n, double clip_distance, double *out_pos,
                     uint8_t *out_collided, uint32_t flags);
 
+/* ---- full Game.getValidMove (game/collision.go:69-394) for a batch of moving entities.
+ * The per-tick callers are game/combat.go:333 (every projectile, one goroutine each,
+ * game/combat.go:206-239), game/update_sprites.go:263 and game/update_units.go:24. */
+
+/* The moving model.Entity and the move it asks for (collision.go:69-81). */
+typedef struct pm3d_mover {
+    double pos_x, pos_y, pos_z;    /* entity.Pos(), entity.PosZ()                     */
+    double move_x, move_y, move_z; /* moveX, moveY, moveZ                             */
+    double radius, height;         /* CollisionRadius(), CollisionHeight()            */
+    int32_t self, parent;          /* collider index of the entity itself / of entity.Parent(); -1 = none */
+    uint8_t anchor, destroyed;     /* Anchor(), IsDestroyed()                         */
+    uint8_t _pad[6];
+} pm3d_mover;                      /* 80 bytes */
+
+/* One collidable entity: g.player.Unit or a sprite of a collision type (collision.go:20-29). */
+typedef struct pm3d_collider {
+    double x, y, z, radius, height; /* Pos(), PosZ(), CollisionRadius(), CollisionHeight() */
+    uint8_t anchor, destroyed;
+    uint8_t _pad[6];
+} pm3d_collider;                   /* 48 bytes */
+
+/* What getValidMove returns, flattened: (*geom.Vector2, posZ, isCollision, collisions[0], len(collisions))
+ * plus the closest intersection point the checkAlternate branch steers away from (collision.go:222-229). */
+typedef struct pm3d_move_result {
+    double x, y, z;
+    int32_t collided;
+    int32_t n_collisions;          /* len(collisionEntities)                          */
+    int32_t first_entity;          /* collisions[0].entity as a collider index, -1 = none */
+    int32_t n_points;              /* len(intersectPoints)                            */
+    double first_x, first_y, first_z; /* collisions[0].collision, .collisionZ          */
+    double near_x, near_y;         /* intersectPoints[minI]; NaN when there is none    */
+} pm3d_move_result;                /* 80 bytes */
+
+/* g.player.Unit and the collidable sprites, in the order the host walks them (the reference's
+ * sync.Map order is unspecified; ties in the collision sort keep this order).  player_index = the
+ * element that is g.player.Unit, -1 = none. */
+int pm3d_upload_colliders(pm3d_ctx *ctx, const pm3d_collider *colliders, int n, int player_index);
+/* getValidMove(entity, x, y, z, checkAlternate=false) for n movers against the uploaded collision
+ * segments, colliders and level-0 grid.  The checkAlternate=true escape heuristics (collision.go:204-306,
+ * trigonometry on the entity heading) are composed on the host from this call: see INTEGRATION.md. */
+int pm3d_valid_move_batch(pm3d_ctx *ctx, const pm3d_mover *movers, int64_t n, double clip_distance,
+                          pm3d_move_result *out, uint32_t flags);
+
 /* Host mirror of Map.GenerateWallCollisionLines (game/model/map.go:811-851) so synthetic
  * workloads can build g.collisionMap without the Go side.  level0: [map_w][map_h].
  * Returns the number of segments (writes at most cap), or a negative status. */
@@ -227,6 +270,12 @@ int pm3d_flush_l2(pm3d_ctx *ctx);
  * (random, adversarial and path-range) bit for bit against the IEEE division.  out_mismatches must read 0. */
 int pm3d_selfcheck_division(pm3d_ctx *ctx, uint64_t seed, int blocks, int iters, uint64_t *out_mismatches,
                             uint64_t *out_tested);
+/* Device self-check of the fast floor cast (texel index from one fused multiply-add plus a rounding-boundary
+ * test) against the reference's float64 sequence int((weight*floorXWall + (1-weight)*posX) * texSize), on random
+ * operands and on operands steered next to integer texel boundaries.  out_accepted counts the pairs the fast
+ * path accepted (the rest fall back to the reference sequence in the kernel); out_mismatches must read 0. */
+int pm3d_selfcheck_floor(pm3d_ctx *ctx, uint64_t seed, int blocks, int iters, uint64_t *out_mismatches,
+                         uint64_t *out_tested, uint64_t *out_accepted);
 
 #ifdef __cplusplus
 }

@@ -193,5 +193,58 @@ def move_walls_batch(scene: Scene, segs: np.ndarray, moves: np.ndarray, clip: fl
     return pos, collided, hits
 
 
+MOVER_DTYPE = np.dtype(
+    [
+        ("pos_x", "<f8"), ("pos_y", "<f8"), ("pos_z", "<f8"), ("move_x", "<f8"), ("move_y", "<f8"), ("move_z", "<f8"),
+        ("radius", "<f8"), ("height", "<f8"), ("self", "<i4"), ("parent", "<i4"),
+        ("anchor", "u1"), ("destroyed", "u1"), ("_pad", "u1", (6,)),
+    ]
+)
+assert MOVER_DTYPE.itemsize == 80
+COLLIDER_DTYPE = np.dtype(
+    [("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("radius", "<f8"), ("height", "<f8"),
+     ("anchor", "u1"), ("destroyed", "u1"), ("_pad", "u1", (6,))]
+)
+assert COLLIDER_DTYPE.itemsize == 48
+MOVE_RESULT_DTYPE = np.dtype(
+    [("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("collided", "<i4"), ("n_collisions", "<i4"), ("first_entity", "<i4"),
+     ("n_points", "<i4"), ("first_x", "<f8"), ("first_y", "<f8"), ("first_z", "<f8"), ("near_x", "<f8"), ("near_y", "<f8")]
+)
+assert MOVE_RESULT_DTYPE.itemsize == 80
+
+
+def line_circle_intersection(line, cx, cy, radius, is_segment=True):
+    a = np.ascontiguousarray(line, dtype=np.float64)
+    out = np.zeros(4, dtype=np.float64)
+    n = lib().orc_line_circle_intersection(_ptr(a), C.c_double(cx), C.c_double(cy), C.c_double(radius),
+                                           C.c_int(int(is_segment)), _ptr(out))
+    return [(float(out[2 * i]), float(out[2 * i + 1])) for i in range(n)]
+
+
+def valid_move_batch(scene: Scene, segs, colliders, player: int, clip: float, movers, threads: int = 1):
+    """Game.getValidMove(..., checkAlternate=false) for a batch of movers (game/collision.go:69-203, 307-355)."""
+    segs = np.ascontiguousarray(segs, dtype=np.float64).reshape(-1, 4)
+    colliders = np.ascontiguousarray(colliders, dtype=COLLIDER_DTYPE).reshape(-1)
+    movers = np.ascontiguousarray(movers, dtype=MOVER_DTYPE).reshape(-1)
+    out = np.zeros(len(movers), dtype=MOVE_RESULT_DTYPE)
+    lib().orc_valid_move_batch(C.byref(scene.c), _ptr(segs), C.c_int32(len(segs)), _ptr(colliders),
+                               C.c_int32(len(colliders)), C.c_int32(player), C.c_double(clip), _ptr(movers),
+                               C.c_int64(len(movers)), _ptr(out), C.c_int32(threads))
+    return out
+
+
+def valid_move_alternate(scene: Scene, segs, colliders, player: int, clip: float, mover, heading: float,
+                         velocity: float, check_alternate: bool = True):
+    """Game.getValidMove with the checkAlternate escape heuristics for ONE mover (game/collision.go:204-306)."""
+    segs = np.ascontiguousarray(segs, dtype=np.float64).reshape(-1, 4)
+    colliders = np.ascontiguousarray(colliders, dtype=COLLIDER_DTYPE).reshape(-1)
+    mover = np.ascontiguousarray(mover, dtype=MOVER_DTYPE).reshape(-1)[:1]
+    out = np.zeros(1, dtype=MOVE_RESULT_DTYPE)
+    lib().orc_valid_move_alternate(C.byref(scene.c), _ptr(segs), C.c_int32(len(segs)), _ptr(colliders),
+                                   C.c_int32(len(colliders)), C.c_int32(player), C.c_double(clip), _ptr(mover),
+                                   C.c_double(heading), C.c_double(velocity), C.c_int(int(check_alternate)), _ptr(out))
+    return out[0]
+
+
 def go_int(v: float) -> int:
     return int(lib().orc_go_int(float(v)))

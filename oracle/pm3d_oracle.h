@@ -142,6 +142,49 @@ void orc_move_walls_batch(const orc_scene *s, const double *segs, int32_t n_segs
                           int64_t n_moves, double clip_distance, double *out_pos, uint8_t *out_collided,
                           int32_t *out_hits, int32_t threads);
 
+/* ---- full Game.getValidMove (pm3d_oracle_move.c) -------------------------------- */
+
+/* The moving model.Entity and the requested move (game/collision.go:69-81). */
+typedef struct orc_mover {
+    double pos_x, pos_y, pos_z;    /* entity.Pos(), entity.PosZ()                     */
+    double move_x, move_y, move_z; /* moveX, moveY, moveZ                             */
+    double radius, height;         /* CollisionRadius(), CollisionHeight()            */
+    int32_t self, parent;          /* collider index of the entity / of entity.Parent(), -1 = none */
+    uint8_t anchor, destroyed;     /* Anchor(), IsDestroyed()                         */
+    uint8_t _pad[6];
+} orc_mover;                       /* 80 bytes */
+
+/* One collidable entity: the player unit or a sprite of a collision type (collision.go:20-29). */
+typedef struct orc_collider {
+    double x, y, z, radius, height;
+    uint8_t anchor, destroyed;
+    uint8_t _pad[6];
+} orc_collider;                    /* 48 bytes */
+
+typedef struct orc_move_result {
+    double x, y, z;                /* returned position                               */
+    int32_t collided;              /* isCollision                                     */
+    int32_t n_collisions;          /* len(collisionEntities)                          */
+    int32_t first_entity;          /* collisions[0].entity (collider index), -1 = none */
+    int32_t n_points;              /* len(intersectPoints)                            */
+    double first_x, first_y, first_z; /* collisions[0].collision, .collisionZ         */
+    double near_x, near_y;         /* intersectPoints[minI] of collision.go:222-229 (NaN when none / all Inf) */
+} orc_move_result;                 /* 80 bytes */
+
+/* geom.LineCircleIntersection [R]; writes up to 2 points (x,y pairs), returns their number */
+int orc_line_circle_intersection(const double *line, double cx, double cy, double radius, int is_segment,
+                                 double *out_xy);
+/* getValidMove(entity, x, y, z, checkAlternate=false) for a batch (game/collision.go:69-203, 307-355) [V].
+ * player = collider index of g.player.Unit (-1 = none). */
+void orc_valid_move_batch(const orc_scene *s, const double *segs, int32_t n_segs, const orc_collider *colliders,
+                          int32_t n_colliders, int32_t player, double clip_distance, const orc_mover *movers,
+                          int64_t n, orc_move_result *out, int32_t threads);
+/* getValidMove with the checkAlternate escape heuristics (game/collision.go:204-306) [V] for one entity;
+ * heading = entity.Heading(), velocity = entity.Velocity(). */
+void orc_valid_move_alternate(const orc_scene *s, const double *segs, int32_t n_segs, const orc_collider *colliders,
+                              int32_t n_colliders, int32_t player, double clip_distance, const orc_mover *m,
+                              double heading, double velocity, int check_alternate, orc_move_result *out);
+
 /* Go int(float64) on amd64. */
 int64_t orc_go_int(double v);
 

@@ -26,7 +26,7 @@ struct CastParams {
     int2 *col_span;
     uint2 *col_tt;
     ulonglong2 *col_ps;
-    double *flo_xw, *flo_yw, *flo_dw, *flo_rc;
+    double *flo_xw, *flo_yw, *flo_dw, *flo_rc, *flo_dx, *flo_dy;
     int32_t *flo_fs;
     int4 *agg;
     double *zbuf;
@@ -177,7 +177,14 @@ __device__ __forceinline__ void cast_ray(const CastParams &p, const int view, co
             const size_t fi = (size_t)view * p.w + x;
             p.zbuf[fi] = perpWallDist;
             p.flo_xw[fi] = fxw; p.flo_yw[fi] = fyw; p.flo_dw[fi] = perpWallDist; p.flo_fs[fi] = fs;
-            p.flo_rc[fi] = exp_mid(perpWallDist) ? 1.0 / perpWallDist : 0.0;
+            // fast floor cast (compose_kernel.cu): texel coordinates t = P + w*(X1 - P) in texel units.  Eligible
+            // columns have a mid-range wall distance and |coordinates| <= 2^24 texels (error bound in DESIGN.md)
+            const double S = (double)p.tex_size, lim = 16777216.0;
+            const double X1 = fxw * S, Y1 = fyw * S, PX = rayPosX * S, PY = rayPosY * S;
+            const bool elig = exp_mid(perpWallDist) && fabs(X1) <= lim && fabs(Y1) <= lim && fabs(PX) <= lim && fabs(PY) <= lim;
+            p.flo_rc[fi] = elig ? 1.0 / perpWallDist : 0.0;
+            p.flo_dx[fi] = X1 - PX;
+            p.flo_dy[fi] = Y1 - PY;
             agg_fs_min = fs; agg_fs_max = fs;
         }
     }

@@ -41,7 +41,7 @@ struct ComposeParams {
     const int2 *col_span;
     const uint2 *col_tt;
     const ulonglong2 *col_ps;
-    const double *flo_xw, *flo_yw, *flo_dw, *flo_rc;
+    const double *flo_xw, *flo_yw, *flo_dw, *flo_rc, *flo_dx, *flo_dy;
     const int32_t *flo_fs;
     const int4 *agg;
     const double *zbuf;
@@ -142,7 +142,7 @@ __device__ __forceinline__ uint32_t shade_opaque(uint32_t t, uint32_t tint) {
 }
 
 // literal painter's loop over the BACKGROUND layers of pixel (x, y) — the definition
-__device__ __noinline__ uint32_t background_painter(const ComposeParams &p, int view, int x, int y, uint32_t u) {
+__device__ __forceinline__ uint32_t background_painter(const ComposeParams &p, int view, int x, int y, uint32_t u) {
     const pm3d_view &c = p.views[view];
     const uint32_t box_tint = (uint32_t)c.max_light[0] | ((uint32_t)c.max_light[1] << 8) |
                               ((uint32_t)c.max_light[2] << 16) | 0xff000000u;
@@ -307,9 +307,23 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS) k_compose(cons
     const bool vec = ((p.w & 3) == 0) && full4;
     const bool fast_ok = !p.force_painter && full4;
     const int tmask = p.tex_size - 1;
-    const double mapw = (double)p.map_w, maph = (double)p.map_h, texd = (double)p.tex_size;
+    const double texd = (double)p.tex_size;
     const size_t fi0 = (size_t)view * p.w + x0;
     uint32_t *out32 = reinterpret_cast<uint32_t *>(p.out) + (size_t)view * p.h * p.w;
+
+    // fast floor cast: texel-unit camera position, map bounds in texels, and the largest row distance for which
+    // every column of this lane keeps |weight| <= 4 (negative when a column is not eligible)
+    const double ptx = posx * texd, pty = posy * texd;
+    const uint32_t boundx = (uint32_t)min((uint64_t)p.map_w << p.tex_shift, (uint64_t)0x80000000u);
+    const uint32_t boundy = (uint32_t)min((uint64_t)p.map_h << p.tex_shift, (uint64_t)0x80000000u);
+    double lane_cd_max = -1.0;
+    if (fast_ok) {
+        double cw[4], cr[4];
+        load4(p.flo_dw, fi0, vec, 4, cw);
+        load4(p.flo_rc, fi0, vec, 4, cr);
+        if (cr[0] != 0.0 && cr[1] != 0.0 && cr[2] != 0.0 && cr[3] != 0.0)
+            lane_cd_max = 4.0 * fmin(fmin(fabs(cw[0]), fabs(cw[1])), fmin(fabs(cw[2]), fabs(cw[3])));
+    }
 
     // per-lane mask of the warp's sprites that overlap this lane's four columns (lanes then walk
     // different sprites concurrently instead of every lane scanning the whole list)
@@ -393,37 +407,37 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS) k_compose(cons
         if (done) {
             // every pixel of this lane is covered by an opaque sprite texel
         } else if (fast_ok && y >= fs_max && (r.info & 0x80000000u)) {
-            // ---------- every pixel of this lane is a floor candidate: four casts in straight line
-            double cw[4], cr[4], cx[4], cy[4], fx[4], fy[4];
-            load4(p.flo_dw, fi0, vec, 4, cw);
-            load4(p.flo_rc, fi0, vec, 4, cr);
-            load4(p.flo_xw, fi0, vec, 4, cx);
-            load4(p.flo_yw, fi0, vec, 4, cy);
-            bool inb = true;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const double weight = floor_weight(r, cw[j], cr[j]);
-                fx[j] = weight * cx[j] + (1.0 - weight) * posx;
-                fy[j] = weight * cy[j] + (1.0 - weight) * posy;
-                inb = inb && (fx[j] >= 0.0) && (fy[j] >= 0.0) && (fx[j] < mapw) && (fy[j] < maph);
-            }
-            if (inb) {
-                int tx[4], ty[4], ft[4];
+            // ---------- every pixel of this lane is a floor candidate: four fast casts in straight line
+            //            (pm3d_internal.cuh "fast floor cast"); anything doubtful goes to the mixed path below,
+            //            which runs the reference sequence
+            if ((r.info & 0x20000000u) && r.cd <= lane_cd_max) {
+                double cr[4], dx[4], dy[4];
+                load4(p.flo_rc, fi0, vec, 4, cr);
+                load4(p.flo_dx, fi0, vec, 4, dx);
+                load4(p.flo_dy, fi0, vec, 4, dy);
+                uint32_t tx[4], ty[4];
+                bool ok = true;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    tx[j] = (int)(fx[j] * texd);
-                    ty[j] = (int)(fy[j] * texd);
-                    ft[j] = __ldg(p.floor_tiles + (tx[j] >> p.tex_shift) * p.map_h + (ty[j] >> p.tex_shift));
+                    const double wq = r.cd * cr[j];
+                    ok = floor_fast_index(wq, dx[j], ptx, boundx, tx[j]) && ok;
+                    ok = floor_fast_index(wq, dy[j], pty, boundy, ty[j]) && ok;
                 }
-                if ((ft[0] | ft[1] | ft[2] | ft[3]) >= 0) {
-                    uint32_t t[4];
+                if (ok) {
+                    int ft[4];
 #pragma unroll
                     for (int j = 0; j < 4; j++)
-                        t[j] = __ldg(p.atlas + ((((size_t)ft[j] << p.tex_shift) + (size_t)(ty[j] & tmask)) << p.tex_shift) + (size_t)(tx[j] & tmask));
-                    if ((t[0] & t[1] & t[2] & t[3]) >= 0xff000000u) {
+                        ft[j] = __ldg(p.floor_tiles + (tx[j] >> p.tex_shift) * p.map_h + (ty[j] >> p.tex_shift));
+                    if ((ft[0] | ft[1] | ft[2] | ft[3]) >= 0) {
+                        uint32_t t[4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) px[j] = floor_tint(t[j], r.tint);
-                        done = true;
+                        for (int j = 0; j < 4; j++)
+                            t[j] = __ldg(p.atlas + ((((size_t)ft[j] << p.tex_shift) + (size_t)(ty[j] & tmask)) << p.tex_shift) + (size_t)(tx[j] & tmask));
+                        if ((t[0] & t[1] & t[2] & t[3]) >= 0xff000000u) {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) px[j] = floor_tint(t[j], r.tint);
+                            done = true;
+                        }
                     }
                 }
             }
@@ -482,9 +496,17 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS) k_compose(cons
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < 4; j++)
                 if ((pending >> j) & 1u) px[j] = blend_over(0u, box_texel(p, r.info, bu[j]), box_tint);
-                if ((slow >> j) & 1u) px[j] = background_painter(p, view, x0 + j, y, bu[j]);
+            if (slow) {
+                // one inlined copy of the painter (a call would force the kernel parameters into local memory)
+#pragma unroll 1
+                for (int j = 0; j < 4; j++) {
+                    if (!((slow >> j) & 1u)) continue;
+                    const uint32_t u = j == 0 ? bu[0] : (j == 1 ? bu[1] : (j == 2 ? bu[2] : bu[3]));
+                    const uint32_t v = background_painter(p, view, x0 + j, y, u);
+                    if (j == 0) px[0] = v; else if (j == 1) px[1] = v; else if (j == 2) px[2] = v; else px[3] = v;
+                }
             }
         }
 
@@ -562,7 +584,7 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     ComposeParams p;
     p.views = ctx->cur_views;
     p.col_span = ctx->col_span; p.col_tt = ctx->col_tt; p.col_ps = ctx->col_ps;
-    p.flo_xw = ctx->flo_xw; p.flo_yw = ctx->flo_yw; p.flo_dw = ctx->flo_dw; p.flo_rc = ctx->flo_rc; p.flo_fs = ctx->flo_fs;
+    p.flo_xw = ctx->flo_xw; p.flo_yw = ctx->flo_yw; p.flo_dw = ctx->flo_dw; p.flo_rc = ctx->flo_rc; p.flo_dx = ctx->flo_dx; p.flo_dy = ctx->flo_dy; p.flo_fs = ctx->flo_fs;
     p.agg = ctx->agg;
     p.zbuf = ctx->zbuf;
     p.row_rec = ctx->row_rec;

@@ -26,7 +26,7 @@ int pm3d_launch_front(pm3d_ctx *ctx, int n_views) {
     p.dist = ctx->dist;
     p.wall_lut = ctx->wall_lut;
     p.col_span = ctx->col_span; p.col_tt = ctx->col_tt; p.col_ps = ctx->col_ps;
-    p.flo_xw = ctx->flo_xw; p.flo_yw = ctx->flo_yw; p.flo_dw = ctx->flo_dw; p.flo_rc = ctx->flo_rc; p.flo_fs = ctx->flo_fs;
+    p.flo_xw = ctx->flo_xw; p.flo_yw = ctx->flo_yw; p.flo_dw = ctx->flo_dw; p.flo_rc = ctx->flo_rc; p.flo_dx = ctx->flo_dx; p.flo_dy = ctx->flo_dy; p.flo_fs = ctx->flo_fs;
     p.agg = ctx->agg;
     p.zbuf = ctx->zbuf;
     p.dbg = ctx->keep_columns ? ctx->dbg_cols : nullptr;

@@ -287,6 +287,263 @@ __global__ void __launch_bounds__(256) k_move(LosParams p) {
     p.out_flag[i] = collided;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Full Game.getValidMove(entity, x, y, z, checkAlternate=false) (game/collision.go:69-203, 307-355): one
+// thread per moving entity.  Walls: the bin walk above, collecting the DISTINCT segments the move segment
+// intersects (a segment is registered in several cells).  Colliders: every lane of a warp reads the same
+// collider at the same time (one broadcast load per warp) and applies the reference's proximity and Z
+// pre-filters before the two geom.LineCircleIntersection stages.  The sorted collision list is reduced to
+// what its consumers read — collisions[0] and len(collisions) (game/combat.go:335-341,
+// game/update_units.go:31-33): the record nearest to the entity, earliest inserted on ties.
+struct MoveParams {
+    LosParams los;
+    const pm3d_mover *movers;
+    const pm3d_collider *colliders;
+    pm3d_move_result *out;
+    int n_colliders, player;
+};
+
+#define GEOM_EPS 1e-14
+__device__ __forceinline__ double sqd(double x) { return x * x; }
+
+// geom.LineCircleIntersection(li, ci, isSegment=true) [R] — the Rosetta-code routine raycaster-go adopted;
+// operations in the routine's own order, no contraction (-fmad=false).  Returns 0..2 points.
+__device__ __noinline__ int line_circle_intersection(double x1, double y1, double x2, double y2, double x0, double y0,
+                                                    double radius, double *out) {
+    int n = 0;
+    const double A = y2 - y1, B = x1 - x2, C = x2 * y1 - x1 * y2;
+    const double a = sqd(A) + sqd(B);
+    double b, c;
+    const bool bnz = fabs(B) >= GEOM_EPS;
+    if (bnz) {
+        b = 2 * (A * C + A * B * y0 - sqd(B) * x0);
+        c = sqd(C) + 2 * B * C * y0 - sqd(B) * (sqd(radius) - sqd(x0) - sqd(y0));
+    } else {
+        b = 2 * (B * C + A * B * x0 - sqd(A) * y0);
+        c = sqd(C) + 2 * A * C * x0 - sqd(A) * (sqd(radius) - sqd(x0) - sqd(y0));
+    }
+    double d = sqd(b) - 4 * a * c;
+    if (d < 0) return 0;
+    const double d1 = sqrt(sqd(x2 - x1) + sqd(y2 - y1));
+    auto within = [&](double x, double y) -> bool {
+        const double d2 = sqrt(sqd(x - x1) + sqd(y - y1)), d3 = sqrt(sqd(x2 - x) + sqd(y2 - y));
+        return fabs(d1 - d2 - d3) < GEOM_EPS;
+    };
+    const int roots = d == 0 ? 1 : 2;
+    if (d != 0) d = sqrt(d);
+    for (int k = 0; k < roots; k++) {
+        const double num = roots == 1 ? -b : (k == 0 ? -b + d : -b - d);
+        double x, y;
+        if (bnz) { x = num / (2 * a); y = -(A * x + C) / B; }
+        else     { y = num / (2 * a); x = -(B * y + C) / A; }
+        if (within(x, y)) { out[n * 2] = x; out[n * 2 + 1] = y; n++; }
+    }
+    return n;
+}
+
+// zEntityMinMax (game/collision.go:380-394)
+__device__ __forceinline__ void z_min_max(double z, double height, int anchor, double &lo, double &hi) {
+    lo = 0; hi = 0;
+    if (anchor == PM3D_ANCHOR_BOTTOM) { lo = z; hi = z + height; }
+    else if (anchor == PM3D_ANCHOR_CENTER) { lo = z - height / 2; hi = z + height / 2; }
+    else if (anchor == PM3D_ANCHOR_TOP) { lo = z - height; hi = z; }
+}
+
+#define MOVE_MAX_WALL_HITS 8
+__global__ void __launch_bounds__(128) k_valid_move(MoveParams q) {
+    const LosParams &p = q.los;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const pm3d_mover m = q.movers[i];
+    pm3d_move_result r;
+    double posX = m.pos_x, posY = m.pos_y, posZ = m.pos_z;
+    r.x = posX; r.y = posY; r.z = posZ;
+    r.collided = 0; r.n_collisions = 0; r.first_entity = -1; r.n_points = 0;
+    r.first_x = r.first_y = r.first_z = 0; r.near_x = r.near_y = __longlong_as_double(0x7ff8000000000000ll);
+    if (m.radius <= 0 || m.height <= 0 || (posX == m.move_x && posY == m.move_y && posZ == m.move_z)) {
+        q.out[i] = r;
+        return;
+    }
+    double newX = m.move_x, newY = m.move_y, newZ = m.move_z;
+    const double4 ray = make_double4(posX, posY, newX, newY);
+    const double checkDist = sqrt(sqd(newX - posX) + sqd(newY - posY) + sqd(newZ - posZ));  // geom3d.Line3d.Distance
+    const double prox = ceil(checkDist);                                                 // model.PointInProximity
+
+    int n_points = 0, n_collisions = 0;
+    double near_d2 = INFINITY, best_d2 = 0;
+    bool have_best = false;
+    auto add_point = [&](double x, double y) {
+        n_points++;
+        const double d2 = sqd(x - posX) + sqd(y - posY);
+        if (d2 < near_d2) { near_d2 = d2; r.near_x = x; r.near_y = y; }
+    };
+    auto consider = [&](int entity, double x, double y, double z) {
+        n_collisions++;
+        const double d2 = sqd(x - posX) + sqd(y - posY);
+        if (!have_best || d2 < best_d2 || (best_d2 != best_d2 && d2 == d2)) {
+            have_best = true; best_d2 = d2;
+            r.first_entity = entity; r.first_x = x; r.first_y = y; r.first_z = z;
+        }
+    };
+
+    // ---- walls (:93-97): distinct intersected segments, then their points in segment order
+    int wall_id[MOVE_MAX_WALL_HITS];
+    int n_wall = 0;
+    bool brute = false;
+    {
+        auto visit = [&](int id) {
+            const double2 s01 = __ldg(reinterpret_cast<const double2 *>(p.segs + id));
+            const double2 s23 = __ldg(reinterpret_cast<const double2 *>(p.segs + id) + 1);
+            if (!segments_intersect(ray, make_double4(s01.x, s01.y, s23.x, s23.y))) return;
+            for (int k = 0; k < n_wall && k < MOVE_MAX_WALL_HITS; k++)
+                if (wall_id[k] == id) return;
+            if (n_wall < MOVE_MAX_WALL_HITS) wall_id[n_wall] = id;
+            n_wall++;
+        };
+        const double gx0 = (double)p.bin_x0, gy0 = (double)p.bin_y0;
+        const double gx1 = (double)(p.bin_x0 + p.bin_w), gy1 = (double)(p.bin_y0 + p.bin_h);
+        const bool inside = ray.x >= gx0 && ray.x < gx1 && ray.z >= gx0 && ray.z < gx1 && ray.y >= gy0 && ray.y < gy1 &&
+                            ray.w >= gy0 && ray.w < gy1;
+        if (inside) {
+            int cx = (int)floor(ray.x) - p.bin_x0, cy = (int)floor(ray.y) - p.bin_y0;
+            const int ex = (int)floor(ray.z) - p.bin_x0, ey = (int)floor(ray.w) - p.bin_y0;
+            const double dx = ray.z - ray.x, dy = ray.w - ray.y;
+            const int sx = dx > 0 ? 1 : -1, sy = dy > 0 ? 1 : -1;
+            const double inv_dx = dx != 0 ? 1.0 / fabs(dx) : 0.0, inv_dy = dy != 0 ? 1.0 / fabs(dy) : 0.0;
+            double tx = dx != 0 ? (dx > 0 ? (floor(ray.x) + 1.0 - ray.x) : (ray.x - floor(ray.x))) * inv_dx : 1e300;
+            double ty = dy != 0 ? (dy > 0 ? (floor(ray.y) + 1.0 - ray.y) : (ray.y - floor(ray.y))) * inv_dy : 1e300;
+            int steps = abs(ex - cx) + abs(ey - cy);
+            for (;;) {
+                const int cell = cy * p.bin_w + cx;
+                const int b = __ldg(p.cell_start + cell), e = __ldg(p.cell_start + cell + 1);
+                for (int k = b; k < e; k++) visit(__ldg(p.cell_items + k));
+                if (steps-- <= 0) break;
+                if ((tx < ty && cx != ex) || cy == ey) { tx += inv_dx; cx += sx; }
+                else { ty += inv_dy; cy += sy; }
+            }
+        }
+        brute = !inside || n_wall > MOVE_MAX_WALL_HITS;  // outside the bins, or more hits than the list holds
+    }
+    const bool player_block = q.player >= 0 && m.self != q.player && m.parent != q.player && !m.destroyed;
+    // the player block (:100-132) re-reads every wall point, so it needs them in segment order
+    auto for_each_wall_point = [&](auto &&fn) {
+        if (brute) {
+            for (int id = 0; id < p.n_segs; id++) {
+                const double2 s01 = __ldg(reinterpret_cast<const double2 *>(p.segs + id));
+                const double2 s23 = __ldg(reinterpret_cast<const double2 *>(p.segs + id) + 1);
+                double px, py;
+                if (line_intersection(ray, make_double4(s01.x, s01.y, s23.x, s23.y), &px, &py)) fn(px, py);
+            }
+        } else {
+            // ascending segment id (insertion order of the reference loop): selection over <= 8 ids
+            int prev = -1;
+            for (int k = 0; k < n_wall; k++) {
+                int id = 0x7fffffff;
+                for (int t = 0; t < n_wall; t++)
+                    if (wall_id[t] > prev && wall_id[t] < id) id = wall_id[t];
+                prev = id;
+                const double2 s01 = __ldg(reinterpret_cast<const double2 *>(p.segs + id));
+                const double2 s23 = __ldg(reinterpret_cast<const double2 *>(p.segs + id) + 1);
+                double px, py;
+                line_intersection(ray, make_double4(s01.x, s01.y, s23.x, s23.y), &px, &py);
+                fn(px, py);
+            }
+        }
+    };
+    for_each_wall_point([&](double px, double py) { add_point(px, py); });
+    const int walls = n_points;
+
+    // ---- g.player.Unit (:100-132)
+    if (player_block) {
+        const pm3d_collider pl = q.colliders[q.player];
+        if (fabs(pl.x - newX) <= prox && fabs(pl.y - newY) <= prox) {
+            double smin, smax, tmin, tmax, zI = -1;
+            z_min_max(newZ, m.height, m.anchor, smin, smax);
+            z_min_max(pl.z, pl.height, pl.anchor, tmin, tmax);
+            if (!(smin > tmax || tmin > smax)) {
+                const double mid = smin + (smax - smin) / 2;
+                zI = mid < tmin ? tmin : (mid > tmax ? tmax : mid);
+            }
+            double comb[4];
+            const int nc = line_circle_intersection(posX, posY, newX, newY, pl.x, pl.y, pl.radius + m.radius, comb);
+            if (zI >= 0 && nc > 0) {
+                double extra[8];
+                int n_extra = 0;
+                for (int k = 0; k < nc; k++) {
+                    double got[4];
+                    const int ng = line_circle_intersection(comb[k * 2], comb[k * 2 + 1], pl.x, pl.y, pl.x, pl.y, pl.radius, got);
+                    for (int g = 0; g < ng; g++) {
+                        extra[n_extra * 2] = got[g * 2]; extra[n_extra * 2 + 1] = got[g * 2 + 1]; n_extra++;
+                        add_point(got[g * 2], got[g * 2 + 1]);
+                    }
+                    // :123-127 appends one collision per point of intersectPoints so far — wall points included
+                    if (walls > 0) for_each_wall_point([&](double px, double py) { consider(q.player, px, py, zI); });
+                    for (int e = 0; e < n_extra; e++) consider(q.player, extra[e * 2], extra[e * 2 + 1], zI);
+                }
+            }
+        }
+    }
+
+    // ---- collidable sprites (:135-194), list order
+    for (int s = 0; s < q.n_colliders; s++) {
+        if (s == q.player || s == m.self || s == m.parent) continue;
+        const pm3d_collider *sp = q.colliders + s;
+        const double sx = sp->x, sy = sp->y;
+        if (!(fabs(sx - newX) <= prox && fabs(sy - newY) <= prox)) continue;
+        const double srad = sp->radius;
+        if (srad <= 0 || sp->destroyed) continue;
+        double smin, smax, tmin, tmax;
+        z_min_max(newZ, m.height, m.anchor, smin, smax);
+        z_min_max(sp->z, sp->height, sp->anchor, tmin, tmax);
+        if (smin > tmax || tmin > smax) continue;
+        const double mid = smin + (smax - smin) / 2;
+        const double zI = mid < tmin ? tmin : (mid > tmax ? tmax : mid);
+        if (zI < 0) continue;
+        const double comb_r = srad + m.radius;
+        double comb[4];
+        const int nc = line_circle_intersection(posX, posY, newX, newY, sx, sy, comb_r, comb);
+        bool circle_hit = false;
+        for (int k = 0; k < nc; k++) {
+            double got[4];
+            const int ng = line_circle_intersection(comb[k * 2], comb[k * 2 + 1], sx, sy, sx, sy, srad, got);
+            for (int g = 0; g < ng; g++) {
+                circle_hit = true;
+                add_point(got[g * 2], got[g * 2 + 1]);
+                consider(s, got[g * 2], got[g * 2 + 1], zI);
+            }
+        }
+        if (!circle_hit && sqrt(sqd(sx - newX) + sqd(sy - newY)) <= comb_r) {  // inside the circle without touching it
+            add_point(newX, newY);
+            consider(s, newX, newY, zI);
+        }
+    }
+
+    r.n_points = n_points;
+    r.n_collisions = n_collisions;
+    if (n_points > 0) {  // :202, :307-311 "cannot move"
+        r.collided = 1;
+        q.out[i] = r;
+        return;
+    }
+    // ---- :314-352 map clamp, level-0 cell test, floor clamp
+    int64_t ix = go_int(newX), iy = go_int(newY);
+    if (ix < 0 || newX < 0) { newX = p.clip; ix = 0; }
+    else if (ix >= p.map_w) { newX = (double)p.map_w - p.clip; ix = go_int(newX); }
+    if (iy < 0 || newY < 0) { newY = p.clip; iy = 0; }
+    else if (iy >= p.map_h) { newY = (double)p.map_h - p.clip; iy = go_int(newY); }
+    ix = ix > p.map_w - 1 ? p.map_w - 1 : (ix < 0 ? 0 : ix);
+    iy = iy > p.map_h - 1 ? p.map_h - 1 : (iy < 0 ? 0 : iy);
+    if (__ldg(p.grid0 + ix * p.map_h + iy) == 0) { posX = newX; posY = newY; }
+    else r.collided = 1;
+    posZ = newZ;
+    double zMin, zMax;
+    z_min_max(0.0, m.height, m.anchor, zMin, zMax);
+    zMin = fabs(zMin);
+    if (posZ < zMin) { posZ = zMin; r.collided = 1; }
+    r.x = posX; r.y = posY; r.z = posZ;
+    q.out[i] = r;
+}
+
 static int ensure_io(pm3d_ctx *ctx, void **buf, size_t *have, size_t need) {
     if (*have >= need) return PM3D_OK;
     if (*buf) PM3D_CUDA(ctx, cudaFree(*buf));
@@ -372,4 +629,68 @@ extern "C" int pm3d_los_batch(pm3d_ctx *ctx, const double *rays, int64_t n, uint
 extern "C" int pm3d_move_batch(pm3d_ctx *ctx, const double *moves, int64_t n, double clip_distance, double *out_pos,
                                uint8_t *out_collided, uint32_t flags) {
     return run_batch(ctx, true, moves, n, clip_distance, out_pos, out_collided, flags);
+}
+
+extern "C" int pm3d_upload_colliders(pm3d_ctx *ctx, const pm3d_collider *colliders, int n, int player_index) {
+    if (!ctx) return PM3D_ERR_ARG;
+    if (n < 0 || (n > 0 && !colliders) || player_index < -1 || player_index >= n)
+        return pm3d_fail(ctx, PM3D_ERR_ARG, "bad collider list (n = %d, player_index = %d)", n, player_index);
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->colliders) PM3D_CUDA(ctx, cudaFree(ctx->colliders));
+    ctx->colliders = nullptr;
+    PM3D_CUDA(ctx, cudaMalloc((void **)&ctx->colliders, sizeof(pm3d_collider) * (size_t)(n > 0 ? n : 1)));
+    if (n) PM3D_CUDA(ctx, cudaMemcpyAsync(ctx->colliders, colliders, sizeof(pm3d_collider) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->n_colliders = n;
+    ctx->player_index = player_index;
+    return PM3D_OK;
+}
+
+extern "C" int pm3d_valid_move_batch(pm3d_ctx *ctx, const pm3d_mover *movers, int64_t n, double clip_distance,
+                                     pm3d_move_result *out, uint32_t flags) {
+    if (!ctx) return PM3D_ERR_ARG;
+    if (n < 0 || (n > 0 && (!movers || !out))) return pm3d_fail(ctx, PM3D_ERR_ARG, "null batch pointers");
+    if (!ctx->cell_start) return pm3d_fail(ctx, PM3D_ERR_ARG, "pm3d_upload_segments must be called first");
+    if (!ctx->grid) return pm3d_fail(ctx, PM3D_ERR_ARG, "pm3d_upload_grid must be called first");
+    if (!ctx->colliders) return pm3d_fail(ctx, PM3D_ERR_ARG, "pm3d_upload_colliders must be called first (n = 0 is fine)");
+    if (n == 0) return PM3D_OK;
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool in_dev = flags & PM3D_IN_DEVICE, out_dev = flags & PM3D_OUT_DEVICE;
+    const pm3d_mover *d_in = movers;
+    pm3d_move_result *d_out = out;
+    int rc;
+    if (!in_dev) {
+        if ((rc = ensure_io(ctx, &ctx->io_a, &ctx->io_a_bytes, (size_t)n * sizeof(pm3d_mover)))) return rc;
+        PM3D_CUDA(ctx, cudaMemcpyAsync(ctx->io_a, movers, (size_t)n * sizeof(pm3d_mover), cudaMemcpyHostToDevice, ctx->stream));
+        d_in = (const pm3d_mover *)ctx->io_a;
+    }
+    if (!out_dev) {
+        if ((rc = ensure_io(ctx, &ctx->io_c, &ctx->io_c_bytes, (size_t)n * sizeof(pm3d_move_result)))) return rc;
+        d_out = (pm3d_move_result *)ctx->io_c;
+    }
+    MoveParams q;
+    LosParams &p = q.los;
+    p.rays = nullptr;
+    p.segs = (const double4 *)ctx->segs;
+    p.seg_irect = ctx->seg_irect;
+    p.cell_start = ctx->cell_start;
+    p.cell_items = ctx->cell_items;
+    p.cell_rec = ctx->cell_rec;
+    p.n = n;
+    p.n_segs = ctx->n_segs;
+    p.bin_x0 = ctx->bin_x0; p.bin_y0 = ctx->bin_y0; p.bin_w = ctx->bin_w; p.bin_h = ctx->bin_h;
+    p.grid0 = ctx->grid;
+    p.map_w = ctx->map_w; p.map_h = ctx->map_h;
+    p.clip = clip_distance;
+    p.out_flag = nullptr; p.out_pos = nullptr;
+    q.movers = d_in; q.colliders = ctx->colliders; q.out = d_out;
+    q.n_colliders = ctx->n_colliders; q.player = ctx->player_index;
+    const long long blocks = (n + 127) / 128;
+    if (blocks > 0x7fffffffll) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "batch too large");
+    k_valid_move<<<(unsigned)blocks, 128, 0, ctx->stream>>>(q);
+    ctx->launches++;
+    PM3D_CUDA(ctx, cudaGetLastError());
+    if (!out_dev) PM3D_CUDA(ctx, cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(pm3d_move_result), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!(flags & PM3D_NO_SYNC)) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PM3D_OK;
 }

@@ -86,10 +86,10 @@ void pm3d_destroy(pm3d_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     void *ptrs[] = {ctx->grid, ctx->dist, ctx->wall_lut, ctx->atlas, ctx->floor_tiles, ctx->sheet_pixels, ctx->sheet_info,
-                    ctx->views, ctx->col_span, ctx->col_tt, ctx->col_ps, ctx->flo_xw, ctx->flo_yw, ctx->flo_dw, ctx->flo_rc, ctx->flo_fs, ctx->agg, ctx->zbuf, ctx->row_rec, ctx->dbg_cols, ctx->sprites,
+                    ctx->views, ctx->col_span, ctx->col_tt, ctx->col_ps, ctx->flo_xw, ctx->flo_yw, ctx->flo_dw, ctx->flo_rc, ctx->flo_dx, ctx->flo_dy, ctx->flo_fs, ctx->agg, ctx->zbuf, ctx->row_rec, ctx->dbg_cols, ctx->sprites,
                     ctx->sprite_offset, ctx->draw_rec, ctx->n_draw, ctx->bin_list, ctx->bin_rect, ctx->bin_count, ctx->rects,
                     ctx->conv, ctx->frame, ctx->checksums, ctx->segs, ctx->seg_irect, ctx->cell_start,
-                    ctx->cell_items, ctx->cell_rec, ctx->inbuf, ctx->io_a, ctx->io_b, ctx->io_c, ctx->flush_buf};
+                    ctx->cell_items, ctx->cell_rec, ctx->colliders, ctx->inbuf, ctx->io_a, ctx->io_b, ctx->io_c, ctx->flush_buf};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (ctx->stage) cudaFreeHost(ctx->stage);
@@ -310,6 +310,8 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
     if ((rc = dev_realloc(ctx, &ctx->flo_yw, V * W))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->flo_dw, V * W))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->flo_rc, V * W))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->flo_dx, V * W))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->flo_dy, V * W))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->flo_fs, V * W))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->agg, V * L * ctx->n_groups * 2))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->zbuf, V * W))) return rc;

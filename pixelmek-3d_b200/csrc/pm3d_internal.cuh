@@ -18,7 +18,8 @@
 //   col_ps    ulonglong2  pos0, step2: texel row of screen row y = (pos0 + y*step2) >> 33 (mod 2^64)
 // and the level-0 floor-cast parameters as [view][column]:
 //   flo_xw, flo_yw, flo_dw  double  floorXWall, floorYWall, distWall
-//   flo_rc                  double  RN(1/distWall) when exp_mid(distWall), else 0 (compose then divides)
+//   flo_rc                  double  RN(1/distWall) when the column is eligible for the fast floor cast, else 0
+//   flo_dx, flo_dy          double  RN(floorXWall*texSize - posX*texSize), same for Y (fast floor cast)
 //   flo_fs                  int     first floor row (drawEnd + 1, or h when none)
 // plus one aggregate per (view, level, 64-column group, 32-column half):
 //   agg  int4  x: min ya over drawn slices (INT_MAX if none); y: min fs; z: max fs (level 0 only)
@@ -90,7 +91,7 @@ struct pm3d_ctx {
     int2 *col_span = nullptr;        // [views][levels][w]
     uint2 *col_tt = nullptr;
     ulonglong2 *col_ps = nullptr;
-    double *flo_xw = nullptr, *flo_yw = nullptr, *flo_dw = nullptr, *flo_rc = nullptr;  // [views][w]
+    double *flo_xw = nullptr, *flo_yw = nullptr, *flo_dw = nullptr, *flo_rc = nullptr, *flo_dx = nullptr, *flo_dy = nullptr;  // [views][w]
     int32_t *flo_fs = nullptr;
     int4 *agg = nullptr;             // [views][levels][n_groups][2]
     double *zbuf = nullptr;          // [views][w]
@@ -142,6 +143,8 @@ struct pm3d_ctx {
     int32_t *cell_items = nullptr;
     int4 *cell_rec = nullptr;        // count + first three candidate ids (or offset) per bin cell
     int bin_x0 = 0, bin_y0 = 0, bin_w = 0, bin_h = 0;
+    pm3d_collider *colliders = nullptr;  // g.player.Unit + collidable sprites (pm3d_upload_colliders)
+    int n_colliders = 0, player_index = -1;
     void *io_a = nullptr, *io_b = nullptr, *io_c = nullptr;  // batch staging on device
     size_t io_a_bytes = 0, io_b_bytes = 0, io_c_bytes = 0;
 
@@ -205,6 +208,32 @@ __device__ __forceinline__ double div_by_rcp(double a, double b, double r) {
     const double q1 = __fma_rn(e0, r, q0);
     const double e1 = __fma_rn(-b, q1, a);
     return __fma_rn(e1, r, q1);
+}
+
+// ---- fast floor cast --------------------------------------------------------------------------
+// The reference evaluates, per floor pixel (all binary64, every operation rounded):
+//     weight = currentDist / distWall
+//     fx     = weight * floorXWall + (1 - weight) * posX          (same for y)
+//     cell   = int(fx),  texel = int(fx * texSize) % texSize
+// Only the INTEGER int(fx * texSize) =: int(t) matters (cell = int(t) >> log2 texSize, texSize a power of two, so
+// the scaling is exact).  The kernel evaluates t' = fma(w', D, P) with w' = RN(cd * RN(1/distWall)),
+// D = RN(X1 - P), X1 = floorXWall * texSize, P = posX * texSize, then m = RN(t' + 2^32): for t' in
+// [0, 2^32) the low 20 mantissa bits of m are the fraction of t' rounded to nearest in units of 2^-20 and the
+// next 32 bits are its integer part (negative t' decode to >= 2^32 - 2^29, i.e. "out of bounds").
+// Error bound, for |w| <= 4 and |X1|, |P| <= 2^24 (cast_kernel.cuh marks eligible columns, the compose kernel
+// checks cd <= 4 |distWall| per lane row), with u = 2^-53 and T the real-number value:
+//     |t  - T| <= u (2|W||X1| + |P|(|W| + 2|1-W|) + |t|)  <= 38 * 2^24 u
+//     |t' - T| <= u (3|W||D| + |t'|)                       <= 40 * 2^24 u        => |t - t'| < 2^-22.7
+// so whenever the rounded fraction is NOT zero (t' farther than 2^-21 from every integer) int(t') = int(t) and
+// both lie on the same side of the map bounds.  A zero fraction (probability ~2^-20 per coordinate) sends the
+// lane to the reference sequence.  tests: parity suite (every frame is compared bit for bit with the oracle,
+// PM3D_OPT_FORCE_PAINTER runs the reference sequence everywhere) + pm3d_selfcheck_floor (selfcheck.cu).
+#define PM3D_FLOOR_MAGIC 4294967296.0
+__device__ __forceinline__ bool floor_fast_index(double w, double D, double P, uint32_t bound, uint32_t &idx) {
+    const double m = __fma_rn(w, D, P) + PM3D_FLOOR_MAGIC;
+    const uint32_t lo = (uint32_t)__double2loint(m), hi = (uint32_t)__double2hiint(m);
+    idx = __funnelshift_r(lo, hi, 20);
+    return (lo & 0xfffffu) != 0u && idx < bound;
 }
 
 // lighting: byte(ClampInt(int(base + sqrt(dist)*falloff + illumination (+ extra)), min, max)) per channel

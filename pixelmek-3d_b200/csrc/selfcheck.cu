@@ -5,6 +5,12 @@
 // uniform mantissas over a wide exponent range, divisors with all-ones / all-zero / single-bit mantissas,
 // quotients engineered to sit next to rounding boundaries (a = b * m with m +- a few ulps, and
 // a = RN(b * (m + 1/2 ulp))), and operands drawn from the path's own value range.
+//
+// pm3d_selfcheck_floor: floor_fast_index (pm3d_internal.cuh "fast floor cast") against the reference sequence
+// int((weight*floorXWall + (1-weight)*posX) * texSize) on eligible operands — uniformly random ones and ones
+// steered to within a few thousand ulps of an integer texel boundary, where the two roundings could disagree.
+// Whenever the fast path accepts (non-zero rounded fraction, index below the bound) its index must equal the
+// reference's and the reference coordinate must be non-negative.
 #include "pm3d_internal.cuh"
 
 __device__ __forceinline__ uint64_t sm64(uint64_t &s) {
@@ -57,6 +63,72 @@ __global__ void k_selfcheck_division(uint64_t seed, int iters, unsigned long lon
     }
     atomicAdd(mismatches, bad);
     atomicAdd(tested, n);
+}
+
+__global__ void k_selfcheck_floor(uint64_t seed, int iters, unsigned long long *counters) {
+    uint64_t s = seed ^ ((uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * 0xD1342543DE82EF95ull);
+    unsigned long long bad = 0, n = 0, accepted = 0;
+    const double U = 1.0 / 9007199254740992.0;
+    for (int it = 0; it < iters; it++) {
+        const uint64_t r0 = sm64(s), r1 = sm64(s), r2 = sm64(s), r3 = sm64(s), r4 = sm64(s);
+        const int shift = 4 + (int)(r4 % 7);                        // texSize 16 .. 1024
+        const double S = (double)(1 << shift);
+        const double span = 16777216.0 / S;                          // coordinates up to 2^24 texels
+        const double scale = (r4 & 0x100) ? span : ((r4 & 0x200) ? 512.0 : 8.0);
+        const double posx = (double)(r0 >> 11) * U * scale;
+        double fxw = (double)(r1 >> 11) * U * scale;
+        if (r4 & 0x400) fxw = floor(fxw);                            // wall faces sit on integers
+        const double dw = 1e-2 + (double)(r2 >> 11) * U * ((r4 & 0x800) ? 1e3 : 10.0);
+        double cd = (double)(r3 >> 11) * U * 4.0 * dw;
+        const double rc = 1.0 / dw;
+        const double X1 = fxw * S, P = posx * S, D = X1 - P;
+        if ((r4 >> 16) & 1) {
+            // steer t = P + w*D next to an integer n: w = (n - P)/D, cd = w*dw, then nudge by up to 2^14 ulps
+            const double t0 = P + (cd * rc) * D;
+            const double nn = floor(t0 + 0.5);
+            const double w = (nn - P) / D;
+            if (w > 0.0 && w <= 3.999 && fabs(D) > 1e-6) {
+                cd = w * dw;
+                long long cb = __double_as_longlong(cd) + (long long)((r4 >> 20) % 32769) - 16384;
+                cd = __longlong_as_double(cb);
+            }
+        }
+        if (!(cd > 0.0) || !exp_mid(cd) || !(cd <= 4.0 * dw)) continue;
+        // reference sequence (game path: no contraction)
+        const double weight = cd / dw;
+        const double fx = weight * fxw + (1.0 - weight) * posx;
+        const double t = fx * S;
+        uint32_t idx;
+        const bool ok = floor_fast_index(cd * rc, D, P, 0x80000000u, idx);
+        n++;
+        if (ok) {
+            accepted++;
+            if (!(fx >= 0.0) || (uint32_t)(long long)t != idx) bad++;
+        }
+    }
+    atomicAdd(counters, bad);
+    atomicAdd(counters + 1, n);
+    atomicAdd(counters + 2, accepted);
+}
+
+extern "C" int pm3d_selfcheck_floor(pm3d_ctx *ctx, uint64_t seed, int blocks, int iters, uint64_t *out_mismatches,
+                                    uint64_t *out_tested, uint64_t *out_accepted) {
+    if (!ctx || blocks < 1 || iters < 1 || !out_mismatches || !out_tested || !out_accepted) return PM3D_ERR_ARG;
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned long long *d = nullptr;
+    PM3D_CUDA(ctx, cudaMalloc((void **)&d, 24));
+    PM3D_CUDA(ctx, cudaMemsetAsync(d, 0, 24, ctx->stream));
+    k_selfcheck_floor<<<blocks, 256, 0, ctx->stream>>>(seed, iters, d);
+    ctx->launches++;
+    PM3D_CUDA(ctx, cudaGetLastError());
+    unsigned long long h[3] = {0, 0, 0};
+    PM3D_CUDA(ctx, cudaMemcpyAsync(h, d, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PM3D_CUDA(ctx, cudaFree(d));
+    *out_mismatches = h[0];
+    *out_tested = h[1];
+    *out_accepted = h[2];
+    return PM3D_OK;
 }
 
 extern "C" int pm3d_selfcheck_division(pm3d_ctx *ctx, uint64_t seed, int blocks, int iters, uint64_t *out_mismatches,

@@ -75,8 +75,8 @@ __device__ __forceinline__ void view_setup(const ViewParams &p, const int view) 
         if (y < horizon) v = (uint32_t)((((uint64_t)(2 * (int64_t)y + 1)) * sky_step) >> 33);
         else v = (uint32_t)((((uint64_t)(2 * ((int64_t)y - horizon) + 1)) * box_step) >> 33);
         if (v > (uint32_t)p.tex_size - 1) v = p.tex_size - 1;
-        // bit 29: the row distance is mid-range, so weight = cd / distWall may use the reciprocal path
-        r.info = (valid ? 0x80000000u : 0u) | (y < horizon ? 0x40000000u : 0u) | (exp_mid(r.cd) ? 0x20000000u : 0u) | v;
+        // bit 29: the row distance is positive and mid-range: weight = cd / distWall may use the reciprocal paths
+        r.info = (valid ? 0x80000000u : 0u) | (y < horizon ? 0x40000000u : 0u) | ((exp_mid(r.cd) && r.cd > 0.0) ? 0x20000000u : 0u) | v;
         p.row_rec[(size_t)view * p.h + y] = r;
     }
 

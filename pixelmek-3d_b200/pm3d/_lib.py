@@ -67,6 +67,27 @@ assert COLUMN_DTYPE.itemsize == 56
 CONV_DTYPE = np.dtype([("distance", "<f8"), ("point_x", "<f8"), ("point_y", "<f8"), ("sprite", "<i4"), ("_pad", "<i4")])
 assert CONV_DTYPE.itemsize == 32
 
+MOVER_DTYPE = np.dtype(
+    [
+        ("pos_x", "<f8"), ("pos_y", "<f8"), ("pos_z", "<f8"), ("move_x", "<f8"), ("move_y", "<f8"), ("move_z", "<f8"),
+        ("radius", "<f8"), ("height", "<f8"), ("self", "<i4"), ("parent", "<i4"),
+        ("anchor", "u1"), ("destroyed", "u1"), ("_pad", "u1", (6,)),
+    ]
+)
+assert MOVER_DTYPE.itemsize == 80
+
+COLLIDER_DTYPE = np.dtype(
+    [("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("radius", "<f8"), ("height", "<f8"),
+     ("anchor", "u1"), ("destroyed", "u1"), ("_pad", "u1", (6,))]
+)
+assert COLLIDER_DTYPE.itemsize == 48
+
+MOVE_RESULT_DTYPE = np.dtype(
+    [("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("collided", "<i4"), ("n_collisions", "<i4"), ("first_entity", "<i4"),
+     ("n_points", "<i4"), ("first_x", "<f8"), ("first_y", "<f8"), ("first_z", "<f8"), ("near_x", "<f8"), ("near_y", "<f8")]
+)
+assert MOVE_RESULT_DTYPE.itemsize == 80
+
 # every symbol include/pm3d.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -93,6 +114,8 @@ SYMBOLS = {
     "pm3d_upload_segments": (C.c_int, [_P, _P, C.c_int]),
     "pm3d_los_batch": (C.c_int, [_P, _P, C.c_int64, _P, C.c_uint32]),
     "pm3d_move_batch": (C.c_int, [_P, _P, C.c_int64, C.c_double, _P, _P, C.c_uint32]),
+    "pm3d_upload_colliders": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "pm3d_valid_move_batch": (C.c_int, [_P, _P, C.c_int64, C.c_double, _P, C.c_uint32]),
     "pm3d_generate_wall_collision_lines": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double, _P, C.c_int]),
     "pm3d_device_alloc": (C.c_int, [_P, C.c_int64, C.POINTER(_P)]),
     "pm3d_device_free": (C.c_int, [_P, _P]),
@@ -107,6 +130,7 @@ SYMBOLS = {
     "pm3d_ktimer_collect": (C.c_int, [_P, _P, C.c_int]),
     "pm3d_launch_count": (C.c_int64, [_P]),
     "pm3d_flush_l2": (C.c_int, [_P]),
+    "pm3d_selfcheck_floor": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pm3d_selfcheck_division": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 }
 

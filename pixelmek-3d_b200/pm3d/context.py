@@ -6,7 +6,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import COLUMN_DTYPE, CONV_DTYPE, SPRITE_DTYPE, VIEW_DTYPE, Pm3dError, ptr
+from ._lib import (COLLIDER_DTYPE, COLUMN_DTYPE, CONV_DTYPE, MOVE_RESULT_DTYPE, MOVER_DTYPE, SPRITE_DTYPE, VIEW_DTYPE,
+                   Pm3dError, ptr)
 from .scene import SceneData
 
 
@@ -183,6 +184,20 @@ class Context:
         self._check(self.lib.pm3d_move_batch(self.h, ptr(moves), n, float(clip), ptr(pos), ptr(col), 0), "pm3d_move_batch")
         return pos, col
 
+    def upload_colliders(self, colliders: np.ndarray, player_index: int = -1):
+        """g.player.Unit + the collidable sprites, in the order the host walks them."""
+        colliders = np.ascontiguousarray(colliders, dtype=COLLIDER_DTYPE).reshape(-1)
+        self._check(self.lib.pm3d_upload_colliders(self.h, ptr(colliders) if len(colliders) else None, len(colliders),
+                                                   int(player_index)), "pm3d_upload_colliders")
+
+    def valid_move_batch(self, movers: np.ndarray, clip: float) -> np.ndarray:
+        """Game.getValidMove(entity, x, y, z, checkAlternate=false) for every mover."""
+        movers = np.ascontiguousarray(movers, dtype=MOVER_DTYPE).reshape(-1)
+        out = np.zeros(len(movers), dtype=MOVE_RESULT_DTYPE)
+        self._check(self.lib.pm3d_valid_move_batch(self.h, ptr(movers), len(movers), float(clip), ptr(out), 0),
+                    "pm3d_valid_move_batch")
+        return out
+
     # ------------------------------------------------------------------ device memory + timers
     def device_alloc(self, nbytes: int) -> int:
         p = C.c_void_p()
@@ -220,6 +235,13 @@ class Context:
 
     def flush_l2(self):
         self._check(self.lib.pm3d_flush_l2(self.h), "pm3d_flush_l2")
+
+    def selfcheck_floor(self, seed: int, blocks: int, iters: int) -> tuple[int, int, int]:
+        """(mismatches, operand sets tested, sets the fast path accepted) of the fast floor cast on the device."""
+        bad, n, acc = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.pm3d_selfcheck_floor(self.h, int(seed), int(blocks), int(iters), C.byref(bad), C.byref(n),
+                                                  C.byref(acc)), "pm3d_selfcheck_floor")
+        return int(bad.value), int(n.value), int(acc.value)
 
     def selfcheck_division(self, seed: int, blocks: int, iters: int) -> tuple[int, int]:
         """(mismatches, pairs tested) of the division-free floor-cast quotient against `/` on the device."""

@@ -195,6 +195,15 @@ def test_division_free_floor_weight_is_correctly_rounded(gpu_ctx):
     assert bad == 0, f"{bad} of {n} quotients differ from a / b"
 
 
+def test_fast_floor_cast_index_equals_reference_sequence(gpu_ctx):
+    """compose's fast floor cast (one FMA per coordinate + a rounding-boundary test, pm3d_internal.cuh) must give
+    the reference's texel index whenever it accepts; 1.5e9 operand sets, half of them steered to within 2^14 ulps
+    of an integer texel boundary."""
+    bad, n, acc = gpu_ctx.selfcheck_floor(4242, 148 * 8, 5000)
+    assert n > 1_000_000_000 and acc > n // 4
+    assert bad == 0, f"{bad} of {acc} accepted fast floor casts differ from the reference sequence ({n} tested)"
+
+
 def test_painter_and_front_to_back_paths_agree(gpu_ctx):
     """PM3D_OPT_FORCE_PAINTER runs the literal painter's loop on every pixel; the default
     front-to-back shortcut must give identical bytes (translucent boundary tile + sprite rims)."""

@@ -149,8 +149,11 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
  * shortcut of the compose kernel (A/B check: output must not change); PM3D_OPT_PIPELINE = n
  * (1..4, default 1) keeps n internal frame slots so that, for PM3D_NO_SYNC renders into HOST
  * memory, the device-to-host copy of frame i (on a second stream) overlaps the kernels of frame
- * i+1; results are valid after pm3d_sync.  Call it after pm3d_set_view. */
-enum { PM3D_OPT_KEEP_COLUMNS = 1, PM3D_OPT_FORCE_PAINTER = 2, PM3D_OPT_PIPELINE = 3 };
+ * i+1; results are valid after pm3d_sync.  Call it after pm3d_set_view.  PM3D_OPT_OVERLAP (default 1): the
+ * per-frame intermediate buffers exist twice and the cast/setup launch of frame i+1 runs on a second stream
+ * beside the compose launch of frame i (enqueue-only callers: pm3d_render_resident, PM3D_NO_SYNC); 0 = one
+ * set of buffers, one stream. */
+enum { PM3D_OPT_KEEP_COLUMNS = 1, PM3D_OPT_FORCE_PAINTER = 2, PM3D_OPT_PIPELINE = 3, PM3D_OPT_OVERLAP = 4 };
 int pm3d_set_option(pm3d_ctx *ctx, int option, int value);
 
 /* ------------------------------------------------------------------ frame path
@@ -159,6 +162,8 @@ int pm3d_set_option(pm3d_ctx *ctx, int option, int value);
  *   sprites: all views' sprite snapshots concatenated; sprite_offset[n_views+1] delimits them
  *   out_rgba: n_views * h * w * 4 bytes, premultiplied RGBA8 (NULL = keep on device only)
  *   out_rects: one per sprite (SetScreenRect); out_conv: one per view.  Either may be NULL.
+ *   With PM3D_NO_SYNC every host output (out_rgba, out_rects, out_conv) should be pinned memory
+ *   (pm3d_host_alloc): a copy into pageable memory blocks the caller until the stream reaches it.
  *   flags: PM3D_OUT_DEVICE -> out_rgba is device memory.                                  */
 int pm3d_render(pm3d_ctx *ctx, const pm3d_view *views, int n_views, const pm3d_sprite *sprites,
                 const int32_t *sprite_offset, uint8_t *out_rgba, pm3d_rect *out_rects,

@@ -611,14 +611,14 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     if (const char *e = getenv("PM3D_COMPOSE_ROWS")) rows = atoi(e);      // tuning overrides (tools/)
     if (const char *e = getenv("PM3D_COMPOSE_MINB")) minb = atoi(e);
     dim3 block(COMPOSE_WARPS * 32), grid(ctx->n_groups, (ctx->h + COMPOSE_WARPS * rows - 1) / (COMPOSE_WARPS * rows), n_views);
-    pm3d_kt_mark(ctx, 2, 0);
+    pm3d_kt_mark(ctx, 2, 0, ctx->stream);
     if (rows == 8 && minb == 8) k_compose<8, 8><<<grid, block, 0, ctx->stream>>>(p);
     else if (rows == 8) k_compose<8, 6><<<grid, block, 0, ctx->stream>>>(p);
     else if (rows == 4 && minb == 8) k_compose<4, 8><<<grid, block, 0, ctx->stream>>>(p);
     else if (rows == 4) k_compose<4, 6><<<grid, block, 0, ctx->stream>>>(p);
     else if (minb == 8) k_compose<2, 8><<<grid, block, 0, ctx->stream>>>(p);
     else k_compose<2, 6><<<grid, block, 0, ctx->stream>>>(p);
-    pm3d_kt_mark(ctx, 2, 1);
+    pm3d_kt_mark(ctx, 2, 1, ctx->stream);
     ctx->launches++;
     PM3D_CUDA(ctx, cudaGetLastError());
     return PM3D_OK;

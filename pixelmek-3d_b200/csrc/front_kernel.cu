@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, 4) k_front(CastParams cp, ViewPa
     }
 }
 
-int pm3d_launch_front(pm3d_ctx *ctx, int n_views) {
+int pm3d_launch_front(pm3d_ctx *ctx, int n_views, cudaStream_t stream) {
     CastParams p;
     p.views = ctx->cur_views;
     p.grid = ctx->grid;
@@ -53,10 +53,10 @@ int pm3d_launch_front(pm3d_ctx *ctx, int n_views) {
     const long long n_cast = (n_pairs + VIEW_THREADS / 64 - 1) / (VIEW_THREADS / 64);
     if (n_cast + n_views > 0x7fffffffll) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "too many rays for one launch");
     const unsigned grid = (unsigned)(n_cast + n_views);
-    pm3d_kt_mark(ctx, 0, 0);
-    if (p.dbg) k_front<true><<<grid, VIEW_THREADS, 0, ctx->stream>>>(p, v, (int)n_cast, n_pairs);
-    else k_front<false><<<grid, VIEW_THREADS, 0, ctx->stream>>>(p, v, (int)n_cast, n_pairs);
-    pm3d_kt_mark(ctx, 0, 1);
+    pm3d_kt_mark(ctx, 0, 0, stream);
+    if (p.dbg) k_front<true><<<grid, VIEW_THREADS, 0, stream>>>(p, v, (int)n_cast, n_pairs);
+    else k_front<false><<<grid, VIEW_THREADS, 0, stream>>>(p, v, (int)n_cast, n_pairs);
+    pm3d_kt_mark(ctx, 0, 1, stream);
     ctx->launches++;
     PM3D_CUDA(ctx, cudaGetLastError());
     return PM3D_OK;

@@ -31,15 +31,6 @@ static int dev_realloc(pm3d_ctx *ctx, T **ptr, size_t count) {
     return PM3D_OK;
 }
 
-static int ensure_stage(pm3d_ctx *ctx, size_t bytes) {
-    if (ctx->stage_bytes >= bytes) return PM3D_OK;
-    if (ctx->stage) { PM3D_CUDA(ctx, cudaFreeHost(ctx->stage)); ctx->stage = nullptr; ctx->stage_bytes = 0; }
-    size_t cap = std::max<size_t>(bytes, 1 << 20);
-    PM3D_CUDA(ctx, cudaMallocHost(&ctx->stage, cap));
-    ctx->stage_bytes = cap;
-    return PM3D_OK;
-}
-
 extern "C" {
 
 int pm3d_version(void) { return PM3D_VERSION; }
@@ -68,7 +59,9 @@ int pm3d_create(int device, void *stream, pm3d_ctx **out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     if (stream) {
+        // work the caller orders on its own stream must precede every kernel of a frame: one stream, one set
         ctx->stream = (cudaStream_t)stream;
+        ctx->n_sets = 1;
     } else {
         e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) {
@@ -85,19 +78,27 @@ void pm3d_destroy(pm3d_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->front_stream) cudaStreamSynchronize(ctx->front_stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     void *ptrs[] = {ctx->grid, ctx->dist, ctx->wall_lut, ctx->atlas, ctx->floor_tiles, ctx->sheet_pixels, ctx->sheet_info,
-                    ctx->views, ctx->col_span, ctx->col_tt, ctx->col_ps, ctx->flo_xw, ctx->flo_yw, ctx->flo_dw, ctx->flo_rc, ctx->flo_dx, ctx->flo_dy, ctx->flo_fs, ctx->agg, ctx->zbuf, ctx->row_rec, ctx->dbg_cols, ctx->sprites,
-                    ctx->sprite_offset, ctx->draw_rec, ctx->n_draw, ctx->bin_list, ctx->bin_rect, ctx->bin_count, ctx->rects,
-                    ctx->conv, ctx->frame, ctx->checksums, ctx->segs, ctx->seg_irect, ctx->cell_start,
-                    ctx->cell_items, ctx->cell_rec, ctx->colliders, ctx->inbuf, ctx->io_a, ctx->io_b, ctx->io_c, ctx->flush_buf};
+                    ctx->views, ctx->sprites, ctx->sprite_offset, ctx->frame, ctx->checksums, ctx->segs, ctx->seg_irect,
+                    ctx->cell_start, ctx->cell_items, ctx->cell_rec, ctx->colliders, ctx->io_a, ctx->io_b, ctx->io_c, ctx->flush_buf};
     for (void *p : ptrs)
         if (p) cudaFree(p);
-    if (ctx->stage) cudaFreeHost(ctx->stage);
+    for (auto &fs : ctx->sets) {
+        for (void *p : fs.p)
+            if (p) cudaFree(p);
+        if (fs.inbuf) cudaFree(fs.inbuf);
+        if (fs.stage) cudaFreeHost(fs.stage);
+        if (fs.ev_stage) cudaEventDestroy(fs.ev_stage);
+        if (fs.ev_front) cudaEventDestroy(fs.ev_front);
+        if (fs.ev_compose) cudaEventDestroy(fs.ev_compose);
+    }
+    if (ctx->front_stream) cudaStreamDestroy(ctx->front_stream);
     for (int i = 0; i < 16; i++) {
         if (ctx->ev_start[i]) cudaEventDestroy(ctx->ev_start[i]);
         if (ctx->ev_stop[i]) cudaEventDestroy(ctx->ev_stop[i]);
     }
-    if (ctx->stage_ev) cudaEventDestroy(ctx->stage_ev);
     for (int i = 0; i < 4; i++) {
         if (ctx->frame_ring[i]) cudaFree(ctx->frame_ring[i]);
         if (ctx->ev_rendered[i]) cudaEventDestroy(ctx->ev_rendered[i]);
@@ -112,6 +113,7 @@ void pm3d_destroy(pm3d_ctx *ctx) {
 
 int pm3d_sync(pm3d_ctx *ctx) {
     if (!ctx) return PM3D_ERR_ARG;
+    if (ctx->front_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->front_stream));
     PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->copy_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     return PM3D_OK;
@@ -264,6 +266,14 @@ int pm3d_set_option(pm3d_ctx *ctx, int option, int value) {
     case PM3D_OPT_FORCE_PAINTER:
         ctx->force_painter = value ? 1 : 0;
         return PM3D_OK;
+    case PM3D_OPT_OVERLAP:
+        PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+        if (ctx->front_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->front_stream));
+        PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->n_sets = value ? 2 : 1;
+        ctx->cur_set = 0;
+        if (ctx->w > 0) return pm3d_set_view(ctx, ctx->w, ctx->h, ctx->max_views, ctx->max_sprites);
+        return PM3D_OK;
     case PM3D_OPT_PIPELINE: {
         if (value < 1 || value > 4) return pm3d_fail(ctx, PM3D_ERR_ARG, "pipeline depth must be 1..4");
         if (ctx->w < 1) return pm3d_fail(ctx, PM3D_ERR_ARG, "pm3d_set_view must precede PM3D_OPT_PIPELINE");
@@ -297,38 +307,60 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
         return pm3d_fail(ctx, PM3D_ERR_ARG, "bad view size / capacity");
     if (ctx->num_levels < 1) return pm3d_fail(ctx, PM3D_ERR_ARG, "pm3d_upload_grid must precede pm3d_set_view");
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->front_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->front_stream));
     PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     ctx->w = width; ctx->h = height; ctx->max_views = max_views; ctx->max_sprites = max_sprites_total;
     ctx->n_groups = (width + 63) / 64;
     const size_t V = max_views, L = ctx->num_levels, W = width, H = height, S = std::max(max_sprites_total, 1);
     int rc;
     if ((rc = dev_realloc(ctx, &ctx->views, V))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->col_span, V * L * W))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->col_tt, V * L * W))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->col_ps, V * L * W))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->flo_xw, V * W))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->flo_yw, V * W))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->flo_dw, V * W))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->flo_rc, V * W))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->flo_dx, V * W))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->flo_dy, V * W))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->flo_fs, V * W))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->agg, V * L * ctx->n_groups * 2))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->zbuf, V * W))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->row_rec, V * H))) return rc;
-    if (ctx->keep_columns) {
-        if ((rc = dev_realloc(ctx, &ctx->dbg_cols, V * L * W))) return rc;
-        ctx->dbg_levels = (int)L; ctx->dbg_views = (int)V;
-    }
     if ((rc = dev_realloc(ctx, &ctx->sprites, S))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->sprite_offset, V + 1))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->draw_rec, S))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->n_draw, V))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->bin_list, S * ctx->n_groups))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->bin_rect, S * ctx->n_groups))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->bin_count, V * ctx->n_groups))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->rects, S))) return rc;
-    if ((rc = dev_realloc(ctx, &ctx->conv, V))) return rc;
+    if (!ctx->front_stream) PM3D_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->front_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        pm3d_ctx::FrameSet &fs = ctx->sets[k];
+        pm3d_load_set(ctx, k);
+        if (k >= ctx->n_sets) {  // PM3D_OPT_OVERLAP = 0: the second set is released
+#define X(f) if (ctx->f) { PM3D_CUDA(ctx, cudaFree(ctx->f)); ctx->f = nullptr; }
+            PM3D_FRAME_FIELDS(X)
+#undef X
+            pm3d_save_set(ctx, k);
+            continue;
+        }
+        if ((rc = dev_realloc(ctx, &ctx->col_span, V * L * W))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->col_tt, V * L * W))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->col_ps, V * L * W))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->flo_xw, V * W))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->flo_yw, V * W))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->flo_dw, V * W))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->flo_rc, V * W))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->flo_dx, V * W))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->flo_dy, V * W))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->flo_fs, V * W))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->agg, V * L * ctx->n_groups * 2))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->zbuf, V * W))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->row_rec, V * H))) return rc;
+        if (ctx->keep_columns) {
+            if ((rc = dev_realloc(ctx, &ctx->dbg_cols, V * L * W))) return rc;
+            ctx->dbg_levels = (int)L; ctx->dbg_views = (int)V;
+        }
+        if ((rc = dev_realloc(ctx, &ctx->draw_rec, S))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->n_draw, V))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->bin_list, S * ctx->n_groups))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->bin_rect, S * ctx->n_groups))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->bin_count, V * ctx->n_groups))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->rects, S))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->conv, V))) return rc;
+        pm3d_save_set(ctx, k);
+        if (!fs.ev_front) {
+            PM3D_CUDA(ctx, cudaEventCreateWithFlags(&fs.ev_front, cudaEventDisableTiming));
+            PM3D_CUDA(ctx, cudaEventCreateWithFlags(&fs.ev_compose, cudaEventDisableTiming));
+            PM3D_CUDA(ctx, cudaEventCreateWithFlags(&fs.ev_stage, cudaEventDisableTiming));
+        }
+    }
+    ctx->cur_set = 0;
+    pm3d_load_set(ctx, 0);
     if ((rc = dev_realloc(ctx, &ctx->frame, V * W * H * 4))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->checksums, V))) return rc;
     ctx->last_frame = nullptr;
@@ -340,14 +372,38 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
 // ------------------------------------------------------------------ frame path
 
 // the three kernels of one frame batch; inputs come from ctx->cur_*
+// (the caller selected the frame set: pm3d_begin_frame)
 static int render_core(pm3d_ctx *ctx, int n_views, int n_sprites, uint8_t *target) {
     int rc;
-    if ((rc = pm3d_launch_front(ctx, n_views))) return rc;
+    pm3d_ctx::FrameSet &fs = ctx->sets[ctx->cur_set];
+    const bool overlap = ctx->n_sets > 1;
+    cudaStream_t fstream = overlap ? ctx->front_stream : ctx->stream;
+    if ((rc = pm3d_launch_front(ctx, n_views, fstream))) return rc;
+    if (overlap) {
+        PM3D_CUDA(ctx, cudaEventRecord(fs.ev_front, fstream));
+        PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, fs.ev_front, 0));
+    }
     if ((rc = pm3d_launch_compose(ctx, n_views, target))) return rc;
+    if (overlap) PM3D_CUDA(ctx, cudaEventRecord(fs.ev_compose, ctx->stream));
     if (ctx->kt_on && ctx->kt_n < ctx->kt_cap) ctx->kt_n++;
     ctx->last_frame = target;
     ctx->last_views = n_views;
     ctx->last_sprites = n_sprites;
+    return PM3D_OK;
+}
+
+// Select the frame set of the next frame: the named per-frame fields alias it from here on.  Its previous
+// user (the compose kernel two frames back) must be done before the front stream writes into it, and
+// everything enqueued on the main stream so far (uploads, caller-visible ordering) precedes the frame.
+static int pm3d_begin_frame(pm3d_ctx *ctx, cudaStream_t *fstream) {
+    if (ctx->n_sets > 1) {
+        ctx->cur_set = (ctx->cur_set + 1) % ctx->n_sets;
+        pm3d_load_set(ctx, ctx->cur_set);
+        PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->front_stream, ctx->sets[ctx->cur_set].ev_compose, 0));
+        *fstream = ctx->front_stream;
+    } else {
+        *fstream = ctx->stream;
+    }
     return PM3D_OK;
 }
 
@@ -374,6 +430,8 @@ int pm3d_render_resident(pm3d_ctx *ctx, const pm3d_view *d_views, int n_views, c
         return pm3d_fail(ctx, PM3D_ERR_ARG, "null device pointer");
     if (n_sprites_total > ctx->max_sprites) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "%d sprites > max_sprites_total %d", n_sprites_total, ctx->max_sprites);
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t fstream;
+    if ((rc = pm3d_begin_frame(ctx, &fstream))) return rc;
     ctx->cur_views = d_views; ctx->cur_sprites = d_sprites; ctx->cur_offset = d_sprite_offset;
     return render_core(ctx, n_views, n_sprites_total, d_out_rgba);
 }
@@ -449,46 +507,62 @@ int pm3d_render(pm3d_ctx *ctx, const pm3d_view *views, int n_views, const pm3d_s
     const size_t vb = (size_t)n_views * sizeof(pm3d_view), ob = (size_t)(n_views + 1) * 4,
                  sb = (size_t)n_sprites * sizeof(pm3d_sprite);
     const size_t ob_pad = (ob + 15) & ~(size_t)15;
-    int rc = ensure_stage(ctx, vb + ob_pad + sb);
+    cudaStream_t fstream;
+    int rc = pm3d_begin_frame(ctx, &fstream);
     if (rc) return rc;
-    // a PM3D_NO_SYNC caller may still have the previous frame's H2D copies in flight
-    if (ctx->stage_ev) PM3D_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev));
-    else PM3D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev, cudaEventDisableTiming));
-    uint8_t *st = (uint8_t *)ctx->stage;
+    pm3d_ctx::FrameSet &fs = ctx->sets[ctx->cur_set];
+    const size_t in_bytes = vb + ob_pad + sb;
+    // this set's previous H2D (two frames back for a PM3D_NO_SYNC caller) must have left the staging block
+    PM3D_CUDA(ctx, cudaEventSynchronize(fs.ev_stage));
+    if (fs.stage_bytes < in_bytes) {
+        if (fs.stage) { PM3D_CUDA(ctx, cudaFreeHost(fs.stage)); fs.stage = nullptr; fs.stage_bytes = 0; }
+        const size_t cap = std::max<size_t>(in_bytes, 1 << 20);
+        PM3D_CUDA(ctx, cudaMallocHost(&fs.stage, cap));
+        fs.stage_bytes = cap;
+    }
+    uint8_t *st = (uint8_t *)fs.stage;
     memcpy(st, views, vb);
     memcpy(st + vb, sprite_offset, ob);
     if (sb) memcpy(st + vb + ob_pad, sprites, sb);
     // one H2D for the whole per-frame input block: [views | sprite_offset | sprites]
-    if (ctx->inbuf_bytes < vb + ob_pad + sb) {
-        if (ctx->inbuf) PM3D_CUDA(ctx, cudaFree(ctx->inbuf));
-        ctx->inbuf = nullptr;
-        ctx->inbuf_bytes = std::max<size_t>(vb + ob_pad + sb, (size_t)1 << 16) * 2;
-        PM3D_CUDA(ctx, cudaMalloc((void **)&ctx->inbuf, ctx->inbuf_bytes));
+    if (fs.inbuf_bytes < in_bytes) {
+        PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // frames that still read the old block
+        if (fs.inbuf) PM3D_CUDA(ctx, cudaFree(fs.inbuf));
+        fs.inbuf = nullptr;
+        fs.inbuf_bytes = std::max<size_t>(in_bytes, (size_t)1 << 16) * 2;
+        PM3D_CUDA(ctx, cudaMalloc((void **)&fs.inbuf, fs.inbuf_bytes));
     }
-    PM3D_CUDA(ctx, cudaMemcpyAsync(ctx->inbuf, st, vb + ob_pad + sb, cudaMemcpyHostToDevice, ctx->stream));
-    PM3D_CUDA(ctx, cudaEventRecord(ctx->stage_ev, ctx->stream));
+    PM3D_CUDA(ctx, cudaMemcpyAsync(fs.inbuf, st, in_bytes, cudaMemcpyHostToDevice, fstream));
+    PM3D_CUDA(ctx, cudaEventRecord(fs.ev_stage, fstream));
 
     const bool piped = ctx->ring_n > 1 && out_rgba && !(flags & PM3D_OUT_DEVICE) && (flags & PM3D_NO_SYNC);
     const int slot = ctx->ring_pos;
     uint8_t *target = (out_rgba && (flags & PM3D_OUT_DEVICE)) ? out_rgba : (piped ? ctx->frame_ring[slot] : ctx->frame);
     // the slot's previous frame must have left the device before the compose kernel overwrites it
     if (piped) PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0));
-    ctx->cur_views = (const pm3d_view *)ctx->inbuf;
-    ctx->cur_offset = (const int32_t *)(ctx->inbuf + vb);
-    ctx->cur_sprites = (const pm3d_sprite *)(ctx->inbuf + vb + ob_pad);
+    ctx->cur_views = (const pm3d_view *)fs.inbuf;
+    ctx->cur_offset = (const int32_t *)(fs.inbuf + vb);
+    ctx->cur_sprites = (const pm3d_sprite *)(fs.inbuf + vb + ob_pad);
     if ((rc = render_core(ctx, n_views, n_sprites, target))) return rc;
 
-    // the small results first: they must not queue behind the frame on the D2H copy engine
-    if (out_rects && n_sprites)
-        PM3D_CUDA(ctx, cudaMemcpyAsync(out_rects, ctx->rects, (size_t)n_sprites * sizeof(pm3d_rect), cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_conv)
-        PM3D_CUDA(ctx, cudaMemcpyAsync(out_conv, ctx->conv, (size_t)n_views * sizeof(pm3d_convergence), cudaMemcpyDeviceToHost, ctx->stream));
     const size_t fb = (size_t)n_views * ctx->w * ctx->h * 4;
+    // pipelined: every D2H of this frame goes to the copy stream (small results first), so the main stream
+    // never waits for the copy engine and the next frame's kernels start at once
+    cudaStream_t cs = ctx->stream;
     if (piped) {
         PM3D_CUDA(ctx, cudaEventRecord(ctx->ev_rendered[slot], ctx->stream));
         PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[slot], 0));
-        PM3D_CUDA(ctx, cudaMemcpyAsync(out_rgba, target, fb, cudaMemcpyDeviceToHost, ctx->copy_stream));
-        PM3D_CUDA(ctx, cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
+        cs = ctx->copy_stream;
+    }
+    if (out_rects && n_sprites)
+        PM3D_CUDA(ctx, cudaMemcpyAsync(out_rects, ctx->rects, (size_t)n_sprites * sizeof(pm3d_rect), cudaMemcpyDeviceToHost, cs));
+    if (out_conv)
+        PM3D_CUDA(ctx, cudaMemcpyAsync(out_conv, ctx->conv, (size_t)n_views * sizeof(pm3d_convergence), cudaMemcpyDeviceToHost, cs));
+    // the set's rects/conv have now been read: only after this point may its next frame rewrite them
+    if (ctx->n_sets > 1) PM3D_CUDA(ctx, cudaEventRecord(fs.ev_compose, cs));
+    if (piped) {
+        PM3D_CUDA(ctx, cudaMemcpyAsync(out_rgba, target, fb, cudaMemcpyDeviceToHost, cs));
+        PM3D_CUDA(ctx, cudaEventRecord(ctx->ev_copied[slot], cs));
         ctx->ring_pos = (slot + 1) % ctx->ring_n;
     } else if (out_rgba && !(flags & PM3D_OUT_DEVICE)) {
         PM3D_CUDA(ctx, cudaMemcpyAsync(out_rgba, ctx->frame, fb, cudaMemcpyDeviceToHost, ctx->stream));

@@ -117,6 +117,22 @@ struct pm3d_ctx {
     cudaEvent_t ev_rendered[4] = {}, ev_copied[4] = {};
     uint64_t *checksums = nullptr;   // [max_views]
 
+    // Two sets of the per-frame buffers above (PM3D_FRAME_FIELDS) + input staging, so that the front kernel of
+    // frame i+1 (front_stream) overlaps the compose kernel of frame i (stream).  The named fields above always
+    // alias the set of the frame rendered last (downloads read them); PM3D_OPT_OVERLAP = 0 uses one set/stream.
+    struct FrameSet {
+        void *p[24] = {};
+        uint8_t *inbuf = nullptr;      // device copy of one call's [views | sprite_offset | sprites]
+        size_t inbuf_bytes = 0;
+        void *stage = nullptr;         // pinned host staging of the same block
+        size_t stage_bytes = 0;
+        cudaEvent_t ev_stage = nullptr;    // the H2D out of `stage` has executed
+        cudaEvent_t ev_front = nullptr;    // front kernel done (recorded on front_stream)
+        cudaEvent_t ev_compose = nullptr;  // compose done and the set's results read: the set may be rewritten
+    } sets[2];
+    int n_sets = 2, cur_set = 0;
+    cudaStream_t front_stream = nullptr;
+
     // inputs the kernels read this call (ctx-owned copies, or caller device memory)
     const pm3d_view *cur_views = nullptr;
     const pm3d_sprite *cur_sprites = nullptr;
@@ -127,13 +143,6 @@ struct pm3d_ctx {
     cudaEvent_t *kt_ev = nullptr;  // [kt_cap][3][2]
     int kt_cap = 0, kt_n = 0, kt_on = 0;
 
-    uint8_t *inbuf = nullptr;        // device copy of one call's [views | sprite_offset | sprites]
-    size_t inbuf_bytes = 0;
-
-    // pinned staging for host-side arguments
-    void *stage = nullptr;
-    size_t stage_bytes = 0;
-    cudaEvent_t stage_ev = nullptr;  // recorded after the last H2D out of `stage`
 
     // LOS / collision
     double *segs = nullptr;          // [n_segs][4]
@@ -156,8 +165,24 @@ struct pm3d_ctx {
 
 int pm3d_fail(pm3d_ctx *ctx, int code, const char *fmt, ...);
 // event pair around kernel `k` (0 cast, 1 view setup, 2 compose) of the frame being sampled
-inline void pm3d_kt_mark(pm3d_ctx *ctx, int k, int end) {
-    if (ctx->kt_on && ctx->kt_n < ctx->kt_cap) cudaEventRecord(ctx->kt_ev[(ctx->kt_n * 3 + k) * 2 + end], ctx->stream);
+inline void pm3d_kt_mark(pm3d_ctx *ctx, int k, int end, cudaStream_t stream) {
+    if (ctx->kt_on && ctx->kt_n < ctx->kt_cap) cudaEventRecord(ctx->kt_ev[(ctx->kt_n * 3 + k) * 2 + end], stream);
+}
+// the per-frame device buffers that exist once per frame set
+#define PM3D_FRAME_FIELDS(X)                                                                                       \
+    X(col_span) X(col_tt) X(col_ps) X(flo_xw) X(flo_yw) X(flo_dw) X(flo_rc) X(flo_dx) X(flo_dy) X(flo_fs) X(agg) \
+    X(zbuf) X(row_rec) X(dbg_cols) X(draw_rec) X(n_draw) X(bin_list) X(bin_rect) X(bin_count) X(rects) X(conv)
+inline void pm3d_load_set(pm3d_ctx *ctx, int k) {
+    int i = 0;
+#define X(f) ctx->f = (decltype(ctx->f))ctx->sets[k].p[i++];
+    PM3D_FRAME_FIELDS(X)
+#undef X
+}
+inline void pm3d_save_set(pm3d_ctx *ctx, int k) {
+    int i = 0;
+#define X(f) ctx->sets[k].p[i++] = (void *)ctx->f;
+    PM3D_FRAME_FIELDS(X)
+#undef X
 }
 #define PM3D_CUDA(ctx, call)                                                                         \
     do {                                                                                             \
@@ -166,7 +191,7 @@ inline void pm3d_kt_mark(pm3d_ctx *ctx, int k, int end) {
     } while (0)
 
 // kernel launchers (one per .cu)
-int pm3d_launch_front(pm3d_ctx *ctx, int n_views);  // column cast + per-view setup, one launch
+int pm3d_launch_front(pm3d_ctx *ctx, int n_views, cudaStream_t stream);  // column cast + per-view setup, one launch
 int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out);
 int pm3d_launch_checksum(pm3d_ctx *ctx, int n_views, const uint8_t *frames);
 

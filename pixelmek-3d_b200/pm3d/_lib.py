@@ -17,6 +17,7 @@ PM3D_NO_SYNC = 4
 OPT_KEEP_COLUMNS = 1
 OPT_FORCE_PAINTER = 2
 OPT_PIPELINE = 3
+OPT_OVERLAP = 4
 
 
 class Pm3dError(RuntimeError):

@@ -24,6 +24,7 @@ class Context:
         self.w = self.h_px = 0
         self._keep = []
         self._no_sprites = np.zeros(0, dtype=SPRITE_DTYPE)
+        self._res_ring, self._res_pos = [], 0   # pinned (rects, conv) result buffers for enqueue-only renders
 
     # ------------------------------------------------------------------ plumbing
     def _check(self, rc: int, what: str):
@@ -79,6 +80,13 @@ class Context:
     def set_view(self, w: int, h: int, max_views: int = 1, max_sprites_total: int = 2048):
         self._check(self.lib.pm3d_set_view(self.h, w, h, max_views, max_sprites_total), "pm3d_set_view")
         self.w, self.h_px = w, h
+        # a device-to-host copy into PAGEABLE memory blocks the caller until the stream reaches it, so
+        # PM3D_NO_SYNC renders write their small results (rects, convergence) into a ring of pinned buffers
+        self._res_ring, self._res_pos = [], 0
+        if max(max_sprites_total, 1) * 16 + max_views * 32 <= (1 << 20):
+            for _ in range(8):
+                self._res_ring.append((self.host_alloc(max(max_sprites_total, 1) * 16, np.int32, (max(max_sprites_total, 1), 4)),
+                                       self.host_alloc(max_views * CONV_DTYPE.itemsize, CONV_DTYPE, (max_views,))))
 
     def set_option(self, option: int, value: int):
         self._check(self.lib.pm3d_set_option(self.h, option, value), "pm3d_set_option")
@@ -104,8 +112,14 @@ class Context:
         elif not (isinstance(sprite_offset, np.ndarray) and sprite_offset.dtype == np.int32 and sprite_offset.flags.c_contiguous):
             sprite_offset = np.ascontiguousarray(sprite_offset, dtype=np.int32)
         ns = int(sprite_offset[-1])
-        rects = np.empty((max(ns, 1), 4), dtype=np.int32)
-        conv = np.empty(nv, dtype=CONV_DTYPE)
+        if no_sync and self._res_ring:
+            # pinned slot, valid until 8 more renders were enqueued
+            rects, conv = self._res_ring[self._res_pos]
+            self._res_pos = (self._res_pos + 1) % len(self._res_ring)
+            rects, conv = rects[:max(ns, 1)], conv[:nv]
+        else:
+            rects = np.empty((max(ns, 1), 4), dtype=np.int32)
+            conv = np.empty(nv, dtype=CONV_DTYPE)
         flags = 0
         rgba = None
         out_p = None

@@ -356,3 +356,52 @@ def test_pipelined_frames_equal_synchronous_frames(gpu_ctx):
             assert np.array_equal(got[i]["conv"]["sprite"], want[i]["conv"]["sprite"])
     finally:
         ctx.set_option(pm3d._lib.OPT_PIPELINE, 1)
+
+
+def test_overlapped_frames_equal_serial_frames(gpu_ctx):
+    """PM3D_OPT_OVERLAP (default on): the cast/setup launch of frame i+1 runs beside the compose launch of frame i
+    on a second stream with a second set of intermediate buffers.  Many frames enqueued back to back (resident
+    inputs, and host inputs with PM3D_NO_SYNC) must give the bytes, rectangles and convergence of the serial path."""
+    ctx = gpu_ctx
+    n = 9
+    c = W.config_c2(w=640, h=360, n_sprites=60, n_poses=n)
+    off = c["offsets"]
+    ctx.upload_scene(c["scene"])
+    ctx.set_view(640, 360, 1, 60)
+    fb = 640 * 360 * 4
+
+    def run_resident():
+        d_v, d_s, d_o, d_out = ctx.device_alloc(c["views"].nbytes), ctx.device_alloc(c["sprites"].nbytes), ctx.device_alloc(8), ctx.device_alloc(n * fb)
+        ctx.h2d(d_v, c["views"]); ctx.h2d(d_s, c["sprites"]); ctx.h2d(d_o, np.array([0, 60], np.int32))
+        for rep in range(3):                      # reuse each set several times
+            for i in range(n):
+                ctx.render_resident(d_v + i * 104, 1, d_s + int(off[i]) * 64, d_o, 60, d_out + i * fb)
+        ctx.sync()
+        frames = np.zeros((n, 360, 640, 4), np.uint8)
+        ctx.d2h(frames, d_out)
+        rects, conv = ctx.download_results(60, 1)
+        for p in (d_v, d_s, d_o, d_out):
+            ctx.device_free(p)
+        return frames, rects.copy(), conv.copy()
+
+    def run_host():
+        bufs = [ctx.host_alloc(fb, np.uint8, (1, 360, 640, 4)) for _ in range(n)]
+        got = [ctx.render(c["views"][i:i + 1], c["sprites"][off[i]:off[i + 1]], out=bufs[i], no_sync=True) for i in range(n)]
+        ctx.sync()
+        return got
+
+    try:
+        ctx.set_option(pm3d._lib.OPT_OVERLAP, 0)
+        f0, r0, c0 = run_resident()
+        h0 = [{k: np.copy(v) for k, v in g.items()} for g in run_host()]
+        ctx.set_option(pm3d._lib.OPT_OVERLAP, 1)
+        f1, r1, c1 = run_resident()
+        h1 = run_host()
+    finally:
+        ctx.set_option(pm3d._lib.OPT_OVERLAP, 1)
+    assert np.array_equal(f0, f1)
+    assert np.array_equal(r0, r1) and c0.tobytes() == c1.tobytes()
+    assert len({f0[i].tobytes() for i in range(n)}) == n        # the poses really differ
+    for i in range(n):
+        assert np.array_equal(h0[i]["rgba"], h1[i]["rgba"]) and np.array_equal(h0[i]["rgba"][0], f0[i]), f"frame {i}"
+        assert np.array_equal(h0[i]["rects"], h1[i]["rects"]) and h0[i]["conv"].tobytes() == h1[i]["conv"].tobytes()

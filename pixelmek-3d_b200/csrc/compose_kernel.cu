@@ -90,6 +90,21 @@ __device__ __noinline__ uint32_t sprite_texel(const DrawRec &d, const uint32_t *
     return __ldg(sheet_pixels + d.sheet_px + (uint64_t)ty * d.sheet_w + tx);
 }
 
+// index of the texel sprite `d` shows at pixel (x, y) inside sheet_pixels, or ~0 when it does not cover the pixel
+// (inlined twice in the front-to-back walk so that the loads of two sprites are in flight together)
+#define NO_TEXEL 0xffffffffffffffffull
+__device__ __forceinline__ uint64_t sprite_index(const DrawRec &d, int x, int y, double z) {
+    if (x < d.dsx || x >= d.dex || x <= 0 || y < d.dsy || y >= d.dey) return NO_TEXEL;
+    if (!(d.transformY < z)) return NO_TEXEL;
+    const uint32_t k = (uint32_t)(x - d.dsx);
+    const uint32_t tx = (uint32_t)__umul64hi((uint64_t)k * d.tex_w, d.xmagic);
+    if (tx < d.tx_lo || tx >= d.tx_hi) return NO_TEXEL;
+    uint32_t ty = (uint32_t)((d.ypos0 + (uint64_t)(int64_t)y * d.ystep2) >> 33);
+    if (ty > d.tex_h - 1) ty = d.tex_h - 1;
+    if (ty < d.ty_lo || ty >= d.ty_hi) return NO_TEXEL;
+    return d.sheet_px + (uint64_t)ty * d.sheet_w + tx;
+}
+
 __device__ __forceinline__ uint32_t floor_tint(uint32_t px, uint32_t t) {
     // pixel.R = uint8(float64(pixel.R) * float64(pixelSt.R) / 256); alpha unchanged
     const uint32_t rr = ((px & 255u) * (t & 255u)) >> 8;
@@ -201,11 +216,24 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS) k_compose(cons
 
     const int group = blockIdx.x, view = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wrow0 = blockIdx.y * COMPOSE_ROWS + warp * WARP_ROWS;
+    const pm3d_view &c = p.views[view];
+    // Row blocks are issued from the horizon outwards: the rows around it carry the sprites and the mixed
+    // wall/floor/sky rows, i.e. the longest CTAs, and a single frame is only a few waves of CTAs — started
+    // last they would be the tail of the launch.
+    int yblock;
+    {
+        const int n = gridDim.y, k = blockIdx.y;
+        int cb = (p.h / 2 + c.pitch_px) / COMPOSE_ROWS;
+        cb = cb < 0 ? 0 : (cb > n - 1 ? n - 1 : cb);
+        const int lo = cb, hi = n - 1 - cb;                      // blocks above / below the horizon block
+        const int m = lo < hi ? lo : hi;
+        if (k <= 2 * m) yblock = (k & 1) ? cb - ((k + 1) >> 1) : cb + (k >> 1);
+        else yblock = lo < hi ? k : n - 1 - k;
+    }
+    const int wrow0 = yblock * COMPOSE_ROWS + warp * WARP_ROWS;
     if (wrow0 >= p.h) return;
     const int wrow1 = min(wrow0 + WARP_ROWS, p.h);
     const int gx0 = group * GROUP_COLS;
-    const pm3d_view &c = p.views[view];
     const double posx = c.pos_x, posy = c.pos_y;
     const uint32_t box_tint = (uint32_t)c.max_light[0] | ((uint32_t)c.max_light[1] << 8) |
                               ((uint32_t)c.max_light[2] << 16) | 0xff000000u;
@@ -363,7 +391,58 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS) k_compose(cons
         const bool sprite_f2b = n_list > 0 && !overflow && !p.force_painter;
         double zb[4] = {0.0, 0.0, 0.0, 0.0};
         if (n_list > 0) load4(p.zbuf, fi0, vec, nvalid, zb);
-        if (sprite_f2b) {
+        if (sprite_f2b && WARP_ROWS < 8) {
+            // Latency mode (few rows per warp, single frames).  Two sprites per step: a lane's walk is a chain of dependent loads (record -> texel), so the records
+            // and texels of the next two candidates are fetched together and then resolved nearest first.
+            int wd = n_words - 1;
+            uint32_t m = s_xm[warp][wd][lane];
+            auto next_sprite = [&]() -> int {  // nearest remaining sprite of this lane that crosses row y, or -1
+                for (;;) {
+                    while (m == 0u) {
+                        if (--wd < 0) return -1;
+                        m = s_xm[warp][wd][lane];
+                    }
+                    const int bit = 31 - __clz(m);
+                    m &= ~(1u << bit);
+                    const int i = wd * 32 + bit;
+                    const Rect16 rc = wl.rect[i];
+                    if (y >= rc.y0 && y < rc.y1) return i;
+                }
+            };
+#pragma unroll 1
+            while (s_got != full) {
+                const int i0 = next_sprite();
+                if (i0 < 0) break;
+                const int i1 = next_sprite();
+                const DrawRec &d0 = draw[wl.id[i0]];
+                const DrawRec &d1 = draw[wl.id[i1 < 0 ? i0 : i1]];
+                uint64_t a0[4], a1[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const bool need = j < nvalid && !((s_got >> j) & 1u);
+                    a0[j] = need ? sprite_index(d0, x0 + j, y, zb[j]) : NO_TEXEL;
+                    a1[j] = (need && i1 >= 0) ? sprite_index(d1, x0 + j, y, zb[j]) : NO_TEXEL;
+                }
+                uint32_t t0[4], t1[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    t0[j] = a0[j] != NO_TEXEL ? __ldg(p.sheet_pixels + a0[j]) : 0u;
+                    t1[j] = a1[j] != NO_TEXEL ? __ldg(p.sheet_pixels + a1[j]) : 0u;
+                }
+                const uint32_t tint0 = d0.tint, tint1 = d1.tint;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint32_t a = t0[j] >> 24;
+                    if (a == 255u) { s_top[j] = blend_over(0u, t0[j], tint0); s_got |= 1u << j; continue; }
+                    if (a != 0u) s_trans |= 1u << j;
+                    a = t1[j] >> 24;
+                    if (a == 255u) { s_top[j] = blend_over(0u, t1[j], tint1); s_got |= 1u << j; }
+                    else if (a != 0u) s_trans |= 1u << j;
+                }
+            }
+        }
+        if (sprite_f2b && WARP_ROWS >= 8) {
+            // throughput mode (large batches of views): one sprite at a time, no speculative fetches
 #pragma unroll 1
             for (int wd = n_words - 1; wd >= 0; wd--) {
                 uint32_t m = s_xm[warp][wd][lane];

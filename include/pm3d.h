@@ -185,6 +185,19 @@ int pm3d_frame_checksums(pm3d_ctx *ctx, int n_views, uint64_t *out, uint32_t fla
 /* device pointer of the internal framebuffer ring slot written by the last pm3d_render */
 void *pm3d_last_frame_device(pm3d_ctx *ctx);
 
+/* ------------------------------------------------------------------ presentation step
+ * What GameScene.Draw does with rayScreen right after Camera.Draw (game/scene_game.go:169-185): scale it by
+ * 1/renderScale (nearest) onto the screen-sized image and copy it, or run the CRT shader over it
+ * (game/resources/shaders/crt.kage via game/render/effects/crt.go:40-53).  One fused pass, float32 like the
+ * shader; HUD, transitions and menus stay with the game. */
+enum { PM3D_PRESENT_COPY = 0, PM3D_PRESENT_CRT = 1, PM3D_PRESENT_CRT_CURVE = 2 };
+/* screen size and g.renderScale (renderWidth = floor(screenWidth * renderScale), game/config.go:239-251);
+ * call after pm3d_set_view */
+int pm3d_set_present(pm3d_ctx *ctx, int out_w, int out_h, double render_scale);
+/* d_src: n_views frames of the view size in device memory, or NULL for the frames of the last render.
+ * out: n_views * out_h * out_w * 4 bytes (host, or device with PM3D_OUT_DEVICE). */
+int pm3d_present(pm3d_ctx *ctx, const uint8_t *d_src, int n_views, int mode, uint8_t *out, uint32_t flags);
+
 /* ------------------------------------------------------------------ LOS / collision path */
 
 /* g.collisionMap = Map.GenerateWallCollisionLines(clipDistance) (game/mission.go:40):

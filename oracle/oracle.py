@@ -246,5 +246,15 @@ def valid_move_alternate(scene: Scene, segs, colliders, player: int, clip: float
     return out[0]
 
 
+def present(src: np.ndarray, out_w: int, out_h: int, render_scale: float, mode: int, threads: int = 4) -> np.ndarray:
+    """rayScreen -> overlayScreen (game/scene_game.go:169-185): 1/renderScale nearest scale + copy / CRT shader."""
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    sh, sw = src.shape[:2]
+    out = np.zeros((out_h, out_w, 4), dtype=np.uint8)
+    lib().orc_present(_ptr(src), C.c_int32(sw), C.c_int32(sh), C.c_int32(out_w), C.c_int32(out_h),
+                      C.c_double(render_scale), C.c_int32(mode), _ptr(out), C.c_int32(threads))
+    return out
+
+
 def go_int(v: float) -> int:
     return int(lib().orc_go_int(float(v)))

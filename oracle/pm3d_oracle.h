@@ -185,6 +185,15 @@ void orc_valid_move_alternate(const orc_scene *s, const double *segs, int32_t n_
                               int32_t n_colliders, int32_t player, double clip_distance, const orc_mover *m,
                               double heading, double velocity, int check_alternate, orc_move_result *out);
 
+/* ---- presentation step after the raycast (pm3d_oracle_present.c) ----------------- */
+
+/* destination -> source index of the 1/renderScale nearest scale (game/scene_game.go:170-177) [D] */
+void orc_present_axis_map(int32_t n_out, int32_t n_src, double render_scale, int32_t *map);
+/* rayScreen (sw x sh RGBA8 premultiplied) -> overlayScreen (ow x oh): scale, then copy (mode 0) or the CRT
+ * shader without / with curvature (mode 1 / 2; game/resources/shaders/crt.kage, game/scene_game.go:179-185) */
+void orc_present(const uint8_t *src, int32_t sw, int32_t sh, int32_t ow, int32_t oh, double render_scale, int32_t mode,
+                 uint8_t *out, int32_t threads);
+
 /* Go int(float64) on amd64. */
 int64_t orc_go_int(double v);
 

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "pm3d.h"
 
@@ -152,6 +153,11 @@ struct pm3d_ctx {
     int32_t *cell_items = nullptr;
     int4 *cell_rec = nullptr;        // count + first three candidate ids (or offset) per bin cell
     int bin_x0 = 0, bin_y0 = 0, bin_w = 0, bin_h = 0;
+    // presentation step (present_kernel.cu)
+    int32_t *present_map = nullptr;  // [present_w + present_h] output -> source column / row, -1 = outside
+    int present_w = 0, present_h = 0, present_src_w = 0, present_src_h = 0;
+    uint8_t *present_buf = nullptr;
+    size_t present_bytes = 0;
     pm3d_collider *colliders = nullptr;  // g.player.Unit + collidable sprites (pm3d_upload_colliders)
     int n_colliders = 0, player_index = -1;
     void *io_a = nullptr, *io_b = nullptr, *io_c = nullptr;  // batch staging on device

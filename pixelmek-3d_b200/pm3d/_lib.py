@@ -18,6 +18,7 @@ OPT_KEEP_COLUMNS = 1
 OPT_FORCE_PAINTER = 2
 OPT_PIPELINE = 3
 OPT_OVERLAP = 4
+PRESENT_COPY, PRESENT_CRT, PRESENT_CRT_CURVE = 0, 1, 2
 
 
 class Pm3dError(RuntimeError):
@@ -115,6 +116,8 @@ SYMBOLS = {
     "pm3d_upload_segments": (C.c_int, [_P, _P, C.c_int]),
     "pm3d_los_batch": (C.c_int, [_P, _P, C.c_int64, _P, C.c_uint32]),
     "pm3d_move_batch": (C.c_int, [_P, _P, C.c_int64, C.c_double, _P, _P, C.c_uint32]),
+    "pm3d_set_present": (C.c_int, [_P, C.c_int, C.c_int, C.c_double]),
+    "pm3d_present": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_uint32]),
     "pm3d_upload_colliders": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "pm3d_valid_move_batch": (C.c_int, [_P, _P, C.c_int64, C.c_double, _P, C.c_uint32]),
     "pm3d_generate_wall_collision_lines": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double, _P, C.c_int]),

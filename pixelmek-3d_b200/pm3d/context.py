@@ -179,6 +179,23 @@ class Context:
         self._check(self.lib.pm3d_frame_checksums(self.h, n_views, ptr(out), 0), "pm3d_frame_checksums")
         return out
 
+    # ------------------------------------------------------------------ presentation step
+    def set_present(self, out_w: int, out_h: int, render_scale: float):
+        """Screen size + g.renderScale (game/config.go:239-251); after set_view."""
+        self._check(self.lib.pm3d_set_present(self.h, int(out_w), int(out_h), float(render_scale)), "pm3d_set_present")
+        self.present_w, self.present_h = int(out_w), int(out_h)
+
+    def present(self, mode: int, n_views: int = 1, d_src: int | None = None, d_out: int | None = None):
+        """rayScreen -> overlayScreen (game/scene_game.go:169-185) of the last render (or of d_src)."""
+        if d_out is not None:
+            self._check(self.lib.pm3d_present(self.h, C.c_void_p(d_src) if d_src else None, n_views, int(mode),
+                                              C.c_void_p(d_out), _lib.PM3D_OUT_DEVICE | _lib.PM3D_NO_SYNC), "pm3d_present")
+            return None
+        out = np.empty((n_views, self.present_h, self.present_w, 4), dtype=np.uint8)
+        self._check(self.lib.pm3d_present(self.h, C.c_void_p(d_src) if d_src else None, n_views, int(mode), ptr(out), 0),
+                    "pm3d_present")
+        return out
+
     # ------------------------------------------------------------------ LOS / collision path
     def upload_segments(self, segs: np.ndarray):
         segs = np.ascontiguousarray(segs, dtype=np.float64).reshape(-1, 4)

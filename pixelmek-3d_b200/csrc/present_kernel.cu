@@ -22,40 +22,77 @@ struct PresentParams {
 
 __device__ __forceinline__ float clampf01(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
 
-// imageSrc0At(uv * size + origin): channel c (0..2) of the scaled image at uv, in [0, 1]; 0 outside
-__device__ __forceinline__ float tap(const PresentParams &p, const uint32_t *__restrict__ frame, float u, float v, int c) {
-    const float px = u * (float)p.ow, py = v * (float)p.oh;
-    if (!(px >= 0.0f && px < (float)p.ow && py >= 0.0f && py < (float)p.oh)) return 0.0f;
-    const int sx = __ldg(p.xmap + (int)floorf(px)), sy = __ldg(p.ymap + (int)floorf(py));
-    if (sx < 0 || sy < 0) return 0.0f;
+// imageSrc0At(uv * size + origin) over the scaled image, split by axis: the source row / column an image
+// coordinate falls on, or -1 outside the image or outside the scaled source
+__device__ __forceinline__ int tap_row(const PresentParams &p, float v) {
+    const float py = v * (float)p.oh;
+    if (!(py >= 0.0f && py < (float)p.oh)) return -1;
+    return __ldg(p.ymap + (int)floorf(py));
+}
+__device__ __forceinline__ int tap_col(const PresentParams &p, float u) {
+    const float px = u * (float)p.ow;
+    if (!(px >= 0.0f && px < (float)p.ow)) return -1;
+    return __ldg(p.xmap + (int)floorf(px));
+}
+// channel c (0..2) of the texel as float(byte) / 255 (s_unorm holds exactly that quotient for every byte)
+__device__ __forceinline__ float tap(const PresentParams &p, const uint32_t *__restrict__ frame, const float *s_unorm,
+                                     int sx, int sy, int c) {
+    if ((sx | sy) < 0) return 0.0f;
     const uint32_t t = __ldg(frame + (size_t)sy * p.sw + sx);
-    return (float)((t >> (8 * c)) & 255u) / 255.0f;
+    return s_unorm[(t >> (8 * c)) & 255u];
 }
 
-__device__ __forceinline__ uint32_t crt_pixel(const PresentParams &p, const uint32_t *__restrict__ frame, int X, int Y) {
+// x^y for x >= 0 through exp2f(y * log2f(x)) (CUDA's full-accuracy exp2f / log2f, ~2 ulp each): the shader's pow
+// is the GPU's own approximation anyway and the result is quantised to 8 bits (tests: <= 1 LSB vs the C library)
+__device__ __forceinline__ float pow_pos(float x, float y) { return x > 0.0f ? exp2f(y * log2f(x)) : 0.0f; }
+
+// scanline factor 0.4 + 0.7 * pow(clamp(0.35 + 0.35 * sin(uv.y * size.y * 1.5)), 1.7) of crt.kage:60-62
+__device__ __forceinline__ float scan_factor(const PresentParams &p, float uy) {
+    const float scans = clampf01(0.35f + 0.35f * sinf(uy * (float)p.oh * 1.5f));
+    return 0.4f + 0.7f * pow_pos(scans, 1.7f);
+}
+
+// `rows`: the six source rows of the taps and the scanline factor when they depend on the row only (no curvature)
+struct RowTaps { int r[6]; float scan; };
+__device__ __forceinline__ void row_taps(const PresentParams &p, float uy, RowTaps &t) {
+    t.r[0] = tap_row(p, uy + 0.0002f);
+    t.r[1] = tap_row(p, uy - 0.0005f);
+    t.r[2] = tap_row(p, uy + 0.0000f);
+    t.r[3] = tap_row(p, -0.02025f + (uy + 0.0002f));
+    t.r[4] = tap_row(p, -0.015f + (uy - 0.0005f));
+    t.r[5] = tap_row(p, -0.0135f + (uy + 0.0000f));
+    t.scan = scan_factor(p, uy);
+}
+
+__device__ __forceinline__ uint32_t crt_pixel(const PresentParams &p, const uint32_t *__restrict__ frame, const float *s_unorm,
+                                              int X, int Y, const RowTaps *rows) {
     const float fx = (float)X + 0.5f, fy = (float)Y + 0.5f;
     float ux = fx / (float)p.ow, uy = fy / (float)p.oh;      // crt.kage:30-33
-    if (p.mode == 2) {                                       // crt.kage:18-27 curve()
+    RowTaps own;
+    if (p.mode == 2) {                                       // crt.kage:18-27 curve(); pow(v, 2) = v * v
         ux = (ux - 0.5f) * 2.0f; uy = (uy - 0.5f) * 2.0f;
         ux *= 1.1f; uy *= 1.1f;
-        ux *= 1.0f + powf(fabsf(uy) / 5.0f, 2.0f);
-        uy *= 1.0f + powf(fabsf(ux) / 4.0f, 2.0f);
+        const float ay = fabsf(uy) / 5.0f;
+        ux *= 1.0f + ay * ay;
+        const float ax = fabsf(ux) / 4.0f;
+        uy *= 1.0f + ax * ax;
         ux = ux / 2.0f + 0.5f; uy = uy / 2.0f + 0.5f;
         ux = ux * 0.92f + 0.04f; uy = uy * 0.92f + 0.04f;
+        if (ux < 0.0f || ux > 1.0f || uy < 0.0f || uy > 1.0f) return 0xff000000u;          // crt.kage:70-72
+        row_taps(p, uy, own);
+        rows = &own;
     }
     float col[3];                                            // crt.kage:41-48
-    col[0] = tap(p, frame, ux + 0.0002f, uy + 0.0002f, 0) + 0.05f;
-    col[1] = tap(p, frame, ux + 0.0000f, uy - 0.0005f, 1) + 0.05f;
-    col[2] = tap(p, frame, ux - 0.0005f, uy + 0.0000f, 2) + 0.05f;
-    col[0] += 0.08f * tap(p, frame, 0.01875f + (ux + 0.0002f), -0.02025f + (uy + 0.0002f), 0);
-    col[1] += 0.05f * tap(p, frame, -0.0165f + (ux + 0.0000f), -0.015f + (uy - 0.0005f), 1);
-    col[2] += 0.08f * tap(p, frame, -0.015f + (ux - 0.0005f), -0.0135f + (uy + 0.0000f), 2);
-    const bool outside = ux < 0.0f || ux > 1.0f || uy < 0.0f || uy > 1.0f;                 // crt.kage:70-72
+    col[0] = tap(p, frame, s_unorm, tap_col(p, ux + 0.0002f), rows->r[0], 0) + 0.05f;
+    col[1] = tap(p, frame, s_unorm, tap_col(p, ux + 0.0000f), rows->r[1], 1) + 0.05f;
+    col[2] = tap(p, frame, s_unorm, tap_col(p, ux - 0.0005f), rows->r[2], 2) + 0.05f;
+    col[0] += 0.08f * tap(p, frame, s_unorm, tap_col(p, 0.01875f + (ux + 0.0002f)), rows->r[3], 0);
+    col[1] += 0.05f * tap(p, frame, s_unorm, tap_col(p, -0.0165f + (ux + 0.0000f)), rows->r[4], 1);
+    col[2] += 0.08f * tap(p, frame, s_unorm, tap_col(p, -0.015f + (ux - 0.0005f)), rows->r[5], 2);
     const float vig = 16.0f * ux * uy * (1.0f - ux) * (1.0f - uy);                         // :54
-    const float vp = outside ? 0.0f : powf(vig, 0.3f);
-    const float scans = clampf01(0.35f + 0.35f * sinf(uy * (float)p.oh * 1.5f));           // :60
-    const float s = powf(scans, 1.7f);
-    const float mask = 1.0f - 0.65f * clampf01((fmodf(fx, 2.0f) - 1.0f) * 2.0f);           // :74
+    const float vp = pow_pos(vig, 0.3f);
+    // :74  1 - 0.65 * clamp((mod(src.x, 2) - 1) * 2, 0, 1): src.x = X + 0.5, so the clamp is 0 on even, 1 on odd columns
+    const float mask = (X & 1) ? 1.0f - 0.65f : 1.0f;
     uint32_t o = 0xff000000u;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -63,43 +100,47 @@ __device__ __forceinline__ uint32_t crt_pixel(const PresentParams &p, const uint
         v *= vp;
         v *= (c == 1 ? 1.05f : 0.95f);
         v *= 2.8f;
-        v *= 0.4f + 0.7f * s;
-        if (outside) v *= 0.0f;
+        v *= rows->scan;                                                                   // :60-62
         v *= mask;
         o |= (uint32_t)(int)floorf(clampf01(v) * 255.0f + 0.5f) << (8 * c);
     }
     return o;
 }
 
+// grid: x = 256-thread chunks of a row's pixel quads, y = output row, z = view
 __global__ void __launch_bounds__(256) k_present(const PresentParams p) {
-    const int qpr = (p.ow + 3) >> 2;  // quads per row
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < p.n_quads; q += (long long)gridDim.x * blockDim.x) {
-        const int qx = (int)(q % qpr);
-        const long long row = q / qpr;
-        const int Y = (int)(row % p.oh), view = (int)(row / p.oh);
-        const uint32_t *frame = reinterpret_cast<const uint32_t *>(p.src) + (size_t)view * p.sh * p.sw;
-        uint32_t *orow = reinterpret_cast<uint32_t *>(p.out) + ((size_t)view * p.oh + Y) * p.ow;
-        const int X0 = qx * 4;
-        uint32_t px[4];
-        if (p.mode == 0) {
-            const int sy = __ldg(p.ymap + Y);
+    __shared__ float s_unorm[256];
+    if (p.mode != 0) {
+        s_unorm[threadIdx.x] = (float)threadIdx.x / 255.0f;
+        __syncthreads();
+    }
+    const int qx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int X0 = qx * 4;
+    if (X0 >= p.ow) return;
+    const int Y = blockIdx.y, view = blockIdx.z;
+    const uint32_t *frame = reinterpret_cast<const uint32_t *>(p.src) + (size_t)view * p.sh * p.sw;
+    uint32_t *orow = reinterpret_cast<uint32_t *>(p.out) + ((size_t)view * p.oh + Y) * p.ow;
+    uint32_t px[4];
+    if (p.mode == 0) {
+        const int sy = __ldg(p.ymap + Y);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int X = X0 + j;
-                const int sx = X < p.ow ? __ldg(p.xmap + X) : -1;
-                px[j] = (sx >= 0 && sy >= 0) ? __ldg(frame + (size_t)sy * p.sw + sx) : 0u;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) px[j] = X0 + j < p.ow ? crt_pixel(p, frame, X0 + j, Y) : 0u;
+        for (int j = 0; j < 4; j++) {
+            const int X = X0 + j;
+            const int sx = X < p.ow ? __ldg(p.xmap + X) : -1;
+            px[j] = (sx >= 0 && sy >= 0) ? __ldg(frame + (size_t)sy * p.sw + sx) : 0u;
         }
-        if (X0 + 3 < p.ow && (p.ow & 3) == 0) {
-            *reinterpret_cast<uint4 *>(orow + X0) = make_uint4(px[0], px[1], px[2], px[3]);
-        } else {
+    } else {
+        RowTaps rows;
+        if (p.mode == 1) row_taps(p, ((float)Y + 0.5f) / (float)p.oh, rows);
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (X0 + j < p.ow) orow[X0 + j] = px[j];
-        }
+        for (int j = 0; j < 4; j++) px[j] = X0 + j < p.ow ? crt_pixel(p, frame, s_unorm, X0 + j, Y, &rows) : 0u;
+    }
+    if (X0 + 3 < p.ow && (p.ow & 3) == 0) {
+        *reinterpret_cast<uint4 *>(orow + X0) = make_uint4(px[0], px[1], px[2], px[3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (X0 + j < p.ow) orow[X0 + j] = px[j];
     }
 }
 
@@ -156,10 +197,9 @@ extern "C" int pm3d_present(pm3d_ctx *ctx, const uint8_t *d_src, int n_views, in
     p.xmap = ctx->present_map; p.ymap = ctx->present_map + ctx->present_w;
     p.sw = ctx->w; p.sh = ctx->h; p.ow = ctx->present_w; p.oh = ctx->present_h; p.mode = mode; p.n_views = n_views;
     p.n_quads = (long long)n_views * p.oh * ((p.ow + 3) / 4);
-    long long blocks = (p.n_quads + 255) / 256;
-    const long long cap = (long long)ctx->sm_count * 8;  // persistent-style: at most 8 CTAs of 256 per SM
-    if (blocks > cap) blocks = cap;
-    k_present<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p);
+    if (p.oh > 65535 || n_views > 65535) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "present: too many rows / views for one launch");
+    const dim3 grid((unsigned)(((p.ow + 3) / 4 + 255) / 256), (unsigned)p.oh, (unsigned)n_views);
+    k_present<<<grid, 256, 0, ctx->stream>>>(p);
     ctx->launches++;
     PM3D_CUDA(ctx, cudaGetLastError());
     if (!(flags & PM3D_OUT_DEVICE)) PM3D_CUDA(ctx, cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, ctx->stream));

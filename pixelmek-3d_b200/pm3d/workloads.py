@@ -375,3 +375,39 @@ def los_rays(level0: np.ndarray, n: int, seed: int) -> np.ndarray:
     rays[:, 2] = free[b, 0] + 0.05 + 0.9 * j[:, 2]
     rays[:, 3] = free[b, 1] + 0.05 + 0.9 * j[:, 3]
     return rays
+
+
+def move_workload(level0: np.ndarray, n_movers: int, n_colliders: int, seed: int, max_len: float = 0.5):
+    """A tick of the projectile / unit fan-out (game/combat.go:206-239): colliders scattered over free cells,
+    movers (a third of them next to a collider) each asking for one short move.  Returns (colliders, movers)."""
+    from ._lib import COLLIDER_DTYPE, MOVER_DTYPE
+
+    rng = SplitMix64(seed)
+    free = np.argwhere(level0 == 0)
+    c = np.zeros(n_colliders, dtype=COLLIDER_DTYPE)
+    cells = free[(rng.uniform(n_colliders) * len(free)).astype(np.int64)]
+    c["x"] = cells[:, 0] + rng.uniform(n_colliders)
+    c["y"] = cells[:, 1] + rng.uniform(n_colliders)
+    c["radius"] = 0.1 + 0.4 * rng.uniform(n_colliders)
+    c["height"] = 0.3 + rng.uniform(n_colliders)
+    m = np.zeros(n_movers, dtype=MOVER_DTYPE)
+    cells = free[(rng.uniform(n_movers) * len(free)).astype(np.int64)]
+    m["pos_x"] = cells[:, 0] + rng.uniform(n_movers)
+    m["pos_y"] = cells[:, 1] + rng.uniform(n_movers)
+    if n_colliders:
+        near = rng.uniform(n_movers) < 0.33
+        pick = (rng.uniform(n_movers) * n_colliders).astype(np.int64)
+        m["pos_x"] = np.where(near, c["x"][pick] + (rng.uniform(n_movers) - 0.5) * 2.0, m["pos_x"])
+        m["pos_y"] = np.where(near, c["y"][pick] + (rng.uniform(n_movers) - 0.5) * 2.0, m["pos_y"])
+    m["pos_z"] = 0.3 * rng.uniform(n_movers)
+    ang = rng.uniform(n_movers) * (2.0 * math.pi)
+    length = rng.uniform(n_movers) * max_len
+    m["move_x"] = m["pos_x"] + np.cos(ang) * length
+    m["move_y"] = m["pos_y"] + np.sin(ang) * length
+    m["move_z"] = m["pos_z"]
+    m["radius"] = 0.01
+    m["height"] = 0.01
+    m["self"] = -1
+    m["parent"] = -1
+    m["anchor"] = 1
+    return c, m

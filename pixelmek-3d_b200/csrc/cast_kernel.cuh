@@ -21,6 +21,8 @@
 struct CastParams {
     const pm3d_view *views;
     const uint16_t *grid;
+    const double *sparse_cells;   // [stored_levels][PM3D_SPARSE_MAX][2]
+    const int32_t *sparse_count;  // [stored_levels], -1 = dense
     const uint8_t *dist;  // per stored level: Chebyshev distance to the nearest wall cell or map edge (0 = wall)
     const int16_t *wall_lut;
     int2 *col_span;
@@ -60,6 +62,39 @@ __device__ __forceinline__ void cast_ray(const CastParams &p, const int view, co
     else             { stepY = 1;  sideDistY = ((double)mapY + 1.0 - rayPosY) * deltaDistY; }
 
     int hit = 0, side = -1;
+
+    // ---- sparse upper levels.  A level above the ground with a handful of wall cells is mostly crossed without a
+    // hit: the ray leaves the grid, draws nothing and (not being level 0) feeds neither the z-buffer nor the floor
+    // cast.  The walk visits only cells the ray passes through (its rounding can shift a border crossing by
+    // ~1e-10 cells, never by a cell), so a ray whose line stays more than 2 cells away from the centre of every
+    // wall cell of the level cannot hit one; it skips the walk and stores the "nothing drawn" record.  NaN or
+    // infinite operands fail the comparisons and take the walk.  (Not with PM3D_OPT_KEEP_COLUMNS: the
+    // per-column debug record wants the exit cell.)
+    if (!DEBUG && level > 0) {
+        const int ns = __ldg(p.sparse_count + sl);
+        if (ns >= 0) {
+            const double *cells = p.sparse_cells + (size_t)sl * PM3D_SPARSE_MAX * 2;
+            const double d2 = rayDirX * rayDirX + rayDirY * rayDirY;
+            bool clear = d2 > 0.0 && d2 < 1e300 && fabs(rayPosX) < 1e9 && fabs(rayPosY) < 1e9;
+            for (int i = 0; i < ns && clear; i++) {
+                const double wx = __ldg(cells + 2 * i) - rayPosX, wy = __ldg(cells + 2 * i + 1) - rayPosY;
+                const double dot = wx * rayDirX + wy * rayDirY;          // |w| |d| cos
+                const double cross = wx * rayDirY - wy * rayDirX;        // |w| |d| sin: distance to the line = |cross| / |d|
+                const bool far_from_line = cross * cross > 4.0 * d2;     // more than 2 cells off the line
+                const bool behind = dot < 0.0 && wx * wx + wy * wy > 4.0;  // behind the camera and not next to it
+                clear = far_from_line || behind;
+            }
+            if (clear) {
+                const size_t ci = ((size_t)view * p.num_levels + level) * p.w + x;
+                if (live) {
+                    p.col_span[ci] = make_int2(0, 0);
+                    p.col_tt[ci] = make_uint2(0u, 0u);
+                    p.col_ps[ci] = make_ulonglong2(0ull, 0ull);
+                }
+                hit = 3;
+            }
+        }
+    }
     // The start cell may be far outside the grid (Go ints are 64-bit); once the walk is
     // inside int32 range all cell arithmetic is 32-bit.
     if (mapX < -2147480000ll || mapX > 2147480000ll || mapY < -2147480000ll || mapY > 2147480000ll) {
@@ -69,6 +104,8 @@ __device__ __forceinline__ void cast_ray(const CastParams &p, const int view, co
         mapX = mapX < 0 ? 0 : (mapX > p.map_w - 1 ? p.map_w - 1 : mapX);
         mapY = mapY < 0 ? 0 : (mapY > p.map_h - 1 ? p.map_h - 1 : mapY);
     }
+    int agg_ya = 0x7fffffff, agg_fs_min = 0x7fffffff, agg_fs_max = 0;
+    if (hit != 3) {  // (skipped rays hold the defaults: nothing drawn)
     int mx = (int)mapX, my = (int)mapY;
     const uint8_t *__restrict__ dist = p.dist + (size_t)sl * p.map_w * p.map_h;
     // free-run length at the start cell; the reference never tests the start cell itself, so a
@@ -144,8 +181,7 @@ __device__ __forceinline__ void cast_ray(const CastParams &p, const int view, co
         p.col_tt[ci] = make_uint2(tile_texx, tint);
         p.col_ps[ci] = make_ulonglong2(pos0, step2);
     }
-    int agg_ya = (live && ya < yb) ? ya : 0x7fffffff;
-    int agg_fs_min = 0x7fffffff, agg_fs_max = 0;
+    agg_ya = (live && ya < yb) ? ya : 0x7fffffff;
 
     if (DEBUG && live) {
         pm3d_column d;
@@ -187,6 +223,7 @@ __device__ __forceinline__ void cast_ray(const CastParams &p, const int view, co
             p.flo_dy[fi] = Y1 - PY;
             agg_fs_min = fs; agg_fs_max = fs;
         }
+    }
     }
     // ---- aggregate over this warp's 32 columns (half a group)
     for (int o = 16; o > 0; o >>= 1) {

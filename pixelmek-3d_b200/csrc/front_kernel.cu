@@ -24,6 +24,7 @@ int pm3d_launch_front(pm3d_ctx *ctx, int n_views, cudaStream_t stream) {
     p.views = ctx->cur_views;
     p.grid = ctx->grid;
     p.dist = ctx->dist;
+    p.sparse_cells = ctx->sparse_cells; p.sparse_count = ctx->sparse_count;
     p.wall_lut = ctx->wall_lut;
     p.col_span = ctx->col_span; p.col_tt = ctx->col_tt; p.col_ps = ctx->col_ps;
     p.flo_xw = ctx->flo_xw; p.flo_yw = ctx->flo_yw; p.flo_dw = ctx->flo_dw; p.flo_rc = ctx->flo_rc; p.flo_dx = ctx->flo_dx; p.flo_dy = ctx->flo_dy; p.flo_fs = ctx->flo_fs;

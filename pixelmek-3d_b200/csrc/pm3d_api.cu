@@ -82,7 +82,7 @@ void pm3d_destroy(pm3d_ctx *ctx) {
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     void *ptrs[] = {ctx->grid, ctx->dist, ctx->wall_lut, ctx->atlas, ctx->floor_tiles, ctx->sheet_pixels, ctx->sheet_info,
                     ctx->views, ctx->sprites, ctx->sprite_offset, ctx->frame, ctx->checksums, ctx->segs, ctx->seg_irect,
-                    ctx->cell_start, ctx->cell_items, ctx->cell_rec, ctx->colliders, ctx->present_map, ctx->present_buf, ctx->io_a, ctx->io_b, ctx->io_c, ctx->flush_buf};
+                    ctx->cell_start, ctx->cell_items, ctx->cell_rec, ctx->colliders, ctx->present_map, ctx->present_buf, ctx->sparse_cells, ctx->sparse_count, ctx->io_a, ctx->io_b, ctx->io_c, ctx->flush_buf};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &fs : ctx->sets) {
@@ -168,6 +168,30 @@ int pm3d_upload_grid(pm3d_ctx *ctx, const uint16_t *grid, int stored_levels, int
         rc = dev_realloc(ctx, &ctx->dist, count);
         if (rc) return rc;
         PM3D_CUDA(ctx, cudaMemcpy(ctx->dist, dist.data(), count, cudaMemcpyHostToDevice));
+    }
+    // sparse levels (cast_kernel.cuh): levels with at most PM3D_SPARSE_MAX wall cells list their cell centres, so
+    // an upper-level ray that provably passes none of them skips the walk across the empty level
+    {
+        std::vector<double> cells((size_t)stored_levels * PM3D_SPARSE_MAX * 2, 0.0);
+        std::vector<int32_t> cnt(stored_levels, -1);
+        for (int l = 0; l < stored_levels; l++) {
+            const uint16_t *g = grid + (size_t)l * map_w * map_h;
+            int n = 0;
+            for (int x = 0; x < map_w && n <= PM3D_SPARSE_MAX; x++)
+                for (int y = 0; y < map_h && n <= PM3D_SPARSE_MAX; y++)
+                    if (g[(size_t)x * map_h + y] > 0) {
+                        if (n < PM3D_SPARSE_MAX) {
+                            cells[((size_t)l * PM3D_SPARSE_MAX + n) * 2] = x + 0.5;
+                            cells[((size_t)l * PM3D_SPARSE_MAX + n) * 2 + 1] = y + 0.5;
+                        }
+                        n++;
+                    }
+            cnt[l] = n <= PM3D_SPARSE_MAX ? n : -1;
+        }
+        if ((rc = dev_realloc(ctx, &ctx->sparse_cells, cells.size()))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->sparse_count, (size_t)stored_levels))) return rc;
+        PM3D_CUDA(ctx, cudaMemcpy(ctx->sparse_cells, cells.data(), cells.size() * 8, cudaMemcpyHostToDevice));
+        PM3D_CUDA(ctx, cudaMemcpy(ctx->sparse_count, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice));
     }
     ctx->stored_levels = stored_levels; ctx->map_w = map_w; ctx->map_h = map_h;
     const bool levels_changed = ctx->num_levels != num_raycast_levels;

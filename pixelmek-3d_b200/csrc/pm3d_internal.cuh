@@ -57,6 +57,8 @@ struct SheetInfo {
     int32_t w, h;
 };
 
+#define PM3D_SPARSE_MAX 32
+
 // ------------------------------------------------------------------ ctx
 
 struct pm3d_ctx {
@@ -70,6 +72,8 @@ struct pm3d_ctx {
     // mission data
     uint16_t *grid = nullptr;
     uint8_t *dist = nullptr;  // [stored_levels][map_w][map_h] free-run distance field of the grid
+    double *sparse_cells = nullptr;   // [stored_levels][PM3D_SPARSE_MAX][2] wall-cell centres of sparse levels
+    int32_t *sparse_count = nullptr;  // [stored_levels] number of wall cells, -1 = more than PM3D_SPARSE_MAX
     int stored_levels = 0, map_w = 0, map_h = 0, num_levels = 0;
     int16_t *wall_lut = nullptr;  // [32768][2]
     uint8_t *atlas = nullptr;

@@ -405,3 +405,35 @@ def test_overlapped_frames_equal_serial_frames(gpu_ctx):
     for i in range(n):
         assert np.array_equal(h0[i]["rgba"], h1[i]["rgba"]) and np.array_equal(h0[i]["rgba"][0], f0[i]), f"frame {i}"
         assert np.array_equal(h0[i]["rects"], h1[i]["rects"]) and h0[i]["conv"].tobytes() == h1[i]["conv"].tobytes()
+
+
+def test_sparse_upper_levels_skip_the_walk_without_changing_a_pixel(gpu_ctx):
+    """proving_grounds has 12 and 3 wall cells on levels 1 and 2: rays of those levels that provably pass none of
+    them skip the DDA walk (cast_kernel.cuh; only without PM3D_OPT_KEEP_COLUMNS).  Frames from poses next to,
+    facing, grazing and facing away from those cells must equal the oracle's, which walks every ray."""
+    scene, g = W.proving_grounds_scene()
+    poses = [
+        (14.5, 27.5, 0.5, 2.98, 0.0),     # looking at the level-1/2 blocks at x = 8..10
+        (9.5, 27.5, 0.5, 1.5708, 0.05),   # between two of them, looking along the row
+        (9.5, 31.5, 0.6, -1.5708, -0.1),  # right behind one
+        (12.0, 30.5, 0.5, 3.14159, 0.2),  # facing one head on, close
+        (12.0, 30.5, 0.5, 0.0, 0.0),      # same spot facing away
+        (7.2, 24.2, 0.5, 0.7854, 0.0),    # grazing a block's corner
+        (480.5, 488.5, 0.5, 0.15, 0.0),   # the far cluster at (490..492, 490)
+        (250.5, 250.5, 0.5, 0.9, 0.0),    # mid map: every upper-level ray skips
+        (31.5, 3.5, 0.5, 0.7854, 0.0),
+    ]
+    views = W.make_views(scene, 480, 270, poses)
+    ctx = gpu_ctx
+    ctx.upload_scene(scene)
+    ctx.set_option(pm3d._lib.OPT_KEEP_COLUMNS, 0)
+    ctx.set_view(480, 270, len(poses), 1)
+    off = np.zeros(len(poses) + 1, dtype=np.int32)
+    got = ctx.render(views, np.zeros(0, pm3d._lib.SPRITE_DTYPE), off)
+    osc = O.Scene(scene)
+    n_upper_walls = 0
+    for i, v in enumerate(views):
+        ref = O.render(osc, orc_camera(v, 480, 270), np.zeros(0, O.SPRITE_DTYPE), threads=4)
+        assert_frame_equal(got["rgba"][i], ref["rgba"], f"pose {i}")
+        n_upper_walls += int((ref["columns"]["tile"][1:] >= 0).sum())
+    assert n_upper_walls > 200     # the upper-level walls are really on screen in some of these frames

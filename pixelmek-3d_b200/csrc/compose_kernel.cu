@@ -131,7 +131,7 @@ __device__ __forceinline__ uint32_t floor_texel(const ComposeParams &p, double f
     const int ft = __ldg(p.floor_tiles + (tx >> p.tex_shift) * p.map_h + (ty >> p.tex_shift));
     if (ft < 0) return 0u;
     const int m = p.tex_size - 1;
-    const uint32_t px = __ldg(p.atlas + ((((size_t)ft << p.tex_shift) + (size_t)(ty & m)) << p.tex_shift) + (size_t)(tx & m));
+    const uint32_t px = __ldg(p.atlas + (((((uint32_t)ft << p.tex_shift) | (uint32_t)(ty & m)) << p.tex_shift) | (uint32_t)(tx & m)));
     if ((px >> 24) == 0) return 0u;
     return floor_tint(px, r.tint);
 }
@@ -140,14 +140,14 @@ __device__ __forceinline__ uint32_t wall_texel(const ComposeParams &p, uint32_t 
     uint32_t ty = (uint32_t)((ps.x + (uint64_t)(int64_t)y * ps.y) >> 33);
     if (ty > (uint32_t)p.tex_size - 1) ty = p.tex_size - 1;
     const uint32_t tile = tile_texx >> 16, tx = tile_texx & 0xffffu;
-    return __ldg(p.atlas + ((((size_t)tile << p.tex_shift) + ty) << p.tex_shift) + tx);
+    return __ldg(p.atlas + ((((tile << p.tex_shift) | ty) << p.tex_shift) | tx));  // 32-bit texel index (pm3d_upload_atlas checks the size)
 }
 
 __device__ __forceinline__ uint32_t box_texel(const ComposeParams &p, uint32_t info, uint32_t u) {
     const int tile = (info & 0x40000000u) ? p.sky_tile : p.floorbox_tile;
     if (tile < 0) return 0u;
     const uint32_t v = info & 0xffffu;
-    return __ldg(p.atlas + ((((size_t)tile << p.tex_shift) + v) << p.tex_shift) + u);
+    return __ldg(p.atlas + (((((uint32_t)tile << p.tex_shift) | v) << p.tex_shift) | u));
 }
 
 // tinted opaque texel over anything: (c*tint + 127)/255, alpha 255
@@ -375,6 +375,9 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS) k_compose(cons
         bu[j] = u > (uint32_t)tmask ? (uint32_t)tmask : u;
     }
 
+    double zb[4] = {0.0, 0.0, 0.0, 0.0};  // z-buffer of this lane's columns (rows share it)
+    if (n_list > 0) load4(p.zbuf, fi0, vec, nvalid, zb);
+
 #pragma unroll 1
     for (int it = 0; it < WARP_ROWS / 2; it++) {
         const int y = wrow0 + it * 2 + ly;
@@ -389,8 +392,6 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS) k_compose(cons
         unsigned s_trans = 0u;  // pixels that met a translucent sprite texel in front of it
         uint32_t s_top[4] = {0u, 0u, 0u, 0u};
         const bool sprite_f2b = n_list > 0 && !overflow && !p.force_painter;
-        double zb[4] = {0.0, 0.0, 0.0, 0.0};
-        if (n_list > 0) load4(p.zbuf, fi0, vec, nvalid, zb);
         if (sprite_f2b && WARP_ROWS < 8) {
             // Latency mode (few rows per warp, single frames).  Two sprites per step: a lane's walk is a chain of dependent loads (record -> texel), so the records
             // and texels of the next two candidates are fetched together and then resolved nearest first.
@@ -511,7 +512,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS) k_compose(cons
                         uint32_t t[4];
 #pragma unroll
                         for (int j = 0; j < 4; j++)
-                            t[j] = __ldg(p.atlas + ((((size_t)ft[j] << p.tex_shift) + (size_t)(ty[j] & tmask)) << p.tex_shift) + (size_t)(tx[j] & tmask));
+                            t[j] = __ldg(p.atlas + (((((uint32_t)ft[j] << p.tex_shift) | (ty[j] & (uint32_t)tmask)) << p.tex_shift) | (tx[j] & (uint32_t)tmask)));
                         if ((t[0] & t[1] & t[2] & t[3]) >= 0xff000000u) {
 #pragma unroll
                             for (int j = 0; j < 4; j++) px[j] = floor_tint(t[j], r.tint);
@@ -685,13 +686,14 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     // rows per warp: enough warps to fill the chip a few times over, otherwise as long as possible
     const long long warps8 = (long long)ctx->n_groups * ((ctx->h + 7) / 8) * n_views;
     const long long resident = (long long)ctx->sm_count * 24;
-    int rows = warps8 >= 8 * resident ? 8 : (warps8 >= 2 * resident ? 4 : 2);
-    int minb = rows == 8 ? 8 : 6;
+    int rows = warps8 >= 64 * resident ? 16 : (warps8 >= 8 * resident ? 8 : (warps8 >= 2 * resident ? 4 : 2));
+    int minb = rows >= 8 ? 8 : 6;
     if (const char *e = getenv("PM3D_COMPOSE_ROWS")) rows = atoi(e);      // tuning overrides (tools/)
     if (const char *e = getenv("PM3D_COMPOSE_MINB")) minb = atoi(e);
     dim3 block(COMPOSE_WARPS * 32), grid(ctx->n_groups, (ctx->h + COMPOSE_WARPS * rows - 1) / (COMPOSE_WARPS * rows), n_views);
     pm3d_kt_mark(ctx, 2, 0, ctx->stream);
-    if (rows == 8 && minb == 8) k_compose<8, 8><<<grid, block, 0, ctx->stream>>>(p);
+    if (rows == 16) k_compose<16, 8><<<grid, block, 0, ctx->stream>>>(p);
+    else if (rows == 8 && minb == 8) k_compose<8, 8><<<grid, block, 0, ctx->stream>>>(p);
     else if (rows == 8) k_compose<8, 6><<<grid, block, 0, ctx->stream>>>(p);
     else if (rows == 4 && minb == 8) k_compose<4, 8><<<grid, block, 0, ctx->stream>>>(p);
     else if (rows == 4) k_compose<4, 6><<<grid, block, 0, ctx->stream>>>(p);

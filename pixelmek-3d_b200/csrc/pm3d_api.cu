@@ -225,6 +225,8 @@ int pm3d_upload_atlas(pm3d_ctx *ctx, const uint8_t *rgba, int n_tiles, int tex_s
     if (!ctx) return PM3D_ERR_ARG;
     if (!rgba || n_tiles < 1 || n_tiles > 32767 || tex_size < 1 || tex_size > 4096 || (tex_size & (tex_size - 1)))
         return pm3d_fail(ctx, PM3D_ERR_ARG, "atlas: tex_size must be a power of two <= 4096, n_tiles in [1,32767]");
+    if ((uint64_t)n_tiles * tex_size * tex_size > (1ull << 32))
+        return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "atlas of %d tiles of %dx%d exceeds 2^32 texels (the kernels index it with 32 bits)", n_tiles, tex_size, tex_size);
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
     size_t bytes = (size_t)n_tiles * tex_size * tex_size * 4;
     int rc = dev_realloc(ctx, &ctx->atlas, bytes);

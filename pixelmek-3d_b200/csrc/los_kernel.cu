@@ -21,7 +21,7 @@ struct LosParams {
     const int32_t *cell_items;
     const int4 *cell_rec;  // per bin cell: x = count, y/z/w = the first three candidate ids (count <= 3) or y = offset into cell_items
     int64_t n;
-    int n_segs, bin_x0, bin_y0, bin_w, bin_h;
+    int n_segs, bin_x0, bin_y0, bin_w, bin_h, max_skip;
     // move queries
     const uint16_t *grid0;
     int map_w, map_h;
@@ -208,6 +208,15 @@ __global__ void __launch_bounds__(LOS_THREADS, 3) k_los(LosParams p, long long r
         }
         // ---- one bin cell of every active ray
         if (active) {
+            // cells without candidates are walked through first (a few cheap instructions each), so that the
+            // lanes arrive at the test block below together with work to do instead of idling through it
+#pragma unroll 1
+            for (int skip = 0; skip < p.max_skip && cur.x == 0 && steps > 0; skip++) {
+                if ((tx < ty && cx != ex) || cy == ey) { tx += inv_dx; cx += sx; }
+                else { ty += inv_dy; cy += sy; }
+                steps--;
+                cur = __ldg(p.cell_rec + cy * p.bin_w + cx);
+            }
             // the step decision needs only tx/ty, so the NEXT cell's record is requested before this
             // cell's candidates are tested; candidates are fetched three at a time (independent loads)
             const bool more = steps > 0;
@@ -592,6 +601,8 @@ static int run_batch(pm3d_ctx *ctx, bool is_move, const double *rays, int64_t n,
     p.cell_rec = ctx->cell_rec;
     p.n = n;
     p.n_segs = ctx->n_segs; p.bin_x0 = ctx->bin_x0; p.bin_y0 = ctx->bin_y0; p.bin_w = ctx->bin_w; p.bin_h = ctx->bin_h;
+    p.max_skip = 3;
+    if (const char *e = getenv("PM3D_LOS_SKIP")) p.max_skip = atoi(e);  // tuning override (tools/)
     p.grid0 = ctx->grid; p.map_w = ctx->map_w; p.map_h = ctx->map_h; p.clip = clip;
     p.out_flag = d_flag;
     p.out_pos = (double2 *)d_pos;
@@ -679,6 +690,8 @@ extern "C" int pm3d_valid_move_batch(pm3d_ctx *ctx, const pm3d_mover *movers, in
     p.n = n;
     p.n_segs = ctx->n_segs;
     p.bin_x0 = ctx->bin_x0; p.bin_y0 = ctx->bin_y0; p.bin_w = ctx->bin_w; p.bin_h = ctx->bin_h;
+    p.max_skip = 3;
+    if (const char *e = getenv("PM3D_LOS_SKIP")) p.max_skip = atoi(e);  // tuning override (tools/)
     p.grid0 = ctx->grid;
     p.map_w = ctx->map_w; p.map_h = ctx->map_h;
     p.clip = clip_distance;

@@ -143,6 +143,9 @@ __device__ bool any_hit(const LosParams &p, const double4 &ray) {
 // and a lane that finishes its ray takes the next one of the range (refill once >= 8 lanes are idle)
 // instead of idling until the slowest ray of a fixed group of 32 is done.  One loop iteration = one bin cell.
 #define LOS_THREADS 256
+#ifndef LOS_LANE_CAP
+#define LOS_LANE_CAP 8
+#endif
 __global__ void __launch_bounds__(LOS_THREADS, 3) k_los(LosParams p, long long rays_per_warp) {
     const int lane = threadIdx.x & 31;
     const long long warp_id = (long long)blockIdx.x * (LOS_THREADS / 32) + (threadIdx.x >> 5);
@@ -153,7 +156,19 @@ __global__ void __launch_bounds__(LOS_THREADS, 3) k_los(LosParams p, long long r
     const double gx0 = (double)p.bin_x0, gy0 = (double)p.bin_y0;
     const double gx1 = (double)(p.bin_x0 + p.bin_w), gy1 = (double)(p.bin_y0 + p.bin_h);
 
+    __shared__ double4 s_ray[LOS_THREADS];
+    __shared__ int4 s_lr[LOS_THREADS];
+    __shared__ uint32_t s_q[LOS_THREADS / 32][32 * LOS_LANE_CAP];
+    __shared__ unsigned s_hit[LOS_THREADS / 32];
+    double4 *wray = s_ray + (threadIdx.x & ~31);
+    int4 *wlr = s_lr + (threadIdx.x & ~31);
+    uint32_t *wq = s_q[threadIdx.x >> 5];
+    unsigned *whit = &s_hit[threadIdx.x >> 5];
+    if (lane == 0) *whit = 0u;
+    __syncwarp();
+
     bool active = false;
+    int cbase = 0;  // candidates of the current cell already tested
     long long idx = 0;
     double4 ray = make_double4(0, 0, 0, 0);
     int4 lr = make_int4(0, 0, 0, 0);
@@ -198,70 +213,90 @@ __global__ void __launch_bounds__(LOS_THREADS, 3) k_los(LosParams p, long long r
                     ty = dy != 0 ? (dy > 0 ? (fy + 1.0 - ray.y) : (ray.y - fy)) * inv_dy : 1e300;
                     steps = abs(ex - cx) + abs(ey - cy);
                     cur = __ldg(p.cell_rec + cy * p.bin_w + cx);
+                    cbase = 0;
+                    wray[lane] = ray;
+                    wlr[lane] = lr;
                     active = true;
                 }
             }
+            __syncwarp();
         }
         if (__ballot_sync(0xffffffffu, active) == 0u) {
             if (next >= end) break;
             continue;
         }
-        // ---- one bin cell of every active ray
+        // ---- one bin cell of every active ray.  Cells without candidates are walked through first (a few cheap
+        //      instructions each) so the lanes reach the test phase together with work to do.
         if (active) {
-            // cells without candidates are walked through first (a few cheap instructions each), so that the
-            // lanes arrive at the test block below together with work to do instead of idling through it
 #pragma unroll 1
             for (int skip = 0; skip < p.max_skip && cur.x == 0 && steps > 0; skip++) {
                 if ((tx < ty && cx != ex) || cy == ey) { tx += inv_dx; cx += sx; }
                 else { ty += inv_dy; cy += sy; }
                 steps--;
                 cur = __ldg(p.cell_rec + cy * p.bin_w + cx);
+                cbase = 0;
             }
-            // the step decision needs only tx/ty, so the NEXT cell's record is requested before this
-            // cell's candidates are tested; candidates are fetched three at a time (independent loads)
-            const bool more = steps > 0;
-            int ncx = cx, ncy = cy;
-            double ntx = tx, nty = ty;
-            if (more) {
-                // never step past the target cell on either axis: keeps the walk inside the bins
-                if ((tx < ty && cx != ex) || cy == ey) { ntx += inv_dx; ncx += sx; }
-                else { nty += inv_dy; ncy += sy; }
-            }
-            const int4 rec = cur;
-            int4 nrec = make_int4(0, -1, -1, -1);
-            if (more) nrec = __ldg(p.cell_rec + ncy * p.bin_w + ncx);
-            bool hit = false;
-            for (int base = 0; base < rec.x && !hit; base += 3) {
-                int ids[3];
-                if (rec.x <= 3) { ids[0] = rec.y; ids[1] = rec.z; ids[2] = rec.w; }
-                else {
+        }
+        // The candidates of the lanes' current cells differ in number (0 .. a dozen), so a lane testing only its
+        // own would leave most of the warp idle.  They are pooled instead: every lane queues up to LOS_LANE_CAP
+        // (ray, segment) pairs in shared memory, then the warp's 32 lanes take the pairs round-robin and run the
+        // reference's exact predicate on whichever ray the pair belongs to (rays are staged in shared memory at
+        // refill).  A hit is reported to the owning lane through a bit mask.
+        const bool more = active && steps > 0;
+        int ncx = cx, ncy = cy;
+        double ntx = tx, nty = ty;
+        int4 nrec = make_int4(0, -1, -1, -1);
+        if (more) {
+            // never step past the target cell on either axis: keeps the walk inside the bins
+            if ((tx < ty && cx != ex) || cy == ey) { ntx += inv_dx; ncx += sx; }
+            else { nty += inv_dy; ncy += sy; }
+            nrec = __ldg(p.cell_rec + ncy * p.bin_w + ncx);  // requested before the tests, used after them
+        }
+        const int left = active ? cur.x - cbase : 0;
+        const int n_put = left < LOS_LANE_CAP ? left : LOS_LANE_CAP;
+        int off = n_put;  // inclusive scan
 #pragma unroll
-                    for (int k = 0; k < 3; k++) ids[k] = base + k < rec.x ? __ldg(p.cell_items + rec.y + base + k) : -1;
-                }
-                int4 br[3];
-                double2 s01[3], s23[3];
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    const int id = ids[k] < 0 ? 0 : ids[k];
-                    br[k] = __ldg(p.seg_irect + id);
-                    s01[k] = __ldg(reinterpret_cast<const double2 *>(p.segs + id));
-                    s23[k] = __ldg(reinterpret_cast<const double2 *>(p.segs + id) + 1);
-                }
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    if (hit || ids[k] < 0 || base + k >= rec.x) continue;
-                    // lineOfSight's integer bounding-rect pre-filter, as written
-                    if ((br[k].x > lr.z && br[k].y > lr.w) || (br[k].z < lr.x && br[k].w < lr.y)) continue;
-                    hit = segments_intersect(ray, make_double4(s01[k].x, s01[k].y, s23[k].x, s23[k].y));
-                }
-            }
-            if (hit || !more) {
-                p.out_flag[idx] = hit ? 0 : 1;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, off, o);
+            if (lane >= o) off += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, off, 31);
+        off -= n_put;
+        for (int k = 0; k < n_put; k++) {
+            const int c = cbase + k;
+            const int id = cur.x <= 3 ? (c == 0 ? cur.y : (c == 1 ? cur.z : cur.w)) : __ldg(p.cell_items + cur.y + c);
+            wq[off + k] = ((uint32_t)lane << 27) | (uint32_t)id;
+        }
+        __syncwarp();
+        for (int q = lane; q < total; q += 32) {
+            const uint32_t e = wq[q];
+            const int owner = (int)(e >> 27), id = (int)(e & 0x7ffffffu);
+            const int4 br = __ldg(p.seg_irect + id);  // lineOfSight's integer bounding-rect pre-filter, as written
+            const int4 olr = wlr[owner];
+            if ((br.x > olr.z && br.y > olr.w) || (br.z < olr.x && br.w < olr.y)) continue;
+            const double2 s01 = __ldg(reinterpret_cast<const double2 *>(p.segs + id));
+            const double2 s23 = __ldg(reinterpret_cast<const double2 *>(p.segs + id) + 1);
+            if (segments_intersect(wray[owner], make_double4(s01.x, s01.y, s23.x, s23.y))) atomicOr(whit, 1u << owner);
+        }
+        __syncwarp();
+        const unsigned hits = *whit;
+        __syncwarp();
+        if (lane == 0) *whit = 0u;
+        if (active) {
+            const bool hit = (hits >> lane) & 1u;
+            if (hit) {
+                p.out_flag[idx] = 0;
+                active = false;
+            } else if (left > n_put) {
+                cbase += n_put;  // more candidates in this cell than one round takes
+            } else if (!more) {
+                p.out_flag[idx] = 1;
                 active = false;
             } else {
                 steps--;
                 cx = ncx; cy = ncy; tx = ntx; ty = nty;
                 cur = nrec;
+                cbase = 0;
             }
         }
     }
@@ -601,7 +636,7 @@ static int run_batch(pm3d_ctx *ctx, bool is_move, const double *rays, int64_t n,
     p.cell_rec = ctx->cell_rec;
     p.n = n;
     p.n_segs = ctx->n_segs; p.bin_x0 = ctx->bin_x0; p.bin_y0 = ctx->bin_y0; p.bin_w = ctx->bin_w; p.bin_h = ctx->bin_h;
-    p.max_skip = 3;
+    p.max_skip = 2;
     if (const char *e = getenv("PM3D_LOS_SKIP")) p.max_skip = atoi(e);  // tuning override (tools/)
     p.grid0 = ctx->grid; p.map_w = ctx->map_w; p.map_h = ctx->map_h; p.clip = clip;
     p.out_flag = d_flag;
@@ -690,7 +725,7 @@ extern "C" int pm3d_valid_move_batch(pm3d_ctx *ctx, const pm3d_mover *movers, in
     p.n = n;
     p.n_segs = ctx->n_segs;
     p.bin_x0 = ctx->bin_x0; p.bin_y0 = ctx->bin_y0; p.bin_w = ctx->bin_w; p.bin_h = ctx->bin_h;
-    p.max_skip = 3;
+    p.max_skip = 2;
     if (const char *e = getenv("PM3D_LOS_SKIP")) p.max_skip = atoi(e);  // tuning override (tools/)
     p.grid0 = ctx->grid;
     p.map_w = ctx->map_w; p.map_h = ctx->map_h;

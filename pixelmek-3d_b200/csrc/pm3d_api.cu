@@ -638,6 +638,7 @@ static inline int64_t host_go_int(double v) {
 int pm3d_upload_segments(pm3d_ctx *ctx, const double *xyxy, int n) {
     if (!ctx) return PM3D_ERR_ARG;
     if (n < 0 || (n > 0 && !xyxy)) return pm3d_fail(ctx, PM3D_ERR_ARG, "null segments");
+    if (n >= (1 << 27)) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "%d collision segments (the LOS kernel packs a segment id into 27 bits)", n);
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
     // bounding box of all endpoints -> bin area dilated by one cell plus one spare
     double minx = 0, miny = 0, maxx = 1, maxy = 1;

@@ -446,6 +446,8 @@ def run_ours(args, rank, world, local_rank):
         t0 = time.perf_counter()
         e2e_loop(e2e_steps, piped)
         dt = time.perf_counter() - t0
+        if os.environ.get("PM3D_BENCH_DEBUG"):
+            print(f"[rank {rank}] e2e piped={piped}: {e2e_steps / dt:.0f} frames/s on this rank", file=sys.stderr, flush=True)
         te = torch.tensor([dt], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)

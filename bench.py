@@ -412,10 +412,12 @@ def run_ours(args, rank, world, local_rank):
     # per-kernel durations: the same frames again with an event pair around each kernel (the event
     # records cost ~1 us each, so they are kept out of the region `value` is computed from)
     kt_frames = min(args.steps, 1024)
+    ctx.set_option(pm3d._lib.OPT_OVERLAP, 0)  # kernels one after the other, as ncu sees them: durations without a co-running launch
     ctx.ktimer_begin(kt_frames)
     for i in range(kt_frames):
         frame(i)
     kt = ctx.ktimer_collect(kt_frames)
+    ctx.set_option(pm3d._lib.OPT_OVERLAP, 1)
     sums = ctx.frame_checksums(1)  # last frame: compact result
     t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -485,6 +487,10 @@ def run_ours(args, rank, world, local_rank):
     line["roofline"] = {"bound": "hbm", "kernel": "k_compose", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650 GB/s",
                         "algorithmic_bytes_per_launch": FRAME_BYTES, "kernel_ms": compose_ms,
+                        "note": "kernel_ms = mean CUDA-event duration of k_compose over the same frames with the front/compose overlap "
+                                "switched off (one kernel at a time, like the ncu launch list); in the timed region of `value` the "
+                                "front launch of frame i+1 runs beside it, so ms_per_step < kernel_ms + front.  The kernel is "
+                                "instruction/latency bound, not HBM bound (DESIGN.md section 5)",
                         "other_kernels_ms": {"k_front (column cast + view setup)": float(kt[:, 0].mean()) if len(kt) else None}}
     line["mrays_per_s"] = value * W_PX * 3 / 1e6
     line["mpixels_per_s"] = value * W_PX * H_PX / 1e6

@@ -11,6 +11,9 @@
 // lattice corner, a neighbour of one), and the dilation covers that neighbour.
 #include <stdlib.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "pm3d_internal.cuh"
 
 struct LosParams {
@@ -345,6 +348,11 @@ struct MoveParams {
     const pm3d_collider *colliders;
     pm3d_move_result *out;
     int n_colliders, player;
+    // colliders binned by the 1x1 cell their position falls in (pm3d_upload_colliders); cb_w == 0: not binned
+    const int32_t *cb_start;  // CSR over [cb_x0, cb_x0 + cb_w) x [cb_y0, cb_y0 + cb_h), ids ascending per cell
+    const int32_t *cb_items;
+    const int32_t *cb_loose;  // colliders outside the binned area (or not finite): always candidates
+    int cb_x0, cb_y0, cb_w, cb_h, n_loose;
 };
 
 #define GEOM_EPS 1e-14
@@ -394,6 +402,7 @@ __device__ __forceinline__ void z_min_max(double z, double height, int anchor, d
 }
 
 #define MOVE_MAX_WALL_HITS 8
+#define MOVE_MAX_CANDIDATES 16
 __global__ void __launch_bounds__(128) k_valid_move(MoveParams q) {
     const LosParams &p = q.los;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -528,21 +537,24 @@ __global__ void __launch_bounds__(128) k_valid_move(MoveParams q) {
         }
     }
 
-    // ---- collidable sprites (:135-194), list order
-    for (int s = 0; s < q.n_colliders; s++) {
-        if (s == q.player || s == m.self || s == m.parent) continue;
+    // ---- collidable sprites (:135-194), list order.  The reference tests every sprite against the proximity box
+    //      |sprite - new| <= ceil(checkDist) first; with the colliders binned by cell only the cells that box touches
+    //      are read.  The candidates are put in ascending list order before they are processed, so counts, nearest
+    //      point and collisions[0] (ties: earliest inserted) are those of the full loop.
+    auto collide = [&](int s) {
+        if (s == q.player || s == m.self || s == m.parent) return;
         const pm3d_collider *sp = q.colliders + s;
         const double sx = sp->x, sy = sp->y;
-        if (!(fabs(sx - newX) <= prox && fabs(sy - newY) <= prox)) continue;
+        if (!(fabs(sx - newX) <= prox && fabs(sy - newY) <= prox)) return;
         const double srad = sp->radius;
-        if (srad <= 0 || sp->destroyed) continue;
+        if (srad <= 0 || sp->destroyed) return;
         double smin, smax, tmin, tmax;
         z_min_max(newZ, m.height, m.anchor, smin, smax);
         z_min_max(sp->z, sp->height, sp->anchor, tmin, tmax);
-        if (smin > tmax || tmin > smax) continue;
+        if (smin > tmax || tmin > smax) return;
         const double mid = smin + (smax - smin) / 2;
         const double zI = mid < tmin ? tmin : (mid > tmax ? tmax : mid);
-        if (zI < 0) continue;
+        if (zI < 0) return;
         const double comb_r = srad + m.radius;
         double comb[4];
         const int nc = line_circle_intersection(posX, posY, newX, newY, sx, sy, comb_r, comb);
@@ -560,7 +572,40 @@ __global__ void __launch_bounds__(128) k_valid_move(MoveParams q) {
             add_point(newX, newY);
             consider(s, newX, newY, zI);
         }
+    };
+    bool binned = false;
+    if (q.cb_w > 0 && prox <= 3.0 && fabs(newX) < 1e9 && fabs(newY) < 1e9) {
+        int cand[MOVE_MAX_CANDIDATES];
+        int nc = 0;
+        bool overflow = false;
+        const int cx0 = max((int)floor(newX - prox) - q.cb_x0, 0), cx1 = min((int)floor(newX + prox) - q.cb_x0, q.cb_w - 1);
+        const int cy0 = max((int)floor(newY - prox) - q.cb_y0, 0), cy1 = min((int)floor(newY + prox) - q.cb_y0, q.cb_h - 1);
+        for (int cx = cx0; cx <= cx1 && !overflow; cx++) {
+            // the cells of one column are consecutive in the CSR: one range per column
+            if (cy0 > cy1) break;
+            const int b = __ldg(q.cb_start + cx * q.cb_h + cy0), e = __ldg(q.cb_start + cx * q.cb_h + cy1 + 1);
+            for (int k = b; k < e; k++) {
+                if (nc == MOVE_MAX_CANDIDATES) { overflow = true; break; }
+                cand[nc++] = __ldg(q.cb_items + k);
+            }
+        }
+        for (int k = 0; k < q.n_loose && !overflow; k++) {
+            if (nc == MOVE_MAX_CANDIDATES) { overflow = true; break; }
+            cand[nc++] = __ldg(q.cb_loose + k);
+        }
+        if (!overflow) {
+            for (int a = 1; a < nc; a++) {  // ascending list order (insertion sort of <= 16 ids)
+                const int v = cand[a];
+                int b = a - 1;
+                for (; b >= 0 && cand[b] > v; b--) cand[b + 1] = cand[b];
+                cand[b + 1] = v;
+            }
+            for (int k = 0; k < nc; k++) collide(cand[k]);
+            binned = true;
+        }
     }
+    if (!binned)
+        for (int s = 0; s < q.n_colliders; s++) collide(s);
 
     r.n_points = n_points;
     r.n_collisions = n_collisions;
@@ -682,10 +727,49 @@ extern "C" int pm3d_upload_colliders(pm3d_ctx *ctx, const pm3d_collider *collide
     if (n < 0 || (n > 0 && !colliders) || player_index < -1 || player_index >= n)
         return pm3d_fail(ctx, PM3D_ERR_ARG, "bad collider list (n = %d, player_index = %d)", n, player_index);
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (ctx->colliders) PM3D_CUDA(ctx, cudaFree(ctx->colliders));
-    ctx->colliders = nullptr;
+    PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    void *old[] = {ctx->colliders, ctx->cb_start, ctx->cb_items, ctx->cb_loose};
+    for (void *p : old)
+        if (p) PM3D_CUDA(ctx, cudaFree(p));
+    ctx->colliders = nullptr; ctx->cb_start = ctx->cb_items = ctx->cb_loose = nullptr;
+    ctx->cb_w = ctx->cb_h = ctx->n_loose = 0;
     PM3D_CUDA(ctx, cudaMalloc((void **)&ctx->colliders, sizeof(pm3d_collider) * (size_t)(n > 0 ? n : 1)));
     if (n) PM3D_CUDA(ctx, cudaMemcpyAsync(ctx->colliders, colliders, sizeof(pm3d_collider) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    // bin the colliders by the cell their position falls in: the area is the bounding box of the finite positions,
+    // at most 4096 x 4096 cells; what lies outside (or is not finite) goes to the "loose" list
+    if (n >= 32) {
+        double minx = 1e300, miny = 1e300, maxx = -1e300, maxy = -1e300;
+        for (int i = 0; i < n; i++)
+            if (isfinite(colliders[i].x) && isfinite(colliders[i].y) && fabs(colliders[i].x) < 1e6 && fabs(colliders[i].y) < 1e6) {
+                minx = std::min(minx, colliders[i].x); maxx = std::max(maxx, colliders[i].x);
+                miny = std::min(miny, colliders[i].y); maxy = std::max(maxy, colliders[i].y);
+            }
+        if (maxx >= minx) {
+            const int x0 = (int)floor(minx), y0 = (int)floor(miny);
+            const int w = std::min((int)floor(maxx) - x0 + 1, 4096), h = std::min((int)floor(maxy) - y0 + 1, 4096);
+            std::vector<int32_t> start((size_t)w * h + 1, 0), loose;
+            std::vector<int32_t> cell(n, -1);
+            for (int i = 0; i < n; i++) {
+                const double x = colliders[i].x, y = colliders[i].y;
+                if (isfinite(x) && isfinite(y) && x >= x0 && y >= y0 && x < (double)x0 + w && y < (double)y0 + h)
+                    cell[i] = ((int)floor(x) - x0) * h + ((int)floor(y) - y0);
+                if (cell[i] >= 0) start[cell[i] + 1]++; else loose.push_back(i);
+            }
+            for (size_t c = 0; c < (size_t)w * h; c++) start[c + 1] += start[c];
+            std::vector<int32_t> items(std::max(n, 1)), fill(start.begin(), start.end() - 1);
+            for (int i = 0; i < n; i++)  // ascending ids per cell
+                if (cell[i] >= 0) items[fill[cell[i]]++] = i;
+            if (loose.size() <= 8) {
+                PM3D_CUDA(ctx, cudaMalloc((void **)&ctx->cb_start, start.size() * 4));
+                PM3D_CUDA(ctx, cudaMalloc((void **)&ctx->cb_items, items.size() * 4));
+                PM3D_CUDA(ctx, cudaMalloc((void **)&ctx->cb_loose, std::max<size_t>(loose.size(), 1) * 4));
+                PM3D_CUDA(ctx, cudaMemcpy(ctx->cb_start, start.data(), start.size() * 4, cudaMemcpyHostToDevice));
+                PM3D_CUDA(ctx, cudaMemcpy(ctx->cb_items, items.data(), items.size() * 4, cudaMemcpyHostToDevice));
+                if (!loose.empty()) PM3D_CUDA(ctx, cudaMemcpy(ctx->cb_loose, loose.data(), loose.size() * 4, cudaMemcpyHostToDevice));
+                ctx->cb_x0 = x0; ctx->cb_y0 = y0; ctx->cb_w = w; ctx->cb_h = h; ctx->n_loose = (int)loose.size();
+            }
+        }
+    }
     PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->n_colliders = n;
     ctx->player_index = player_index;
@@ -733,6 +817,8 @@ extern "C" int pm3d_valid_move_batch(pm3d_ctx *ctx, const pm3d_mover *movers, in
     p.out_flag = nullptr; p.out_pos = nullptr;
     q.movers = d_in; q.colliders = ctx->colliders; q.out = d_out;
     q.n_colliders = ctx->n_colliders; q.player = ctx->player_index;
+    q.cb_start = ctx->cb_start; q.cb_items = ctx->cb_items; q.cb_loose = ctx->cb_loose;
+    q.cb_x0 = ctx->cb_x0; q.cb_y0 = ctx->cb_y0; q.cb_w = ctx->cb_w; q.cb_h = ctx->cb_h; q.n_loose = ctx->n_loose;
     const long long blocks = (n + 127) / 128;
     if (blocks > 0x7fffffffll) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "batch too large");
     k_valid_move<<<(unsigned)blocks, 128, 0, ctx->stream>>>(q);

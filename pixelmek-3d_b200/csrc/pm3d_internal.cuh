@@ -164,6 +164,8 @@ struct pm3d_ctx {
     size_t present_bytes = 0;
     pm3d_collider *colliders = nullptr;  // g.player.Unit + collidable sprites (pm3d_upload_colliders)
     int n_colliders = 0, player_index = -1;
+    int32_t *cb_start = nullptr, *cb_items = nullptr, *cb_loose = nullptr;  // colliders binned by cell (los_kernel.cu)
+    int cb_x0 = 0, cb_y0 = 0, cb_w = 0, cb_h = 0, n_loose = 0;
     void *io_a = nullptr, *io_b = nullptr, *io_c = nullptr;  // batch staging on device
     size_t io_a_bytes = 0, io_b_bytes = 0, io_c_bytes = 0;
 

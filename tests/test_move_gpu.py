@@ -191,3 +191,49 @@ def test_host_mirror_get_valid_move_with_check_alternate(gpu_ctx):
     assert game.lineOfSight(None, ents[0]) is False
     a, b = col.Entity(2.5, 2.5), col.Entity(3.5, 2.5)
     assert game.lineOfSight(a, b) == bool(O.los_batch(g["segments"], np.array([[2.5, 2.5, 3.5, 2.5]]))[0])
+
+
+def test_binned_colliders_equal_the_full_loop_in_awkward_layouts(gpu_ctx):
+    """The colliders are binned by cell when there are >= 32 of them: positions on cell borders, stacked in one cell
+    (more candidates than the kernel's 16-entry list), outside the map, huge, infinite and NaN ("loose" list), movers
+    landing exactly on borders and moves longer than the binned look-up handles (full-loop fallback)."""
+    lvl = np.zeros((1, 24, 20), dtype=np.uint16)
+    lvl[0, 0, :] = lvl[0, -1, :] = 32767
+    lvl[0, :, 0] = lvl[0, :, -1] = 32767
+    scene = W.scene_from_grid(lvl, 1)
+    segs = pm3d.generate_wall_collision_lines(lvl[0], False, W.CLIP_DISTANCE)
+    rng = np.random.default_rng(3)
+    n = 96
+    c = np.zeros(n, dtype=O.COLLIDER_DTYPE)
+    c["x"] = rng.integers(1, 23, n) + rng.choice([0.0, 0.5, 0.999999999, 0.25], n)     # many exactly on borders
+    c["y"] = rng.integers(1, 19, n) + rng.choice([0.0, 0.5, 0.75], n)
+    c["x"][:24] = 10.0 + rng.random(24) * 0.9                                            # 24 stacked in one cell
+    c["y"][:24] = 10.0 + rng.random(24) * 0.9
+    c["x"][24:30] = [-3.5, 40.0, 1e7, float("inf"), float("nan"), -1e12]                 # loose
+    c["y"][24:30] = [5.0, 5.0, 5.0, 5.0, 5.0, 5.0]
+    c["radius"] = 0.05 + rng.random(n) * 0.5
+    c["height"] = 0.2 + rng.random(n)
+    c["anchor"] = rng.integers(0, 3, n)
+    m = np.zeros(6000, dtype=O.MOVER_DTYPE)
+    k = len(m)
+    m["pos_x"] = rng.integers(1, 23, k) + rng.choice([0.0, 0.5, 0.3, 0.999], k)
+    m["pos_y"] = rng.integers(1, 19, k) + rng.choice([0.0, 0.5, 0.7], k)
+    m["pos_x"][:1500] = 9.0 + rng.random(1500) * 3.0                                     # around the stack
+    m["pos_y"][:1500] = 9.0 + rng.random(1500) * 3.0
+    ang = rng.random(k) * 2 * np.pi
+    length = rng.choice([0.25, 0.5, 1.0, 2.5, 3.0, 7.0], k)                              # 7.0: wider than the binned look-up
+    m["move_x"] = np.where(rng.random(k) < 0.3, np.round(m["pos_x"] + np.cos(ang) * length), m["pos_x"] + np.cos(ang) * length)
+    m["move_y"] = np.where(rng.random(k) < 0.3, np.round(m["pos_y"] + np.sin(ang) * length), m["pos_y"] + np.sin(ang) * length)
+    m["move_x"][-40:-20] = -2.5                                                          # next to the loose colliders
+    m["move_y"][-40:-20] = 5.0 + rng.random(20) - 0.5
+    m["move_x"][-20:] = 1e7 + rng.random(20)
+    m["move_y"][-20:] = 5.0
+    m["radius"], m["height"], m["self"], m["parent"], m["anchor"] = 0.2, 0.6, -1, -1, rng.integers(0, 3, k)
+    gpu_ctx.upload_scene(scene)
+    gpu_ctx.upload_segments(segs)
+    for player in (-1, 3, 50):
+        gpu_ctx.upload_colliders(c.astype(pm3d._lib.COLLIDER_DTYPE), player)
+        got = gpu_ctx.valid_move_batch(m.astype(pm3d._lib.MOVER_DTYPE), W.CLIP_DISTANCE)
+        want = O.valid_move_batch(O.Scene(scene), segs, c, player, W.CLIP_DISTANCE, m, threads=8)
+        assert_results_equal(got.view(O.MOVE_RESULT_DTYPE), want)
+    assert int((want["n_collisions"] > 16).sum()) > 10       # the stacked cell overflows the candidate list

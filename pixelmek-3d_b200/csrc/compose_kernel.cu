@@ -29,7 +29,6 @@
 
 #include "pm3d_internal.cuh"
 
-#define COMPOSE_WARPS 4
 // rows per warp (WARP_ROWS, a template parameter: 2, 4 or 8 = 1, 2 or 4 iterations of 2 rows) trades the
 // per-warp prologue against the length of the serial chain: single frames want many short warps, large
 // batches of views want few long ones.
@@ -208,8 +207,10 @@ __device__ __forceinline__ void load4(const int2 *base, size_t i, bool vec, int 
     }
 }
 
-template <int WARP_ROWS, int MIN_BLOCKS>
-__global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS) k_compose(const __grid_constant__ ComposeParams p) {
+// COMPOSE_WARPS warps per CTA: 4 for single frames, 2 for large batches (a CTA's slot is held until its slowest warp
+// ends, and small CTAs waste fewer warp slots); MIN_BLOCKS is given for 4-warp CTAs and scaled.
+template <int WARP_ROWS, int MIN_BLOCKS, int COMPOSE_WARPS>
+__global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_WARPS) k_compose(const __grid_constant__ ComposeParams p) {
     constexpr int COMPOSE_ROWS = COMPOSE_WARPS * WARP_ROWS;
     __shared__ WarpList s_list[COMPOSE_WARPS];
     __shared__ uint32_t s_xm[COMPOSE_WARPS][WARP_WORDS][32];  // per-lane sprite masks (kept out of registers and out of unrolled code)
@@ -690,15 +691,16 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     int minb = rows >= 8 ? 8 : 6;
     if (const char *e = getenv("PM3D_COMPOSE_ROWS")) rows = atoi(e);      // tuning overrides (tools/)
     if (const char *e = getenv("PM3D_COMPOSE_MINB")) minb = atoi(e);
-    dim3 block(COMPOSE_WARPS * 32), grid(ctx->n_groups, (ctx->h + COMPOSE_WARPS * rows - 1) / (COMPOSE_WARPS * rows), n_views);
+    const int cta_warps = rows >= 8 ? 2 : 4;
+    dim3 block(cta_warps * 32), grid(ctx->n_groups, (ctx->h + cta_warps * rows - 1) / (cta_warps * rows), n_views);
     pm3d_kt_mark(ctx, 2, 0, ctx->stream);
-    if (rows == 16) k_compose<16, 8><<<grid, block, 0, ctx->stream>>>(p);
-    else if (rows == 8 && minb == 8) k_compose<8, 8><<<grid, block, 0, ctx->stream>>>(p);
-    else if (rows == 8) k_compose<8, 6><<<grid, block, 0, ctx->stream>>>(p);
-    else if (rows == 4 && minb == 8) k_compose<4, 8><<<grid, block, 0, ctx->stream>>>(p);
-    else if (rows == 4) k_compose<4, 6><<<grid, block, 0, ctx->stream>>>(p);
-    else if (minb == 8) k_compose<2, 8><<<grid, block, 0, ctx->stream>>>(p);
-    else k_compose<2, 6><<<grid, block, 0, ctx->stream>>>(p);
+    if (rows == 16) k_compose<16, 8, 2><<<grid, block, 0, ctx->stream>>>(p);
+    else if (rows == 8 && minb == 8) k_compose<8, 8, 2><<<grid, block, 0, ctx->stream>>>(p);
+    else if (rows == 8) k_compose<8, 6, 2><<<grid, block, 0, ctx->stream>>>(p);
+    else if (rows == 4 && minb == 8) k_compose<4, 8, 4><<<grid, block, 0, ctx->stream>>>(p);
+    else if (rows == 4) k_compose<4, 6, 4><<<grid, block, 0, ctx->stream>>>(p);
+    else if (minb == 8) k_compose<2, 8, 4><<<grid, block, 0, ctx->stream>>>(p);
+    else k_compose<2, 6, 4><<<grid, block, 0, ctx->stream>>>(p);
     pm3d_kt_mark(ctx, 2, 1, ctx->stream);
     ctx->launches++;
     PM3D_CUDA(ctx, cudaGetLastError());

@@ -92,6 +92,9 @@ __device__ __noinline__ uint32_t sprite_texel(const DrawRec &d, const uint32_t *
 // index of the texel sprite `d` shows at pixel (x, y) inside sheet_pixels, or ~0 when it does not cover the pixel
 // (inlined twice in the front-to-back walk so that the loads of two sprites are in flight together)
 #define NO_TEXEL 0xffffffffffffffffull
+#ifndef SPRITE_BATCH
+#define SPRITE_BATCH 2
+#endif
 __device__ __forceinline__ uint64_t sprite_index(const DrawRec &d, int x, int y, double z) {
     if (x < d.dsx || x >= d.dex || x <= 0 || y < d.dsy || y >= d.dey) return NO_TEXEL;
     if (!(d.transformY < z)) return NO_TEXEL;
@@ -244,15 +247,14 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
     //      rows < sky_below are above every wall slice and every floor start
     int fs_max = 0, sky_below = 0x7fffffff;
     {
-        const int n_agg = p.num_levels * 2;
-        for (int i = lane; i < n_agg; i += 32) {
-            const int4 a = p.agg[(((size_t)view * p.num_levels + (i >> 1)) * p.n_groups + group) * 2 + (i & 1)];
-            fs_max = max(fs_max, a.z);
-            sky_below = min(sky_below, min(a.x, a.y));
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            fs_max = max(fs_max, __shfl_xor_sync(0xffffffffu, fs_max, o));
-            sky_below = min(sky_below, __shfl_xor_sync(0xffffffffu, sky_below, o));
+        // every lane reads the same 2*L records (one broadcast transaction each): cheaper than a strided read
+        // followed by ten shuffles
+        const int4 *ag = p.agg + ((size_t)view * p.num_levels * p.n_groups + group) * 2;
+#pragma unroll 2
+        for (int l = 0; l < p.num_levels; l++) {
+            const int4 a0 = __ldg(ag + (size_t)l * p.n_groups * 2), a1 = __ldg(ag + (size_t)l * p.n_groups * 2 + 1);
+            fs_max = max(fs_max, max(a0.z, a1.z));
+            sky_below = min(sky_below, min(min(a0.x, a0.y), min(a1.x, a1.y)));
         }
     }
 
@@ -345,14 +347,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
     const double ptx = posx * texd, pty = posy * texd;
     const uint32_t boundx = (uint32_t)min((uint64_t)p.map_w << p.tex_shift, (uint64_t)0x80000000u);
     const uint32_t boundy = (uint32_t)min((uint64_t)p.map_h << p.tex_shift, (uint64_t)0x80000000u);
-    double lane_cd_max = -1.0;
-    if (fast_ok) {
-        double cw[4], cr[4];
-        load4(p.flo_dw, fi0, vec, 4, cw);
-        load4(p.flo_rc, fi0, vec, 4, cr);
-        if (cr[0] != 0.0 && cr[1] != 0.0 && cr[2] != 0.0 && cr[3] != 0.0)
-            lane_cd_max = 4.0 * fmin(fmin(fabs(cw[0]), fabs(cw[1])), fmin(fabs(cw[2]), fabs(cw[3])));
-    }
+    double lane_cd_max = -2.0;  // -2: not computed yet (only warps that reach a floor row need it)
 
     // per-lane mask of the warp's sprites that overlap this lane's four columns (lanes then walk
     // different sprites concurrently instead of every lane scanning the whole list)
@@ -368,13 +363,18 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
         s_xm[warp][wd][lane] = m;
     }
 
-    // box texel column of each of this lane's pixels
-    uint32_t bu[4];
+    // box texel column of each of this lane's pixels: once per warp when it walks many rows, else by the rows that
+    // show the box (a two-row warp below the horizon never needs it)
+    auto box_col = [&](int j) -> uint32_t {
+        const uint32_t u = (uint32_t)((((uint64_t)(2 * (int64_t)(x0 + j) + 1)) * p.xstep) >> 33);
+        return u > (uint32_t)tmask ? (uint32_t)tmask : u;
+    };
+    uint32_t bu[4] = {0u, 0u, 0u, 0u};
+    if (WARP_ROWS >= 8) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        uint32_t u = (uint32_t)((((uint64_t)(2 * (int64_t)(x0 + j) + 1)) * p.xstep) >> 33);
-        bu[j] = u > (uint32_t)tmask ? (uint32_t)tmask : u;
+        for (int j = 0; j < 4; j++) bu[j] = box_col(j);
     }
+    auto box_u = [&](int j) -> uint32_t { return WARP_ROWS >= 8 ? bu[j] : box_col(j); };
 
     double zb[4] = {0.0, 0.0, 0.0, 0.0};  // z-buffer of this lane's columns (rows share it)
     if (n_list > 0) load4(p.zbuf, fi0, vec, nvalid, zb);
@@ -394,8 +394,9 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
         uint32_t s_top[4] = {0u, 0u, 0u, 0u};
         const bool sprite_f2b = n_list > 0 && !overflow && !p.force_painter;
         if (sprite_f2b && WARP_ROWS < 8) {
-            // Latency mode (few rows per warp, single frames).  Two sprites per step: a lane's walk is a chain of dependent loads (record -> texel), so the records
-            // and texels of the next two candidates are fetched together and then resolved nearest first.
+            // Latency mode (few rows per warp, single frames).  SPRITE_BATCH sprites per step: a lane's walk is a chain of
+            // dependent loads (record -> texel), so the records and texels of the next few candidates are fetched
+            // together and then resolved nearest first.
             int wd = n_words - 1;
             uint32_t m = s_xm[warp][wd][lane];
             auto next_sprite = [&]() -> int {  // nearest remaining sprite of this lane that crosses row y, or -1
@@ -413,33 +414,33 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
             };
 #pragma unroll 1
             while (s_got != full) {
-                const int i0 = next_sprite();
-                if (i0 < 0) break;
-                const int i1 = next_sprite();
-                const DrawRec &d0 = draw[wl.id[i0]];
-                const DrawRec &d1 = draw[wl.id[i1 < 0 ? i0 : i1]];
-                uint64_t a0[4], a1[4];
+                int ids[SPRITE_BATCH];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const bool need = j < nvalid && !((s_got >> j) & 1u);
-                    a0[j] = need ? sprite_index(d0, x0 + j, y, zb[j]) : NO_TEXEL;
-                    a1[j] = (need && i1 >= 0) ? sprite_index(d1, x0 + j, y, zb[j]) : NO_TEXEL;
+                for (int b = 0; b < SPRITE_BATCH; b++) ids[b] = (b == 0 || ids[b - 1] >= 0) ? next_sprite() : -1;
+                if (ids[0] < 0) break;
+                const DrawRec *dr[SPRITE_BATCH];
+#pragma unroll
+                for (int b = 0; b < SPRITE_BATCH; b++) dr[b] = draw + wl.id[ids[b] < 0 ? ids[0] : ids[b]];
+                uint32_t tx[SPRITE_BATCH][4];
+#pragma unroll
+                for (int b = 0; b < SPRITE_BATCH; b++) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const bool need = j < nvalid && !((s_got >> j) & 1u) && ids[b] >= 0;
+                        const uint64_t a = need ? sprite_index(*dr[b], x0 + j, y, zb[j]) : NO_TEXEL;
+                        tx[b][j] = a != NO_TEXEL ? __ldg(p.sheet_pixels + a) : 0u;
+                    }
                 }
-                uint32_t t0[4], t1[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    t0[j] = a0[j] != NO_TEXEL ? __ldg(p.sheet_pixels + a0[j]) : 0u;
-                    t1[j] = a1[j] != NO_TEXEL ? __ldg(p.sheet_pixels + a1[j]) : 0u;
-                }
-                const uint32_t tint0 = d0.tint, tint1 = d1.tint;
+                for (int b = 0; b < SPRITE_BATCH; b++) {  // resolve nearest first
+                    const uint32_t tint = dr[b]->tint;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    uint32_t a = t0[j] >> 24;
-                    if (a == 255u) { s_top[j] = blend_over(0u, t0[j], tint0); s_got |= 1u << j; continue; }
-                    if (a != 0u) s_trans |= 1u << j;
-                    a = t1[j] >> 24;
-                    if (a == 255u) { s_top[j] = blend_over(0u, t1[j], tint1); s_got |= 1u << j; }
-                    else if (a != 0u) s_trans |= 1u << j;
+                    for (int j = 0; j < 4; j++) {
+                        if ((s_got >> j) & 1u) continue;
+                        const uint32_t a = tx[b][j] >> 24;
+                        if (a == 255u) { s_top[j] = blend_over(0u, tx[b][j], tint); s_got |= 1u << j; }
+                        else if (a != 0u) s_trans |= 1u << j;
+                    }
                 }
             }
         }
@@ -491,6 +492,14 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
             // ---------- every pixel of this lane is a floor candidate: four fast casts in straight line
             //            (pm3d_internal.cuh "fast floor cast"); anything doubtful goes to the mixed path below,
             //            which runs the reference sequence
+            if (lane_cd_max == -2.0) {
+                double cw[4], cr[4];
+                load4(p.flo_dw, fi0, vec, 4, cw);
+                load4(p.flo_rc, fi0, vec, 4, cr);
+                lane_cd_max = -1.0;
+                if (cr[0] != 0.0 && cr[1] != 0.0 && cr[2] != 0.0 && cr[3] != 0.0)
+                    lane_cd_max = 4.0 * fmin(fmin(fabs(cw[0]), fabs(cw[1])), fmin(fabs(cw[2]), fabs(cw[3])));
+            }
             if ((r.info & 0x20000000u) && r.cd <= lane_cd_max) {
                 double cr[4], dx[4], dy[4];
                 load4(p.flo_rc, fi0, vec, 4, cr);
@@ -526,7 +535,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
             // ---------- above every wall slice and floor start of the group: sky / floor box only
             uint32_t t[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) t[j] = box_texel(p, r.info, bu[j]);
+            for (int j = 0; j < 4; j++) t[j] = box_texel(p, r.info, box_u(j));
             if ((t[0] & t[1] & t[2] & t[3]) >= 0xff000000u) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) px[j] = shade_opaque(t[j], box_tint);
@@ -578,13 +587,13 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
             }
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                if ((pending >> j) & 1u) px[j] = blend_over(0u, box_texel(p, r.info, bu[j]), box_tint);
+                if ((pending >> j) & 1u) px[j] = blend_over(0u, box_texel(p, r.info, box_u(j)), box_tint);
             if (slow) {
                 // one inlined copy of the painter (a call would force the kernel parameters into local memory)
 #pragma unroll 1
                 for (int j = 0; j < 4; j++) {
                     if (!((slow >> j) & 1u)) continue;
-                    const uint32_t u = j == 0 ? bu[0] : (j == 1 ? bu[1] : (j == 2 ? bu[2] : bu[3]));
+                    const uint32_t u = box_u(j);
                     const uint32_t v = background_painter(p, view, x0 + j, y, u);
                     if (j == 0) px[0] = v; else if (j == 1) px[1] = v; else if (j == 2) px[2] = v; else px[3] = v;
                 }

@@ -392,6 +392,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
         unsigned s_got = 0u;    // pixels whose nearest opaque sprite texel is in s_top
         unsigned s_trans = 0u;  // pixels that met a translucent sprite texel in front of it
         uint32_t s_top[4] = {0u, 0u, 0u, 0u};
+        uint32_t s_stop = 0u;   // list index (one byte per pixel) of the sprite whose opaque texel is in s_top
         const bool sprite_f2b = n_list > 0 && !overflow && !p.force_painter;
         if (sprite_f2b && WARP_ROWS < 8) {
             // Latency mode (few rows per warp, single frames).  SPRITE_BATCH sprites per step: a lane's walk is a chain of
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                     for (int j = 0; j < 4; j++) {
                         if ((s_got >> j) & 1u) continue;
                         const uint32_t a = tx[b][j] >> 24;
-                        if (a == 255u) { s_top[j] = blend_over(0u, tx[b][j], tint); s_got |= 1u << j; }
+                        if (a == 255u) { s_top[j] = blend_over(0u, tx[b][j], tint); s_got |= 1u << j; s_stop |= (uint32_t)ids[b] << (8 * j); }
                         else if (a != 0u) s_trans |= 1u << j;
                     }
                 }
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                         if (j >= nvalid || ((s_got >> j) & 1u)) continue;
                         const uint32_t t = sprite_texel(d, p.sheet_pixels, x0 + j, y, zb[j]);
                         const uint32_t a = t >> 24;
-                        if (a == 255u) { s_top[j] = blend_over(0u, t, d.tint); s_got |= 1u << j; }
+                        if (a == 255u) { s_top[j] = blend_over(0u, t, d.tint); s_got |= 1u << j; s_stop |= (uint32_t)i << (8 * j); }
                         else if (a != 0u) s_trans |= 1u << j;
                     }
                 }
@@ -483,7 +484,10 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                 }
             }
         }
-        const bool need_bg = (s_got & ~s_trans) != full;  // some pixel still shows (or blends with) the background
+        // a pixel with an opaque sprite texel needs no background: whatever is translucent in front of that texel is
+        // blended over it below (when the list overflowed the repaint starts from the background instead)
+        const unsigned s_base = sprite_f2b ? s_got : (s_got & ~s_trans);
+        const bool need_bg = s_base != full;
         if (!need_bg) done = true;
 
         if (done) {
@@ -600,11 +604,13 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
             }
         }
 
-        // ---------- combine: opaque sprite texels win; pixels that met a translucent texel (and every pixel
-        //            when the list overflowed or the painter is forced) are repainted far -> near
+        // ---------- combine: opaque sprite texels win; a pixel that met translucent texels gets them blended far ->
+        //            near over its nearest opaque layer (sprite texel or background) — the layers behind an opaque
+        //            texel cannot show, so this is the painter's result.  When the list overflowed or the painter is
+        //            forced, every sprite is blended over the background.
 #pragma unroll
         for (int j = 0; j < 4; j++)
-            if (((s_got & ~s_trans) >> j) & 1u) px[j] = s_top[j];
+            if ((s_base >> j) & 1u) px[j] = s_top[j];
         const unsigned repaint = p.force_painter ? (n_list > 0 ? full : 0u) : s_trans;
         if (repaint) {
             if (!overflow) {
@@ -616,12 +622,22 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                         m &= m - 1u;
                         const Rect16 rc = wl.rect[i];
                         if (y < rc.y0 || y >= rc.y1) continue;
-                        const DrawRec &d = draw[wl.id[i]];
+                        unsigned todo = 0u;  // pixels being repainted whose opaque base lies behind sprite i
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            if (!((repaint >> j) & 1u)) continue;
-                            px[j] = blend_over(px[j], sprite_texel(d, p.sheet_pixels, x0 + j, y, zb[j]), d.tint);
+                        for (int j = 0; j < 4; j++)
+                            if (((repaint >> j) & 1u) && (!((s_base >> j) & 1u) || i > (int)((s_stop >> (8 * j)) & 255u))) todo |= 1u << j;
+                        if (!todo) continue;
+                        const DrawRec &d = draw[wl.id[i]];
+                        uint32_t t[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {  // the four texels are fetched together
+                            const uint64_t a = ((todo >> j) & 1u) ? sprite_index(d, x0 + j, y, zb[j]) : NO_TEXEL;
+                            t[j] = a != NO_TEXEL ? __ldg(p.sheet_pixels + a) : 0u;
                         }
+                        const uint32_t tint = d.tint;
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            if ((todo >> j) & 1u) px[j] = blend_over(px[j], t[j], tint);
                     }
                 }
             } else {

@@ -25,6 +25,7 @@
 // PM3D_OPT_FORCE_PAINTER forces the literal loop everywhere; tests require identical bytes.
 // The warp that owns the screen-centre pixel also picks the convergence sprite
 // (Camera.GetConvergenceSprite, game/scene_game.go:164).
+#include <stddef.h>
 #include <stdlib.h>
 
 #include "pm3d_internal.cuh"
@@ -32,8 +33,13 @@
 // rows per warp (WARP_ROWS, a template parameter: 2, 4 or 8 = 1, 2 or 4 iterations of 2 rows) trades the
 // per-warp prologue against the length of the serial chain: single frames want many short warps, large
 // batches of views want few long ones.
-#define MAX_WARP_SPRITES 256
-#define WARP_WORDS (MAX_WARP_SPRITES / 32)
+// Warp-private sprite list.  Throughput mode (many rows per warp, large batches): up to 256 entries, the draw records
+// stay in global memory.  Latency mode (single frames with sprites): up to LATENCY_LIST entries whose record prefix (everything
+// sprite_index reads: the first 80 bytes of a DrawRec) is copied to shared memory while the list is built, so the
+// lanes' front-to-back walks — chains of dependent loads on the rows where sprites pile up, the slowest warps of the
+// launch — read their records with an LDS instead of an L2 round trip.
+#define DRAW_PREFIX_VEC 5
+static_assert(offsetof(DrawRec, ty_hi) + 2 <= DRAW_PREFIX_VEC * 16, "sprite_index fields must sit in the copied prefix");
 
 struct ComposeParams {
     const pm3d_view *views;
@@ -69,9 +75,11 @@ __device__ __forceinline__ Rect16 make_rect16(int4 r) {
     o.y0 = (short)max(-32768, min(32767, r.z)); o.y1 = (short)max(-32768, min(32767, r.w));
     return o;
 }
+template <int MAXN, bool RECS>
 struct WarpList {
-    Rect16 rect[MAX_WARP_SPRITES];  // dsx, dex, dsy, dey, paint order
-    uint16_t id[MAX_WARP_SPRITES];
+    uint4 rec[RECS ? MAXN : 1][DRAW_PREFIX_VEC];
+    Rect16 rect[MAXN];  // dsx, dex, dsy, dey, paint order
+    uint16_t id[MAXN];
 };
 
 // ---- one sprite layer at pixel (x, y); returns texel (premultiplied) or 0 when it does not cover
@@ -212,10 +220,17 @@ __device__ __forceinline__ void load4(const int2 *base, size_t i, bool vec, int 
 
 // COMPOSE_WARPS warps per CTA: 4 for single frames, 2 for large batches (a CTA's slot is held until its slowest warp
 // ends, and small CTAs waste fewer warp slots); MIN_BLOCKS is given for 4-warp CTAs and scaled.
-template <int WARP_ROWS, int MIN_BLOCKS, int COMPOSE_WARPS>
+// LATENCY: single frames with sprites (see the sprite list above)
+#ifndef LATENCY_LIST
+#define LATENCY_LIST 96
+#endif
+template <int WARP_ROWS, int MIN_BLOCKS, int COMPOSE_WARPS, bool LATENCY = false>
 __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_WARPS) k_compose(const __grid_constant__ ComposeParams p) {
     constexpr int COMPOSE_ROWS = COMPOSE_WARPS * WARP_ROWS;
-    __shared__ WarpList s_list[COMPOSE_WARPS];
+    constexpr int MAX_WARP_SPRITES = LATENCY ? LATENCY_LIST : 256;
+    static_assert(MAX_WARP_SPRITES % 32 == 0, "the per-lane masks are whole 32-bit words");
+    constexpr int WARP_WORDS = MAX_WARP_SPRITES / 32;
+    __shared__ WarpList<MAX_WARP_SPRITES, LATENCY> s_list[COMPOSE_WARPS];
     __shared__ uint32_t s_xm[COMPOSE_WARPS][WARP_WORDS][32];  // per-lane sprite masks (kept out of registers and out of unrolled code)
 
     const int group = blockIdx.x, view = blockIdx.z;
@@ -241,7 +256,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
     const double posx = c.pos_x, posy = c.pos_y;
     const uint32_t box_tint = (uint32_t)c.max_light[0] | ((uint32_t)c.max_light[1] << 8) |
                               ((uint32_t)c.max_light[2] << 16) | 0xff000000u;
-    WarpList &wl = s_list[warp];
+    WarpList<MAX_WARP_SPRITES, LATENCY> &wl = s_list[warp];
 
     // ---- group aggregates written by the cast: rows >= fs_max are floor candidates in every column,
     //      rows < sky_below are above every wall slice and every floor start
@@ -281,12 +296,24 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
             }
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             const int pos = n_list + __popc(m & ((1u << lane) - 1u));
-            if (keep && pos < MAX_WARP_SPRITES) { wl.id[pos] = id; wl.rect[pos] = make_rect16(rc); }
+            if (keep && pos < MAX_WARP_SPRITES) {
+                wl.id[pos] = id; wl.rect[pos] = make_rect16(rc);
+                if (LATENCY) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(draw + id);
+#pragma unroll
+                    for (int q = 0; q < DRAW_PREFIX_VEC; q++) wl.rec[pos][q] = __ldg(src + q);
+                }
+            }
             n_list += __popc(m);
         }
         if (n_list > MAX_WARP_SPRITES) { overflow = true; n_list = MAX_WARP_SPRITES; }
         __syncwarp();
     }
+
+    // draw record of list entry i as far as sprite_index / tint need it
+    auto list_rec = [&](int i) -> const DrawRec & {
+        return LATENCY ? *reinterpret_cast<const DrawRec *>(&wl.rec[i][0]) : draw[wl.id[i]];
+    };
 
     // ---- convergence (one warp per view): wall hit of the centre ray, overridden by the nearest
     //      focusable sprite covering the centre pixel in front of that wall; ties -> lower list index
@@ -394,7 +421,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
         uint32_t s_top[4] = {0u, 0u, 0u, 0u};
         uint32_t s_stop = 0u;   // list index (one byte per pixel) of the sprite whose opaque texel is in s_top
         const bool sprite_f2b = n_list > 0 && !overflow && !p.force_painter;
-        if (sprite_f2b && WARP_ROWS < 8) {
+        if (sprite_f2b && LATENCY) {
             // Latency mode (few rows per warp, single frames).  SPRITE_BATCH sprites per step: a lane's walk is a chain of
             // dependent loads (record -> texel), so the records and texels of the next few candidates are fetched
             // together and then resolved nearest first.
@@ -421,7 +448,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                 if (ids[0] < 0) break;
                 const DrawRec *dr[SPRITE_BATCH];
 #pragma unroll
-                for (int b = 0; b < SPRITE_BATCH; b++) dr[b] = draw + wl.id[ids[b] < 0 ? ids[0] : ids[b]];
+                for (int b = 0; b < SPRITE_BATCH; b++) dr[b] = &list_rec(ids[b] < 0 ? ids[0] : ids[b]);
                 uint32_t tx[SPRITE_BATCH][4];
 #pragma unroll
                 for (int b = 0; b < SPRITE_BATCH; b++) {
@@ -445,7 +472,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                 }
             }
         }
-        if (sprite_f2b && WARP_ROWS >= 8) {
+        if (sprite_f2b && !LATENCY) {
             // throughput mode (large batches of views): one sprite at a time, no speculative fetches
 #pragma unroll 1
             for (int wd = n_words - 1; wd >= 0; wd--) {
@@ -456,7 +483,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                     const int i = wd * 32 + bit;
                     const Rect16 rc = wl.rect[i];
                     if (y < rc.y0 || y >= rc.y1) continue;
-                    const DrawRec &d = draw[wl.id[i]];
+                    const DrawRec &d = list_rec(i);
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         if (j >= nvalid || ((s_got >> j) & 1u)) continue;
@@ -627,7 +654,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                         for (int j = 0; j < 4; j++)
                             if (((repaint >> j) & 1u) && (!((s_base >> j) & 1u) || i > (int)((s_stop >> (8 * j)) & 255u))) todo |= 1u << j;
                         if (!todo) continue;
-                        const DrawRec &d = draw[wl.id[i]];
+                        const DrawRec &d = list_rec(i);
                         uint32_t t[4];
 #pragma unroll
                         for (int j = 0; j < 4; j++) {  // the four texels are fetched together
@@ -717,14 +744,17 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     if (const char *e = getenv("PM3D_COMPOSE_ROWS")) rows = atoi(e);      // tuning overrides (tools/)
     if (const char *e = getenv("PM3D_COMPOSE_MINB")) minb = atoi(e);
     const int cta_warps = rows >= 8 ? 2 : 4;
+    const bool with_sprites = ctx->cur_n_sprites > 0;  // latency-mode sprite walk (records in shared memory)
     dim3 block(cta_warps * 32), grid(ctx->n_groups, (ctx->h + cta_warps * rows - 1) / (cta_warps * rows), n_views);
     pm3d_kt_mark(ctx, 2, 0, ctx->stream);
     if (rows == 16) k_compose<16, 8, 2><<<grid, block, 0, ctx->stream>>>(p);
     else if (rows == 8 && minb == 8) k_compose<8, 8, 2><<<grid, block, 0, ctx->stream>>>(p);
     else if (rows == 8) k_compose<8, 6, 2><<<grid, block, 0, ctx->stream>>>(p);
     else if (rows == 4 && minb == 8) k_compose<4, 8, 4><<<grid, block, 0, ctx->stream>>>(p);
+    else if (rows == 4 && with_sprites) k_compose<4, 6, 4, true><<<grid, block, 0, ctx->stream>>>(p);
     else if (rows == 4) k_compose<4, 6, 4><<<grid, block, 0, ctx->stream>>>(p);
     else if (minb == 8) k_compose<2, 8, 4><<<grid, block, 0, ctx->stream>>>(p);
+    else if (with_sprites) k_compose<2, 6, 4, true><<<grid, block, 0, ctx->stream>>>(p);
     else k_compose<2, 6, 4><<<grid, block, 0, ctx->stream>>>(p);
     pm3d_kt_mark(ctx, 2, 1, ctx->stream);
     ctx->launches++;

@@ -79,6 +79,7 @@ void pm3d_destroy(pm3d_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->front_stream) cudaStreamSynchronize(ctx->front_stream);
+    if (ctx->front_stream_lo) cudaStreamSynchronize(ctx->front_stream_lo);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     void *ptrs[] = {ctx->grid, ctx->dist, ctx->wall_lut, ctx->atlas, ctx->floor_tiles, ctx->sheet_pixels, ctx->sheet_info,
                     ctx->views, ctx->sprites, ctx->sprite_offset, ctx->frame, ctx->checksums, ctx->segs, ctx->seg_irect,
@@ -95,6 +96,7 @@ void pm3d_destroy(pm3d_ctx *ctx) {
         if (fs.ev_compose) cudaEventDestroy(fs.ev_compose);
     }
     if (ctx->front_stream) cudaStreamDestroy(ctx->front_stream);
+    if (ctx->front_stream_lo) cudaStreamDestroy(ctx->front_stream_lo);
     for (int i = 0; i < 16; i++) {
         if (ctx->ev_start[i]) cudaEventDestroy(ctx->ev_start[i]);
         if (ctx->ev_stop[i]) cudaEventDestroy(ctx->ev_stop[i]);
@@ -114,6 +116,7 @@ void pm3d_destroy(pm3d_ctx *ctx) {
 int pm3d_sync(pm3d_ctx *ctx) {
     if (!ctx) return PM3D_ERR_ARG;
     if (ctx->front_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->front_stream));
+    if (ctx->front_stream_lo) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->front_stream_lo));
     PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->copy_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     return PM3D_OK;
@@ -295,6 +298,7 @@ int pm3d_set_option(pm3d_ctx *ctx, int option, int value) {
     case PM3D_OPT_OVERLAP:
         PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
         if (ctx->front_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->front_stream));
+    if (ctx->front_stream_lo) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->front_stream_lo));
         PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->n_sets = value ? 2 : 1;
         ctx->cur_set = 0;
@@ -334,6 +338,7 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
     if (ctx->num_levels < 1) return pm3d_fail(ctx, PM3D_ERR_ARG, "pm3d_upload_grid must precede pm3d_set_view");
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
     if (ctx->front_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->front_stream));
+    if (ctx->front_stream_lo) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->front_stream_lo));
     PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->copy_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     ctx->w = width; ctx->h = height; ctx->max_views = max_views; ctx->max_sprites = max_sprites_total;
@@ -343,7 +348,14 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
     if ((rc = dev_realloc(ctx, &ctx->views, V))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->sprites, S))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->sprite_offset, V + 1))) return rc;
-    if (!ctx->front_stream) PM3D_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->front_stream, cudaStreamNonBlocking));
+    if (!ctx->front_stream) {
+        // highest priority: the front launch is a handful of long-running CTAs; they must get SM slots as soon as any
+        // free up instead of queueing behind the thousands of CTAs of the compose launch they overlap with
+        int prio_lo = 0, prio_hi = 0;
+        PM3D_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        PM3D_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->front_stream, cudaStreamNonBlocking, prio_hi));
+        PM3D_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->front_stream_lo, cudaStreamNonBlocking));
+    }
     for (int k = 0; k < 2; k++) {
         pm3d_ctx::FrameSet &fs = ctx->sets[k];
         pm3d_load_set(ctx, k);
@@ -403,7 +415,8 @@ static int render_core(pm3d_ctx *ctx, int n_views, int n_sprites, uint8_t *targe
     int rc;
     pm3d_ctx::FrameSet &fs = ctx->sets[ctx->cur_set];
     const bool overlap = ctx->n_sets > 1;
-    cudaStream_t fstream = overlap ? ctx->front_stream : ctx->stream;
+    cudaStream_t fstream = overlap ? ctx->cur_fstream : ctx->stream;
+    ctx->cur_n_sprites = n_sprites;
     if ((rc = pm3d_launch_front(ctx, n_views, fstream))) return rc;
     if (overlap) {
         PM3D_CUDA(ctx, cudaEventRecord(fs.ev_front, fstream));
@@ -421,12 +434,15 @@ static int render_core(pm3d_ctx *ctx, int n_views, int n_sprites, uint8_t *targe
 // Select the frame set of the next frame: the named per-frame fields alias it from here on.  Its previous
 // user (the compose kernel two frames back) must be done before the front stream writes into it, and
 // everything enqueued on the main stream so far (uploads, caller-visible ordering) precedes the frame.
-static int pm3d_begin_frame(pm3d_ctx *ctx, cudaStream_t *fstream) {
+static int pm3d_begin_frame(pm3d_ctx *ctx, int n_views, cudaStream_t *fstream) {
     if (ctx->n_sets > 1) {
         ctx->cur_set = (ctx->cur_set + 1) % ctx->n_sets;
         pm3d_load_set(ctx, ctx->cur_set);
-        PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->front_stream, ctx->sets[ctx->cur_set].ev_compose, 0));
-        *fstream = ctx->front_stream;
+        // a batch whose front launch fills the chip by itself gains nothing from jumping the queue
+        const long long front_ctas = (long long)n_views * ctx->num_levels * ctx->n_groups / 4;
+        ctx->cur_fstream = front_ctas >= 4LL * ctx->sm_count ? ctx->front_stream_lo : ctx->front_stream;
+        PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->cur_fstream, ctx->sets[ctx->cur_set].ev_compose, 0));
+        *fstream = ctx->cur_fstream;
     } else {
         *fstream = ctx->stream;
     }
@@ -457,7 +473,7 @@ int pm3d_render_resident(pm3d_ctx *ctx, const pm3d_view *d_views, int n_views, c
     if (n_sprites_total > ctx->max_sprites) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "%d sprites > max_sprites_total %d", n_sprites_total, ctx->max_sprites);
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t fstream;
-    if ((rc = pm3d_begin_frame(ctx, &fstream))) return rc;
+    if ((rc = pm3d_begin_frame(ctx, n_views, &fstream))) return rc;
     ctx->cur_views = d_views; ctx->cur_sprites = d_sprites; ctx->cur_offset = d_sprite_offset;
     return render_core(ctx, n_views, n_sprites_total, d_out_rgba);
 }
@@ -534,7 +550,7 @@ int pm3d_render(pm3d_ctx *ctx, const pm3d_view *views, int n_views, const pm3d_s
                  sb = (size_t)n_sprites * sizeof(pm3d_sprite);
     const size_t ob_pad = (ob + 15) & ~(size_t)15;
     cudaStream_t fstream;
-    int rc = pm3d_begin_frame(ctx, &fstream);
+    int rc = pm3d_begin_frame(ctx, n_views, &fstream);
     if (rc) return rc;
     pm3d_ctx::FrameSet &fs = ctx->sets[ctx->cur_set];
     const size_t in_bytes = vb + ob_pad + sb;

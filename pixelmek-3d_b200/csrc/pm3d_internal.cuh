@@ -136,13 +136,16 @@ struct pm3d_ctx {
         cudaEvent_t ev_compose = nullptr;  // compose done and the set's results read: the set may be rewritten
     } sets[2];
     int n_sets = 2, cur_set = 0;
-    cudaStream_t front_stream = nullptr;
+    cudaStream_t front_stream = nullptr;     // highest priority: single frames (a handful of long-running front CTAs)
+    cudaStream_t front_stream_lo = nullptr;  // default priority: large batches (both launches fill the chip)
+    cudaStream_t cur_fstream = nullptr;      // the one the frame batch being enqueued uses
 
     // inputs the kernels read this call (ctx-owned copies, or caller device memory)
     const pm3d_view *cur_views = nullptr;
     const pm3d_sprite *cur_sprites = nullptr;
     const int32_t *cur_offset = nullptr;
     int last_sprites = 0;
+    int cur_n_sprites = 0;           // sprites of the frame batch being enqueued
 
     // per-kernel event timing (pm3d_ktimer_*)
     cudaEvent_t *kt_ev = nullptr;  // [kt_cap][3][2]

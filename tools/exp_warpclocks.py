@@ -20,10 +20,14 @@ for pose in (0, 3):
     dur, t0, meta, sm = buf[:, 0], buf[:, 1], buf[:, 2], buf[:, 3]
     nl = meta >> 32; row = meta & 0xffffffff
     ok = dur > 0
-    print(f"pose {pose}: warps {ok.sum()}  kernel span {(t0[ok] + dur[ok]).max() - t0[ok].min()} clk; warp dur mean {dur[ok].mean():.0f} p50 {np.percentile(dur[ok],50):.0f} p90 {np.percentile(dur[ok],90):.0f} p99 {np.percentile(dur[ok],99):.0f} max {dur[ok].max()}")
+    print(f"pose {pose}: warps {ok.sum()}  warp dur mean {dur[ok].mean():.0f} p50 {np.percentile(dur[ok],50):.0f} p90 {np.percentile(dur[ok],90):.0f} p99 {np.percentile(dur[ok],99):.0f} max {dur[ok].max()}")
     # by row band
     for lo in range(0, 1080, 120):
         m = ok & (row >= lo) & (row < lo + 120)
         if m.sum(): print(f"   rows {lo:4d}-{lo+119:4d}: mean {dur[m].mean():7.0f} max {dur[m].max():7d}  n_list mean {nl[m].mean():5.1f} max {nl[m].max():3d}")
     top = np.argsort(-dur)[:8]
-    print("   slowest:", [(int(row[i]), int(nl[i]), int(dur[i])) for i in top])
+    M = (1 << 20) - 1
+    print("   slowest (row, n_list, total | prologue, f2b, bg, repaint clk):")
+    for i in top: print("     ", int(row[i]), int(nl[i]), int(dur[i]), "|", int(t0[i] & M), int((t0[i] >> 20) & M), int((t0[i] >> 40) & M), int((sm[i] >> 44) & M))
+    med = np.argsort(dur)[len(dur)//2]
+    print("   median warp:", int(row[med]), int(nl[med]), int(dur[med]), "|", int(t0[med] & M), int((t0[med] >> 20) & M), int((t0[med] >> 40) & M), int((sm[med] >> 44) & M))

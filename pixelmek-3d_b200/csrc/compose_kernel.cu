@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
         }
         // a pixel with an opaque sprite texel needs no background: whatever is translucent in front of that texel is
         // blended over it below (when the list overflowed the repaint starts from the background instead)
-        const unsigned s_base = sprite_f2b ? s_got : (s_got & ~s_trans);
+        const unsigned s_base = (sprite_f2b && LATENCY) ? s_got : (s_got & ~s_trans);
         const bool need_bg = s_base != full;
         if (!need_bg) done = true;
 
@@ -649,22 +649,32 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                         m &= m - 1u;
                         const Rect16 rc = wl.rect[i];
                         if (y < rc.y0 || y >= rc.y1) continue;
-                        unsigned todo = 0u;  // pixels being repainted whose opaque base lies behind sprite i
+                        if (LATENCY) {
+                            unsigned todo = 0u;  // pixels being repainted whose opaque base lies behind sprite i
 #pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            if (((repaint >> j) & 1u) && (!((s_base >> j) & 1u) || i > (int)((s_stop >> (8 * j)) & 255u))) todo |= 1u << j;
-                        if (!todo) continue;
-                        const DrawRec &d = list_rec(i);
-                        uint32_t t[4];
+                            for (int j = 0; j < 4; j++)
+                                if (((repaint >> j) & 1u) && (!((s_base >> j) & 1u) || i > (int)((s_stop >> (8 * j)) & 255u))) todo |= 1u << j;
+                            if (!todo) continue;
+                            const DrawRec &d = list_rec(i);
+                            uint32_t t[4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {  // the four texels are fetched together
-                            const uint64_t a = ((todo >> j) & 1u) ? sprite_index(d, x0 + j, y, zb[j]) : NO_TEXEL;
-                            t[j] = a != NO_TEXEL ? __ldg(p.sheet_pixels + a) : 0u;
+                            for (int j = 0; j < 4; j++) {  // the four texels are fetched together
+                                const uint64_t a = ((todo >> j) & 1u) ? sprite_index(d, x0 + j, y, zb[j]) : NO_TEXEL;
+                                t[j] = a != NO_TEXEL ? __ldg(p.sheet_pixels + a) : 0u;
+                            }
+                            const uint32_t tint = d.tint;
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                if ((todo >> j) & 1u) px[j] = blend_over(px[j], t[j], tint);
+                        } else {
+                            // throughput mode: every sprite over the background, small code
+                            const DrawRec &d = list_rec(i);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                if (!((repaint >> j) & 1u)) continue;
+                                px[j] = blend_over(px[j], sprite_texel(d, p.sheet_pixels, x0 + j, y, zb[j]), d.tint);
+                            }
                         }
-                        const uint32_t tint = d.tint;
-#pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            if ((todo >> j) & 1u) px[j] = blend_over(px[j], t[j], tint);
                     }
                 }
             } else {

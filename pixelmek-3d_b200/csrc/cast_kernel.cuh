@@ -105,6 +105,7 @@ __device__ __forceinline__ void cast_ray(const CastParams &p, const int view, co
         mapY = mapY < 0 ? 0 : (mapY > p.map_h - 1 ? p.map_h - 1 : mapY);
     }
     int agg_ya = 0x7fffffff, agg_fs_min = 0x7fffffff, agg_fs_max = 0;
+    float agg_zmax = -INFINITY;  // level 0: upper bound of the z-buffer over the warp's columns (sprite culling)
     if (hit != 3) {  // (skipped rays hold the defaults: nothing drawn)
     int mx = (int)mapX, my = (int)mapY;
     const uint8_t *__restrict__ dist = p.dist + (size_t)sl * p.map_w * p.map_h;
@@ -222,6 +223,7 @@ __device__ __forceinline__ void cast_ray(const CastParams &p, const int view, co
             p.flo_dx[fi] = X1 - PX;
             p.flo_dy[fi] = Y1 - PY;
             agg_fs_min = fs; agg_fs_max = fs;
+            agg_zmax = __double2float_ru(perpWallDist);  // NaN stays NaN and is ignored by fmaxf below
         }
     }
     }
@@ -230,10 +232,11 @@ __device__ __forceinline__ void cast_ray(const CastParams &p, const int view, co
         agg_ya = min(agg_ya, __shfl_xor_sync(0xffffffffu, agg_ya, o));
         agg_fs_min = min(agg_fs_min, __shfl_xor_sync(0xffffffffu, agg_fs_min, o));
         agg_fs_max = max(agg_fs_max, __shfl_xor_sync(0xffffffffu, agg_fs_max, o));
+        agg_zmax = fmaxf(agg_zmax, __shfl_xor_sync(0xffffffffu, agg_zmax, o));
     }
     if ((threadIdx.x & 31) == 0) {
         const int half = (threadIdx.x >> 5) & 1;
         p.agg[(((size_t)view * p.num_levels + level) * p.n_groups + group) * 2 + half] =
-            make_int4(agg_ya, agg_fs_min, agg_fs_max, 0);
+            make_int4(agg_ya, agg_fs_min, agg_fs_max, __float_as_int(agg_zmax));
     }
 }

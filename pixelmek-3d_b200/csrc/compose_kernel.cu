@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
     // ---- group aggregates written by the cast: rows >= fs_max are floor candidates in every column,
     //      rows < sky_below are above every wall slice and every floor start
     int fs_max = 0, sky_below = 0x7fffffff;
+    double zmax_group = INFINITY;  // no column of the group has a z-buffer value above this
     {
         // every lane reads the same 2*L records (one broadcast transaction each): cheaper than a strided read
         // followed by ten shuffles
@@ -270,6 +271,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
             const int4 a0 = __ldg(ag + (size_t)l * p.n_groups * 2), a1 = __ldg(ag + (size_t)l * p.n_groups * 2 + 1);
             fs_max = max(fs_max, max(a0.z, a1.z));
             sky_below = min(sky_below, min(min(a0.x, a0.y), min(a1.x, a1.y)));
+            if (l == 0) zmax_group = (double)fmaxf(__int_as_float(a0.w), __int_as_float(a1.w));
         }
     }
 
@@ -293,6 +295,9 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                 id = glist[i];
                 rc = grect[i];  // dsx, dex, dsy, dey
                 keep = rc.w > wrow0 && rc.z < wrow1;
+                // z-cull: a sprite at or behind the farthest wall hit of the group's columns fails `transformY < zBuffer[x]`
+                // in every one of them (camera facing a wall: whole stacks of sprites behind it drop out here)
+                if (keep) keep = __ldg(&draw[id].transformY) < zmax_group;
             }
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             const int pos = n_list + __popc(m & ((1u << lane) - 1u));

@@ -23,7 +23,8 @@
 //   flo_dx, flo_dy          double  RN(floorXWall*texSize - posX*texSize), same for Y (fast floor cast)
 //   flo_fs                  int     first floor row (drawEnd + 1, or h when none)
 // plus one aggregate per (view, level, 64-column group, 32-column half):
-//   agg  int4  x: min ya over drawn slices (INT_MAX if none); y: min fs; z: max fs (level 0 only)
+//   agg  int4  x: min ya over drawn slices (INT_MAX if none); y: min fs; z: max fs (level 0 only);
+//              w: float bits, upper bound of the z-buffer over the 32 columns (level 0 only, -inf if every z is NaN)
 #define GROUP_COLS 64
 
 // Per (view, screen row) values shared by every column.  16 B.

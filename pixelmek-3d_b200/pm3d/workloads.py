@@ -256,10 +256,23 @@ def frustum_sprites(scene: SceneData, pose, n: int, seed: int, max_dist: float =
     rng = SplitMix64(seed)
     x, y, _, heading, _ = pose
     mw, mh = scene.map_size
-    r = 1.0 + (max_dist - 1.0) * np.sqrt(rng.uniform(n))
-    a = heading + (rng.uniform(n) - 0.5) * math.radians(fov_deg)
-    sx = np.clip(x + r * np.cos(a), 1.01, mw - 1.01)
-    sy = np.clip(y + r * np.sin(a), 1.01, mh - 1.01)
+    # uniform over (frustum within max_dist) ∩ map: candidates outside the map are rejected, not clamped onto its edge
+    # (clamping piles hundreds of billboards onto one screen line whenever the camera faces a nearby map border)
+    m = 16 * n
+    sx, sy = np.zeros(0), np.zeros(0)
+    for _ in range(32):
+        r = 1.0 + (max_dist - 1.0) * np.sqrt(rng.uniform(m))
+        a = heading + (rng.uniform(m) - 0.5) * math.radians(fov_deg)
+        cx, cy = x + r * np.cos(a), y + r * np.sin(a)
+        ok = (cx >= 1.01) & (cx <= mw - 1.01) & (cy >= 1.01) & (cy <= mh - 1.01)
+        sx, sy = np.concatenate([sx, cx[ok]]), np.concatenate([sy, cy[ok]])
+        if len(sx) >= n:
+            break
+    if len(sx) < n:  # the frustum barely touches the map: the rest goes anywhere within max_dist (mostly off screen)
+        k = n - len(sx)
+        sx = np.concatenate([sx, np.clip(x + (rng.uniform(k) * 2 - 1) * max_dist, 1.01, mw - 1.01)])
+        sy = np.concatenate([sy, np.clip(y + (rng.uniform(k) * 2 - 1) * max_dist, 1.01, mh - 1.01)])
+    sx, sy = sx[:n], sy[:n]
     scale = 0.3 + 0.7 * rng.uniform(n)
     sheet = (np.floor(rng.uniform(n) * 3)).astype(np.int32)
     xyzs = np.stack([sx, sy, np.zeros(n), scale], axis=1)

@@ -36,6 +36,23 @@ def test_struct_sizes_match_the_header(ensure_built):
     assert pm3d._lib.SPRITE_DTYPE.itemsize == 64
     assert pm3d._lib.COLUMN_DTYPE.itemsize == 56
     assert pm3d._lib.CONV_DTYPE.itemsize == 32
+    assert pm3d._lib.MOVER_DTYPE.itemsize == 80
+    assert pm3d._lib.COLLIDER_DTYPE.itemsize == 48
+    assert pm3d._lib.MOVE_RESULT_DTYPE.itemsize == 80
+    # ... and the header says the same (the sizes are written next to each struct) and C agrees
+    with open(os.path.join(ROOT, "include", "pm3d.h")) as f:
+        header = f.read()
+    for name, size in (("pm3d_view", 104), ("pm3d_sprite", 64), ("pm3d_column", 56), ("pm3d_mover", 80), ("pm3d_collider", 48),
+                       ("pm3d_move_result", 80)):
+        assert re.search(r"\}\s*%s;\s*/\*\s*%d bytes" % (name, size), header), name
+    import subprocess, tempfile
+    src = '#include "pm3d.h"\n#include <stdio.h>\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pm3d_view), sizeof(pm3d_sprite), sizeof(pm3d_column), sizeof(pm3d_convergence), sizeof(pm3d_mover), sizeof(pm3d_collider), sizeof(pm3d_move_result), sizeof(pm3d_rect));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        with open(os.path.join(d, "s.c"), "w") as f:
+            f.write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "s"), os.path.join(d, "s.c")])
+        out = subprocess.check_output([os.path.join(d, "s")]).decode().split()
+    assert [int(x) for x in out] == [104, 64, 56, 32, 80, 48, 80, 16]
 
 
 def test_no_cpu_fallback(ensure_built):

@@ -149,7 +149,10 @@ __device__ bool any_hit(const LosParams &p, const double4 &ray) {
 #ifndef LOS_LANE_CAP
 #define LOS_LANE_CAP 8
 #endif
-__global__ void __launch_bounds__(LOS_THREADS, 3) k_los(LosParams p, long long rays_per_warp) {
+#ifndef LOS_MIN_BLOCKS
+#define LOS_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(LOS_THREADS, LOS_MIN_BLOCKS) k_los(LosParams p, long long rays_per_warp) {
     const int lane = threadIdx.x & 31;
     const long long warp_id = (long long)blockIdx.x * (LOS_THREADS / 32) + (threadIdx.x >> 5);
     long long next = warp_id * rays_per_warp;                      // warp-uniform: next unassigned ray

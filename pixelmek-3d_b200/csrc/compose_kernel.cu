@@ -283,25 +283,45 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
     const int4 *grect = p.bin_rect + (size_t)s0 * p.n_groups + (size_t)group * nv;
     const int4 ginfo = p.bin_count[view * p.n_groups + group];  // entries, min dsy, max dey
     const int gcnt = ginfo.x;
-    int n_list = 0;
+    // The list keeps the NEAREST MAX_WARP_SPRITES entries (the group list is in paint order, far -> near).  When more
+    // qualify, the farther ones stay behind in the group list as entries [0, far_cut): the front-to-back walk only
+    // reaches them for a pixel that sees through every listed sprite, and the repaint takes them first.
+    int n_list = 0, far_cut = 0;
     bool overflow = false;
     if (gcnt > 0 && ginfo.z > wrow0 && ginfo.y < wrow1) {
+        auto qualifies = [&](int i, uint16_t &id, int4 &rc) -> bool {
+            if (i >= gcnt) return false;
+            id = glist[i];
+            rc = grect[i];  // dsx, dex, dsy, dey
+            // rows of this warp, and z-cull: a sprite at or behind the farthest wall hit of the group's columns fails
+            // `transformY < zBuffer[x]` in every one of them (camera facing a wall: whole stacks of sprites behind it
+            // drop out here)
+            return rc.w > wrow0 && rc.z < wrow1 && __ldg(&draw[id].transformY) < zmax_group;
+        };
+        int skip = 0;
+        if (gcnt > MAX_WARP_SPRITES) {  // only then can the list overflow: count first
+            int n_total = 0;
+            for (int base = 0; base < gcnt; base += 32) {
+                uint16_t id; int4 rc;
+                n_total += __popc(__ballot_sync(0xffffffffu, qualifies(base + lane, id, rc)));
+            }
+            skip = max(0, n_total - MAX_WARP_SPRITES);
+            overflow = skip > 0;
+        }
+        int rank = 0;
         for (int base = 0; base < gcnt; base += 32) {
             const int i = base + lane;
-            bool keep = false;
             uint16_t id = 0;
             int4 rc = make_int4(0, 0, 0, 0);
-            if (i < gcnt) {
-                id = glist[i];
-                rc = grect[i];  // dsx, dex, dsy, dey
-                keep = rc.w > wrow0 && rc.z < wrow1;
-                // z-cull: a sprite at or behind the farthest wall hit of the group's columns fails `transformY < zBuffer[x]`
-                // in every one of them (camera facing a wall: whole stacks of sprites behind it drop out here)
-                if (keep) keep = __ldg(&draw[id].transformY) < zmax_group;
-            }
+            const bool keep = qualifies(i, id, rc);
             const unsigned m = __ballot_sync(0xffffffffu, keep);
-            const int pos = n_list + __popc(m & ((1u << lane) - 1u));
-            if (keep && pos < MAX_WARP_SPRITES) {
+            const int r = rank + __popc(m & ((1u << lane) - 1u));
+            if (overflow) {
+                const unsigned first = __ballot_sync(0xffffffffu, keep && r == skip);
+                if (first) far_cut = __shfl_sync(0xffffffffu, i, __ffs(first) - 1);
+            }
+            if (keep && r >= skip) {
+                const int pos = r - skip;
                 wl.id[pos] = id; wl.rect[pos] = make_rect16(rc);
                 if (LATENCY) {
                     const uint4 *src = reinterpret_cast<const uint4 *>(draw + id);
@@ -309,9 +329,9 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                     for (int q = 0; q < DRAW_PREFIX_VEC; q++) wl.rec[pos][q] = __ldg(src + q);
                 }
             }
-            n_list += __popc(m);
+            rank += __popc(m);
         }
-        if (n_list > MAX_WARP_SPRITES) { overflow = true; n_list = MAX_WARP_SPRITES; }
+        n_list = rank - skip;
         __syncwarp();
     }
 
@@ -425,7 +445,8 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
         unsigned s_trans = 0u;  // pixels that met a translucent sprite texel in front of it
         uint32_t s_top[4] = {0u, 0u, 0u, 0u};
         uint32_t s_stop = 0u;   // list index (one byte per pixel) of the sprite whose opaque texel is in s_top
-        const bool sprite_f2b = n_list > 0 && !overflow && !p.force_painter;
+        const bool sprite_f2b = n_list > 0 && !p.force_painter;
+        unsigned s_far = 0u;    // pixels whose opaque texel was found among the far entries (not in the list)
         if (sprite_f2b && LATENCY) {
             // Latency mode (few rows per warp, single frames).  SPRITE_BATCH sprites per step: a lane's walk is a chain of
             // dependent loads (record -> texel), so the records and texels of the next few candidates are fetched
@@ -501,8 +522,8 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
             }
         }
         if (overflow && !p.force_painter) {
-            // more sprites than the warp list holds: walk the group list itself, nearest first
-            for (int i = gcnt - 1; i >= 0 && s_got != full; i--) {
+            // pixels that saw through every listed sprite go on with the far entries of the group list, nearest first
+            for (int i = far_cut - 1; i >= 0 && s_got != full; i--) {
                 const int4 rc = grect[i];
                 if (y < rc.z || y >= rc.w || x0 + 3 < rc.x || x0 >= rc.y) continue;
                 const DrawRec &d = draw[glist[i]];
@@ -511,14 +532,15 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                     if (j >= nvalid || ((s_got >> j) & 1u)) continue;
                     const uint32_t t = sprite_texel(d, p.sheet_pixels, x0 + j, y, zb[j]);
                     const uint32_t a = t >> 24;
-                    if (a == 255u) { s_top[j] = blend_over(0u, t, d.tint); s_got |= 1u << j; }
+                    if (a == 255u) { s_top[j] = blend_over(0u, t, d.tint); s_got |= 1u << j; s_far |= 1u << j; }
                     else if (a != 0u) s_trans |= 1u << j;
                 }
             }
         }
         // a pixel with an opaque sprite texel needs no background: whatever is translucent in front of that texel is
         // blended over it below (when the list overflowed the repaint starts from the background instead)
-        const unsigned s_base = (sprite_f2b && LATENCY) ? s_got : (s_got & ~s_trans);
+        // (a translucent pixel whose opaque texel is a far entry is repainted from the background like one without any)
+        const unsigned s_base = (sprite_f2b && LATENCY) ? (s_got & ~(s_far & s_trans)) : (s_got & ~s_trans);
         const bool need_bg = s_base != full;
         if (!need_bg) done = true;
 
@@ -645,53 +667,52 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
             if ((s_base >> j) & 1u) px[j] = s_top[j];
         const unsigned repaint = p.force_painter ? (n_list > 0 ? full : 0u) : s_trans;
         if (repaint) {
-            if (!overflow) {
-#pragma unroll 1
-                for (int wd = 0; wd < n_words; wd++) {
-                    uint32_t m = s_xm[warp][wd][lane];
-                    while (m) {
-                        const int i = wd * 32 + __ffs(m) - 1;
-                        m &= m - 1u;
-                        const Rect16 rc = wl.rect[i];
-                        if (y < rc.y0 || y >= rc.y1) continue;
-                        if (LATENCY) {
-                            unsigned todo = 0u;  // pixels being repainted whose opaque base lies behind sprite i
-#pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                if (((repaint >> j) & 1u) && (!((s_base >> j) & 1u) || i > (int)((s_stop >> (8 * j)) & 255u))) todo |= 1u << j;
-                            if (!todo) continue;
-                            const DrawRec &d = list_rec(i);
-                            uint32_t t[4];
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {  // the four texels are fetched together
-                                const uint64_t a = ((todo >> j) & 1u) ? sprite_index(d, x0 + j, y, zb[j]) : NO_TEXEL;
-                                t[j] = a != NO_TEXEL ? __ldg(p.sheet_pixels + a) : 0u;
-                            }
-                            const uint32_t tint = d.tint;
-#pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                if ((todo >> j) & 1u) px[j] = blend_over(px[j], t[j], tint);
-                        } else {
-                            // throughput mode: every sprite over the background, small code
-                            const DrawRec &d = list_rec(i);
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                if (!((repaint >> j) & 1u)) continue;
-                                px[j] = blend_over(px[j], sprite_texel(d, p.sheet_pixels, x0 + j, y, zb[j]), d.tint);
-                            }
-                        }
-                    }
-                }
-            } else {
-                // more sprites than the warp list holds: walk the whole group list
-                for (int i = 0; i < gcnt; i++) {
+            if (overflow) {
+                // the far entries first (paint order), for the pixels repainted from the background
+                for (int i = 0; i < far_cut; i++) {
                     const int4 rc = grect[i];
                     if (y < rc.z || y >= rc.w || x0 + 3 < rc.x || x0 >= rc.y) continue;
                     const DrawRec &d = draw[glist[i]];
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        if (!((repaint >> j) & 1u)) continue;
+                        if (!(((repaint & ~s_base) >> j) & 1u)) continue;
                         px[j] = blend_over(px[j], sprite_texel(d, p.sheet_pixels, x0 + j, y, zb[j]), d.tint);
+                    }
+                }
+            }
+#pragma unroll 1
+            for (int wd = 0; wd < n_words; wd++) {
+                uint32_t m = s_xm[warp][wd][lane];
+                while (m) {
+                    const int i = wd * 32 + __ffs(m) - 1;
+                    m &= m - 1u;
+                    const Rect16 rc = wl.rect[i];
+                    if (y < rc.y0 || y >= rc.y1) continue;
+                    if (LATENCY) {
+                        unsigned todo = 0u;  // pixels being repainted whose opaque base lies behind sprite i
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            if (((repaint >> j) & 1u) && (!((s_base >> j) & 1u) || i > (int)((s_stop >> (8 * j)) & 255u))) todo |= 1u << j;
+                        if (!todo) continue;
+                        const DrawRec &d = list_rec(i);
+                        uint32_t t[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {  // the four texels are fetched together
+                            const uint64_t a = ((todo >> j) & 1u) ? sprite_index(d, x0 + j, y, zb[j]) : NO_TEXEL;
+                            t[j] = a != NO_TEXEL ? __ldg(p.sheet_pixels + a) : 0u;
+                        }
+                        const uint32_t tint = d.tint;
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            if ((todo >> j) & 1u) px[j] = blend_over(px[j], t[j], tint);
+                    } else {
+                        // throughput mode: every sprite over the background, small code
+                        const DrawRec &d = list_rec(i);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if (!((repaint >> j) & 1u)) continue;
+                            px[j] = blend_over(px[j], sprite_texel(d, p.sheet_pixels, x0 + j, y, zb[j]), d.tint);
+                        }
                     }
                 }
             }

@@ -185,6 +185,33 @@ def test_many_overlapping_sprites_and_duplicates(gpu_ctx):
     check_all(gpu_ctx, got, want, off, n)
 
 
+@pytest.mark.parametrize("rows", [2, 4, 8, 16])
+def test_warp_list_overflow_in_both_sprite_modes(gpu_ctx, rows, monkeypatch):
+    """700 billboards stacked on one patch overflow the warp-private sprite list in latency mode (96 entries, 2/4 rows
+    per warp) and in throughput mode (256 entries, 8/16 rows per warp): the nearest entries are listed, the farther
+    ones are reached through the group list.  Pixels, rectangles and convergence must equal the oracle's, and the
+    literal painter loop must give the same bytes."""
+    scene = edge_scene()
+    w, h = 192, 108
+    rng = W.SplitMix64(77)
+    n = 700
+    u = rng.uniform(n * 3).reshape(n, 3)
+    xyzs = np.stack([7.0 + 3.0 * u[:, 0], 5.2 + 0.6 * u[:, 1], np.zeros(n), 0.3 + 0.5 * u[:, 2]], axis=1)
+    spr = W.sprite_records(xyzs, (u[:, 2] * 4).astype(np.int32), np.zeros(n, np.uint8), scene.sheets)
+    views = W.make_views(scene, w, h, [(5.5, 5.5, 0.5, 0.0, 0.0)], render_distance=-1.0)
+    off = np.array([0, n], dtype=np.int32)
+    monkeypatch.setenv("PM3D_COMPOSE_ROWS", str(rows))
+    got, want = render_both(gpu_ctx, scene, w, h, views, spr, off)
+    check_all(gpu_ctx, got, want, off, n)
+    fast = got["rgba"].copy()
+    gpu_ctx.set_option(pm3d._lib.OPT_FORCE_PAINTER, 1)
+    try:
+        slow = gpu_ctx.render(views, spr, off)["rgba"].copy()
+    finally:
+        gpu_ctx.set_option(pm3d._lib.OPT_FORCE_PAINTER, 0)
+    assert np.array_equal(fast, slow)
+
+
 def test_division_free_floor_weight_is_correctly_rounded(gpu_ctx):
     """The floor cast's weight = currentDist / distWall is evaluated as a Newton sequence on RN(1/distWall)
     (pm3d_internal.cuh div_by_rcp).  It must equal the IEEE quotient bit for bit: 2.1e9 operand pairs

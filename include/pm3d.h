@@ -260,6 +260,64 @@ int pm3d_valid_move_batch(pm3d_ctx *ctx, const pm3d_mover *movers, int64_t n, do
 int pm3d_generate_wall_collision_lines(const uint16_t *level0, int map_w, int map_h, int has_boundary_wall,
                                        double clip_distance, double *out_xyxy, int cap);
 
+/* ------------------------------------------------------------------ clutter (ground cover around a camera)
+ * ClutterHandler.Update (game/clutter.go:25-117; called per tick from game/scene_game.go:104-105 and once from
+ * game/mission.go:101-103): the cells a fan of sample rays in front of the camera lands on (clutter.go:45-52) get
+ * their rocks and shrubs from Go's math/rand seeded with Map.Seed + posId (clutter.go:75), so a cell's clutter is
+ * the same whenever it comes into view.  The batch call evaluates that for n cameras at once; the sprites it
+ * returns are what ClutterHandler.sprites holds after Update and what getRaycastSprites appends to the camera's
+ * sprite list (game/sprites.go:121-124).  The handler's spritesByPosition cache is an optimisation of the
+ * reference (a cell's sprites do not depend on the history) and stays a host-side detail. */
+
+/* One model.MapClutter entry (game/model/map.go:128-133) as the host resolves it. */
+typedef struct pm3d_clutter_def {
+    double frequency;           /* Frequency: chance of this clutter in a matching cell */
+    double scale;               /* Height / model.METERS_PER_UNIT (clutter.go:88)    */
+    int32_t sheet;              /* g.tex.TextureImage(Image) as a sprite-sheet id    */
+    int32_t rx0, ry0, rx1, ry1; /* GetSpriteSheetSlices(img, 1, 1): (0, 0, w-1, h-1) */
+    int32_t _pad;
+} pm3d_clutter_def;             /* 40 bytes */
+
+/* One camera.  The sample angles are those of clutter.go:44-45 (heading -+ fov/2 in fov/20 steps: 21, or 20 when
+ * the accumulated angle ends a rounding error past the limit); their cos/sin stay on the host like every
+ * transcendental of this ABI. */
+#define PM3D_CLUTTER_MAX_ANGLES 21
+typedef struct pm3d_clutter_query {
+    double cam_x, cam_y;        /* g.player.CameraPosition()                         */
+    int32_t n_angles, _pad;
+    double cs[PM3D_CLUTTER_MAX_ANGLES][2]; /* (cos a, sin a) per sample angle         */
+} pm3d_clutter_query;           /* 360 bytes */
+
+/* One clutter sprite: sprites.NewSprite(model.BasicVisualEntity(x, y, 0, AnchorBottom), scale, img)
+ * (clutter.go:89-99). */
+typedef struct pm3d_clutter_sprite {
+    double x, y;
+    int32_t cell_x, cell_y;     /* the cell it belongs to (posId = (cell_x-1)*mapWidth + cell_y) */
+    int32_t def, _pad;          /* index into Map.Clutter                            */
+} pm3d_clutter_sprite;          /* 32 bytes */
+
+#define PM3D_CLUTTER_MAX_DEFS 64
+#define PM3D_CLUTTER_MAX_DISTANCE 190.0
+/* Mission-time clutter state (needs pm3d_upload_grid first).  defs: Map.Clutter, n_defs <= 64.  cell_class
+ * [map_w][map_h]: a small id of the floor texture path TextureHandler.FloorTexturePathAt returns for the cell
+ * (game/texture/texture.go:135-143); class_mask[c] bit i = defs[i].FloorPathMatch is nil or matches the path of
+ * class c (the regular expressions run on the host, once per distinct path).  map_seed: Map.Seed
+ * (game/model/map.go:93). */
+int pm3d_upload_clutter(pm3d_ctx *ctx, const pm3d_clutter_def *defs, int n_defs, const uint8_t *cell_class,
+                        const uint64_t *class_mask, int n_classes, int64_t map_seed);
+/* ClutterHandler.Update for n cameras; clutter_distance = g.clutterDistance in cells (<= 190).
+ *   out_count[n]: clutter sprites of each camera; out_records / out_sprites: [n][max_per_view], in creation order
+ *   (sample angle, distance, clutter index); out_sprites (may be NULL) are the same sprites as ready-made
+ *   pm3d_sprite records (z 0, anchor bottom, focusable, illumination 0) for pm3d_render.  A camera with more
+ *   than max_per_view sprites reports its full count and keeps the first max_per_view.
+ *   flags: PM3D_IN_DEVICE / PM3D_OUT_DEVICE (all three outputs) / PM3D_NO_SYNC. */
+int pm3d_clutter_batch(pm3d_ctx *ctx, const pm3d_clutter_query *queries, int n, double clutter_distance,
+                       int max_per_view, int32_t *out_count, pm3d_clutter_sprite *out_records,
+                       pm3d_sprite *out_sprites, uint32_t flags);
+/* The rngCooked table of Go's math/rand (607 words) as the library regenerates it (gen_cooked.go's 7.8e12 steps
+ * by polynomial jump-ahead); exported so a test can pin it against known answers. */
+int pm3d_go_rand_cooked(uint64_t *out607);
+
 /* ------------------------------------------------------------------ device memory + timing
  * (so a cgo / ctypes host needs no CUDA binding of its own) */
 int pm3d_device_alloc(pm3d_ctx *ctx, int64_t bytes, void **out);

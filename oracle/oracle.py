@@ -65,9 +65,8 @@ def build(force: bool = False) -> str:
     """Compile oracle/libpm3d_oracle.so with the committed Makefile (building the checker is
     not using it)."""
     so = os.path.join(_HERE, "libpm3d_oracle.so")
-    src = os.path.join(_HERE, "pm3d_oracle.c")
-    hdr = os.path.join(_HERE, "pm3d_oracle.h")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "libpm3d_oracle.so"], stdout=subprocess.DEVNULL)
     return so
 
@@ -258,3 +257,85 @@ def present(src: np.ndarray, out_w: int, out_h: int, render_scale: float, mode: 
 
 def go_int(v: float) -> int:
     return int(lib().orc_go_int(float(v)))
+
+
+# ---------------------------------------------------------------- Go math/rand + ClutterHandler.Update
+
+CLUTTER_DEF_DTYPE = np.dtype([("frequency", "<f8"), ("scale", "<f8"), ("sheet", "<i4"), ("rx0", "<i4"), ("ry0", "<i4"),
+                              ("rx1", "<i4"), ("ry1", "<i4"), ("_pad", "<i4")])
+CLUTTER_QUERY_DTYPE = np.dtype([("cam_x", "<f8"), ("cam_y", "<f8"), ("n_angles", "<i4"), ("_pad", "<i4"),
+                                ("cs", "<f8", (21, 2))])
+CLUTTER_SPRITE_DTYPE = np.dtype([("x", "<f8"), ("y", "<f8"), ("cell_x", "<i4"), ("cell_y", "<i4"), ("def", "<i4"),
+                                 ("_pad", "<i4")])
+assert CLUTTER_DEF_DTYPE.itemsize == 40 and CLUTTER_QUERY_DTYPE.itemsize == 360 and CLUTTER_SPRITE_DTYPE.itemsize == 32
+
+
+class _GoRandState(C.Structure):
+    _fields_ = [("tap", C.c_int32), ("feed", C.c_int32), ("vec", C.c_uint64 * 607)]
+
+
+class GoRand:
+    """rand.New(rand.NewSource(seed)) of Go's math/rand (oracle/pm3d_oracle_clutter.c)."""
+
+    def __init__(self, seed: int):
+        self._s = _GoRandState()
+        self.seed(seed)
+
+    def seed(self, seed: int):
+        lib().orc_gorand_seed(C.byref(self._s), C.c_int64(seed))
+
+    def uint64(self) -> int:
+        lib().orc_gorand_uint64.restype = C.c_uint64
+        return int(lib().orc_gorand_uint64(C.byref(self._s)))
+
+    def int63(self) -> int:
+        lib().orc_gorand_int63.restype = C.c_int64
+        return int(lib().orc_gorand_int63(C.byref(self._s)))
+
+    def intn(self, n: int) -> int:
+        lib().orc_gorand_intn.restype = C.c_int32
+        return int(lib().orc_gorand_intn(C.byref(self._s), C.c_int32(n)))
+
+    def float64(self) -> float:
+        lib().orc_gorand_float64.restype = C.c_double
+        return float(lib().orc_gorand_float64(C.byref(self._s)))
+
+
+def gorand_cooked() -> np.ndarray:
+    """The rngCooked table of math/rand (607 words), regenerated the way gen_cooked.go makes it."""
+    lib().orc_gorand_cooked.restype = C.POINTER(C.c_uint64)
+    return np.ctypeslib.as_array(lib().orc_gorand_cooked(), shape=(607,)).copy()
+
+
+def gorand_gen_state(n: int, jump: bool) -> np.ndarray:
+    out = np.zeros(607, dtype=np.uint64)
+    lib().orc_gorand_gen_state(C.c_uint64(n), C.c_int32(int(jump)), _ptr(out))
+    return out
+
+
+def clutter_angles(heading: float, fov_degrees: float) -> np.ndarray:
+    """The sample angles of game/clutter.go:44-45."""
+    out = np.zeros(64, dtype=np.float64)
+    n = lib().orc_clutter_angles(C.c_double(heading), C.c_double(fov_degrees), _ptr(out), C.c_int32(64))
+    if n < 0:
+        raise ValueError("fov must be positive")
+    return out[:n]
+
+
+def clutter_update(level0: np.ndarray, cell_class: np.ndarray, class_mask: np.ndarray, defs: np.ndarray, map_seed: int,
+                   clutter_distance: float, query: np.ndarray) -> np.ndarray:
+    """ClutterHandler.Update(g, true) on an empty handler for ONE camera (game/clutter.go:25-117)."""
+    level0 = np.ascontiguousarray(level0, dtype=np.uint16)
+    map_w, map_h = level0.shape
+    cell_class = np.ascontiguousarray(cell_class, dtype=np.uint8).reshape(map_w, map_h)
+    class_mask = np.ascontiguousarray(class_mask, dtype=np.uint64)
+    defs = np.ascontiguousarray(defs, dtype=CLUTTER_DEF_DTYPE).reshape(-1)
+    query = np.ascontiguousarray(query, dtype=CLUTTER_QUERY_DTYPE).reshape(-1)[:1]
+    cap = 21 * (int(max(clutter_distance, 0)) + 2) * max(len(defs), 1)
+    out = np.zeros(cap, dtype=CLUTTER_SPRITE_DTYPE)
+    f = lib().orc_clutter_update
+    f.restype = C.c_int64
+    n = f(_ptr(level0), C.c_int32(map_w), C.c_int32(map_h), _ptr(cell_class), _ptr(class_mask), _ptr(defs),
+          C.c_int32(len(defs)), C.c_int64(map_seed), C.c_double(clutter_distance), _ptr(query), _ptr(out), C.c_int64(cap))
+    assert 0 <= n <= cap
+    return out[:n]

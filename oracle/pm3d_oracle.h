@@ -194,6 +194,49 @@ void orc_present_axis_map(int32_t n_out, int32_t n_src, double render_scale, int
 void orc_present(const uint8_t *src, int32_t sw, int32_t sh, int32_t ow, int32_t oh, double render_scale, int32_t mode,
                  uint8_t *out, int32_t threads);
 
+/* ---- Go math/rand + ClutterHandler.Update (pm3d_oracle_clutter.c) ------------------ */
+
+/* rngSource of Go's math/rand [R]; pinned by known answers (tests/test_clutter_cpu.py) */
+typedef struct orc_gorand {
+    int32_t tap, feed;
+    uint64_t vec[607];
+} orc_gorand;
+const uint64_t *orc_gorand_cooked(void);                /* the rngCooked table, regenerated */
+void orc_gorand_gen_state(uint64_t n, int32_t jump, uint64_t *out607); /* gen_cooked.go state after n steps */
+void orc_gorand_seed(orc_gorand *r, int64_t seed);      /* Rand.Seed / rand.NewSource */
+uint64_t orc_gorand_uint64(orc_gorand *r);
+int64_t orc_gorand_int63(orc_gorand *r);
+int32_t orc_gorand_intn(orc_gorand *r, int32_t n);
+double orc_gorand_float64(orc_gorand *r);
+
+/* one model.MapClutter entry (game/model/map.go:128-133), resolved by the host */
+typedef struct orc_clutter_def {
+    double frequency;              /* Frequency                                       */
+    double scale;                  /* Height / model.METERS_PER_UNIT (clutter.go:88)  */
+    int32_t sheet;                 /* g.tex.TextureImage(clutter.Image)               */
+    int32_t rx0, ry0, rx1, ry1;    /* GetSpriteSheetSlices(img, 1, 1) rect            */
+    int32_t _pad;
+} orc_clutter_def;                 /* 40 bytes */
+/* one camera: position and (cos, sin) of the sample angles of clutter.go:45 */
+typedef struct orc_clutter_query {
+    double cam_x, cam_y;
+    int32_t n_angles, _pad;
+    double cs[21][2];
+} orc_clutter_query;               /* 360 bytes */
+typedef struct orc_clutter_sprite {
+    double x, y;                   /* BasicVisualEntity position (z = 0, AnchorBottom) */
+    int32_t cell_x, cell_y;        /* the cell whose posId seeds the generator        */
+    int32_t def, _pad;             /* index into Map.Clutter                          */
+} orc_clutter_sprite;              /* 32 bytes */
+/* the sample angles of clutter.go:44-45; returns their number (<= 21 by construction), -1 for fov <= 0 */
+int32_t orc_clutter_angles(double heading, double fov_degrees, double *out_angles, int32_t cap);
+/* ClutterHandler.Update(g, forceUpdate=true) on an empty handler (game/clutter.go:25-117) [V]: the clutter
+ * sprites in view of one camera, in creation order.  level0 / cell_class: [map_w][map_h]; class_mask[c] bit i =
+ * clutter i's FloorPathMatch accepts the floor texture path of class c.  Returns the count (writes <= cap). */
+int64_t orc_clutter_update(const uint16_t *level0, int32_t map_w, int32_t map_h, const uint8_t *cell_class,
+                           const uint64_t *class_mask, const orc_clutter_def *defs, int32_t n_defs, int64_t map_seed,
+                           double clutter_distance, const orc_clutter_query *q, orc_clutter_sprite *out, int64_t cap);
+
 /* Go int(float64) on amd64. */
 int64_t orc_go_int(double v);
 

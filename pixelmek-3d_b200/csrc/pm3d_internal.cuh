@@ -170,6 +170,13 @@ struct pm3d_ctx {
     int n_colliders = 0, player_index = -1;
     int32_t *cb_start = nullptr, *cb_items = nullptr, *cb_loose = nullptr;  // colliders binned by cell (los_kernel.cu)
     int cb_x0 = 0, cb_y0 = 0, cb_w = 0, cb_h = 0, n_loose = 0;
+    // clutter (clutter_kernel.cu)
+    uint8_t *clutter_class = nullptr;   // [map_w][map_h] floor-path class per cell
+    void *clutter_tab = nullptr;        // class masks | clutter defs | per-draw generator constants
+    size_t clutter_class_bytes = 0, clutter_tab_bytes = 0;
+    int clutter_defs = 0;
+    int64_t clutter_seed = 0;
+    bool clutter_ready = false, clutter_smem_optin = false;
     void *io_a = nullptr, *io_b = nullptr, *io_c = nullptr;  // batch staging on device
     size_t io_a_bytes = 0, io_b_bytes = 0, io_c_bytes = 0;
 

@@ -90,6 +90,21 @@ MOVE_RESULT_DTYPE = np.dtype(
 )
 assert MOVE_RESULT_DTYPE.itemsize == 80
 
+CLUTTER_DEF_DTYPE = np.dtype(
+    [("frequency", "<f8"), ("scale", "<f8"), ("sheet", "<i4"), ("rx0", "<i4"), ("ry0", "<i4"), ("rx1", "<i4"),
+     ("ry1", "<i4"), ("_pad", "<i4")]
+)
+assert CLUTTER_DEF_DTYPE.itemsize == 40
+CLUTTER_MAX_ANGLES, CLUTTER_MAX_DEFS, CLUTTER_MAX_DISTANCE = 21, 64, 190.0
+CLUTTER_QUERY_DTYPE = np.dtype(
+    [("cam_x", "<f8"), ("cam_y", "<f8"), ("n_angles", "<i4"), ("_pad", "<i4"), ("cs", "<f8", (CLUTTER_MAX_ANGLES, 2))]
+)
+assert CLUTTER_QUERY_DTYPE.itemsize == 360
+CLUTTER_SPRITE_DTYPE = np.dtype(
+    [("x", "<f8"), ("y", "<f8"), ("cell_x", "<i4"), ("cell_y", "<i4"), ("def", "<i4"), ("_pad", "<i4")]
+)
+assert CLUTTER_SPRITE_DTYPE.itemsize == 32
+
 # every symbol include/pm3d.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -120,6 +135,9 @@ SYMBOLS = {
     "pm3d_present": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_uint32]),
     "pm3d_upload_colliders": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "pm3d_valid_move_batch": (C.c_int, [_P, _P, C.c_int64, C.c_double, _P, C.c_uint32]),
+    "pm3d_upload_clutter": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int64]),
+    "pm3d_clutter_batch": (C.c_int, [_P, _P, C.c_int, C.c_double, C.c_int, _P, _P, _P, C.c_uint32]),
+    "pm3d_go_rand_cooked": (C.c_int, [_P]),
     "pm3d_generate_wall_collision_lines": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double, _P, C.c_int]),
     "pm3d_device_alloc": (C.c_int, [_P, C.c_int64, C.POINTER(_P)]),
     "pm3d_device_free": (C.c_int, [_P, _P]),

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (COLLIDER_DTYPE, COLUMN_DTYPE, CONV_DTYPE, MOVE_RESULT_DTYPE, MOVER_DTYPE, SPRITE_DTYPE, VIEW_DTYPE,
+from ._lib import (CLUTTER_DEF_DTYPE, CLUTTER_QUERY_DTYPE, CLUTTER_SPRITE_DTYPE, COLLIDER_DTYPE, COLUMN_DTYPE, CONV_DTYPE, MOVE_RESULT_DTYPE, MOVER_DTYPE, SPRITE_DTYPE, VIEW_DTYPE,
                    Pm3dError, ptr)
 from .scene import SceneData
 
@@ -228,6 +228,26 @@ class Context:
         self._check(self.lib.pm3d_valid_move_batch(self.h, ptr(movers), len(movers), float(clip), ptr(out), 0),
                     "pm3d_valid_move_batch")
         return out
+
+    # ------------------------------------------------------------------ clutter
+    def upload_clutter(self, defs: np.ndarray, cell_class: np.ndarray, class_mask: np.ndarray, map_seed: int):
+        """Map.Clutter + the floor-path class of every cell + Map.Seed (after upload_grid)."""
+        defs = np.ascontiguousarray(defs, dtype=CLUTTER_DEF_DTYPE).reshape(-1)
+        cell_class = np.ascontiguousarray(cell_class, dtype=np.uint8)
+        class_mask = np.ascontiguousarray(class_mask, dtype=np.uint64).reshape(-1)
+        self._check(self.lib.pm3d_upload_clutter(self.h, ptr(defs) if len(defs) else None, len(defs), ptr(cell_class),
+                                                 ptr(class_mask), len(class_mask), int(map_seed)), "pm3d_upload_clutter")
+
+    def clutter_batch(self, queries: np.ndarray, clutter_distance: float, max_per_view: int, want_sprites: bool = False):
+        """ClutterHandler.Update for every camera of `queries`: (counts, records[n][max_per_view][, sprites])."""
+        queries = np.ascontiguousarray(queries, dtype=CLUTTER_QUERY_DTYPE).reshape(-1)
+        n = len(queries)
+        counts = np.zeros(n, dtype=np.int32)
+        recs = np.zeros((n, max_per_view), dtype=CLUTTER_SPRITE_DTYPE)
+        sprites = np.zeros((n, max_per_view), dtype=SPRITE_DTYPE) if want_sprites else None
+        self._check(self.lib.pm3d_clutter_batch(self.h, ptr(queries), n, float(clutter_distance), int(max_per_view),
+                                                ptr(counts), ptr(recs), ptr(sprites), 0), "pm3d_clutter_batch")
+        return (counts, recs, sprites) if want_sprites else (counts, recs)
 
     # ------------------------------------------------------------------ device memory + timers
     def device_alloc(self, nbytes: int) -> int:

@@ -328,6 +328,67 @@ def sweep_moves(ctx, rank, world, dist, torch, dev):
     }
 
 
+def sweep_clutter(ctx, rank, world, dist, torch, dev, with_cpu):
+    """ClutterHandler.Update (game/clutter.go:25-117) for the 4096 c4 cameras on the bundled map with its own clutter
+    list and seed, fov 70, clutterDistance 25 cells (the reference default), views sharded i % n_gpus."""
+    import ctypes as C
+    import time
+
+    from pm3d import clutter as cl, shard, workloads as Wk
+    L = __import__("pm3d")._lib
+
+    scene, g = Wk.proving_grounds_scene()
+    n_all = 4096
+    poses = Wk.free_cell_poses(scene, n_all, 4096)
+    clutter = [cl.MapClutter(str(im), float(f), float(h), str(m) or None) for im, m, f, h in
+               zip(g["clutter_image"], g["clutter_match"], g["clutter_frequency"], g["clutter_height"])]
+    sheets = {c.image: (3, int(w), int(h)) for c, (w, h) in zip(clutter, g["clutter_image_size"])}
+    defs, cls, masks = cl.resolve_clutter(clutter, g["floor_grid"], [str(x) for x in g["floor_images"]], sheets)
+    mine = shard.view_shard(n_all, rank, world)
+    q = cl.clutter_queries([(poses[i][0], poses[i][1], poses[i][3]) for i in mine], 70.0)
+    n, cap, cdist = len(q), 21 * 26 * len(clutter), 25.0
+    ctx.upload_scene(scene)
+    ctx.upload_clutter(defs, cls, masks, int(g["map_seed"]))
+    d_q, d_cnt = ctx.device_alloc(q.nbytes), ctx.device_alloc(4 * n)
+    d_rec, d_spr = ctx.device_alloc(32 * n * cap), ctx.device_alloc(64 * n * cap)
+    ctx.h2d(d_q, q)
+    flags = L.PM3D_IN_DEVICE | L.PM3D_OUT_DEVICE | L.PM3D_NO_SYNC
+    call = lambda: ctx._check(ctx.lib.pm3d_clutter_batch(ctx.h, C.c_void_p(d_q), n, cdist, cap, C.c_void_p(d_cnt), C.c_void_p(d_rec),
+                                                         C.c_void_p(d_spr), flags), "pm3d_clutter_batch")
+    call(); ctx.sync()
+    if world > 1:
+        dist.barrier()
+    reps = 20
+    ctx.timer_start(6)
+    for _ in range(reps):
+        call()
+    ctx.timer_stop(6)
+    ms = ctx.timer_ms(6) / reps
+    counts = np.zeros(n, dtype=np.int32)
+    ctx.d2h(counts, d_cnt)
+    for p_ in (d_q, d_cnt, d_rec, d_spr):
+        ctx.device_free(p_)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    tot = torch.tensor([int(counts.sum())], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_max = float(t.item())
+    out = {"workload": f"clutter: ClutterHandler.Update for {n_all} cameras on proving_grounds (2 clutter types, seed {int(g['map_seed'])}), "
+                       "fov 70, clutterDistance 25 cells = 546 samples per camera, sharded i % n_gpus",
+           "updates_per_s": n_all / (ms_max * 1e-3), "ms_per_batch": ms_max, "cameras_per_gpu": n, "clutter_sprites": int(tot.item()),
+           "bytes_per_camera": 360 + 4 + 96 * float(tot.item()) / n_all}
+    if with_cpu:
+        from oracle import oracle as O
+        k, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < 2.0 and k < n:
+            O.clutter_update(scene.grid[0], cls, masks, defs.astype(O.CLUTTER_DEF_DTYPE), int(g["map_seed"]), cdist,
+                             q[k:k + 1].astype(O.CLUTTER_QUERY_DTYPE))
+            k += 1
+        out["cpu_port_updates_per_s_1_thread"] = k / (time.perf_counter() - t0)
+    return out
+
+
 def sweep_present(ctx, torch):
     """Presentation step at 1920x1080 from a 960x540 rayScreen (renderScale 0.5), CRT shader; rank 0's GPU."""
     from pm3d import workloads as Wk
@@ -503,6 +564,7 @@ def run_ours(args, rank, world, local_rank):
             extra["c5"] = sweep_c5(ctx, rank, world, dist, torch, dev)
             extra["moves"] = sweep_moves(ctx, rank, world, dist, torch, dev)
             extra["present"] = sweep_present(ctx, torch)
+            extra["clutter"] = sweep_clutter(ctx, rank, world, dist, torch, dev, rank == 0 and world == 1 and not args.no_cpu)
         except Exception as e:  # the headline line must still print
             extra["error"] = repr(e)
     line["extra"] = extra

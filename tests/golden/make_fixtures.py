@@ -9,9 +9,11 @@ and freezes their outputs for the two bundled maps, together with the map consta
 path needs (lighting, texture table, sprite placements).  The fixtures are DATA derived from
 the reference's YAML by this script; no reference source is copied.
 
-spriteFill placements use Go's math/rand (game/model/map.go:369-372), which cannot be
-reproduced here; the same counts/rects/height ranges are filled with splitmix64 instead
-(SURVEY.md §8c "bit-exactness hazards").
+spriteFill placements use Go's math/rand (game/model/map.go:364-399: rng.Seed(m.Seed + n), then
+RandFloat64In per coordinate and height, game/model/rand.go:36-44).  The oracle restates that generator
+(oracle/pm3d_oracle_clutter.c, pinned against the library's published seed-1 outputs in
+tests/test_clutter_cpu.py), so the fill positions frozen here are the ones the game itself generates.
+Clutter (Map.Clutter, Map.Seed) rides along for the clutter tests.
 
     python tests/golden/make_fixtures.py
 """
@@ -31,22 +33,6 @@ from oracle import mapgen  # noqa: E402
 REF = "/root/reference/game/resources"
 METERS_PER_UNIT = 20.0  # game/model/model.go:12
 CLIP_DISTANCE = 0.01    # game/game.go:33
-
-_M64 = (1 << 64) - 1
-
-
-def splitmix64(state):
-    state = (state + 0x9E3779B97F4A7C15) & _M64
-    z = state
-    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
-    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
-    return state, z ^ (z >> 31)
-
-
-def rand01(state):
-    state, v = splitmix64(state)
-    return state, (v >> 11) / float(1 << 53)
-
 
 def png_size(path):
     with open(path, "rb") as f:
@@ -86,7 +72,7 @@ def build(map_name: str, mission_name: str | None):
         tex_sx.append("")
         tex_sy.append("")
 
-    # sprites: explicit positions, stamps (deterministic), fills (splitmix64 substitute)
+    # sprites: explicit positions, fills (Go math/rand through the oracle's restatement), stamps
     by_id = {s["id"]: s for s in (m.get("sprites") or []) if s.get("id")}
     spr = []  # (x, y, z, scale, image, anchor)
 
@@ -97,17 +83,18 @@ def build(map_name: str, mission_name: str | None):
     for s in m.get("sprites") or []:
         for pos in s.get("positions") or []:
             add(s, pos[0], pos[1], s.get("height") or 0)
-    state = int(m.get("seed") or 0) & _M64
+    from oracle import oracle as O
+    map_seed = int(m.get("seed") or 0)
     for n, fill in enumerate(m.get("spriteFill") or []):
-        st = (state + n) & _M64
-        (x0, y0), (x1, y1) = fill["rect"]
-        lo, hi = fill.get("heightRange") or [0, 0]
+        rng = O.GoRand(map_seed + n)                           # rng.Seed(m.Seed + int64(n)), map.go:372
+        (x0, y0), (x1, y1) = [[float(v) for v in p] for p in fill["rect"]]
+        hr = fill.get("heightRange") or []
         s = by_id[fill["sprite"]]
         for _ in range(int(fill["quantity"])):
-            st, a = rand01(st)
-            st, b = rand01(st)
-            st, c = rand01(st)
-            add(s, x0 + (x1 - x0) * a, y0 + (y1 - y0) * b, lo + (hi - lo) * c)
+            fx = x0 + (x1 - x0) * rng.float64()                 # RandFloat64In, rand.go:36-44
+            fy = y0 + (y1 - y0) * rng.float64()
+            height = float(hr[0]) + (float(hr[1]) - float(hr[0])) * rng.float64() if len(hr) == 2 else 0.0
+            add(s, fx, fy, height)
     for stamp in m.get("spriteStamps") or []:
         for px, py in stamp["positions"]:
             for ref in stamp["sprites"]:
@@ -130,7 +117,16 @@ def build(map_name: str, mission_name: str | None):
         "sprite_image": np.array([images.index(s[4]) for s in spr], dtype=np.int32),
         "sprite_anchor": np.array([s[5] for s in spr], dtype=np.uint8),
         "sprite_images": np.array(images), "sprite_image_sizes": np.array(image_sizes, dtype=np.int32).reshape(-1, 2),
+        "map_seed": np.int64(map_seed),
     }
+    clutter = m.get("clutter") or []
+    if clutter:
+        out["clutter_image"] = np.array([c["image"] for c in clutter])
+        out["clutter_match"] = np.array([c.get("floorPathMatch") or "" for c in clutter])
+        out["clutter_frequency"] = np.array([float(c["frequency"]) for c in clutter], dtype=np.float64)
+        out["clutter_height"] = np.array([float(c["height"]) for c in clutter], dtype=np.float64)
+        out["clutter_image_size"] = np.array([png_size(os.path.join(REF, "sprites", c["image"])) for c in clutter],
+                                             dtype=np.int32).reshape(-1, 2)
     if mission_name:
         with open(os.path.join(REF, "missions", mission_name + ".yaml")) as f:
             ms = yaml.safe_load(f)

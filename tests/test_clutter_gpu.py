@@ -35,13 +35,22 @@ def assert_same(counts, recs, want, sprites=None, defs=None):
                 assert np.array_equal(s[k], defs[k][w["def"]])
 
 
+def fixture_clutter(g):
+    """Map.Clutter of the bundled map, frozen in tests/golden by make_fixtures.py"""
+    return [cl.MapClutter(str(im), float(f), float(h), str(m) or None)
+            for im, m, f, h in zip(g["clutter_image"], g["clutter_match"], g["clutter_frequency"], g["clutter_height"])]
+
+
 def proving_grounds_clutter(ctx):
     scene, g = W.proving_grounds_scene()
     ctx.upload_scene(scene)
-    clutter = [cl.MapClutter("rocks/rock_0.png", 0.3, 1.0, "grass"), cl.MapClutter("shrubbery/bush_0.png", 0.5, 1.0, "grass")]
-    sheets = {"rocks/rock_0.png": (3, 18, 18), "shrubbery/bush_0.png": (3, 24, 24)}   # proving_grounds.yaml:77-85
+    clutter = fixture_clutter(g)
+    assert [(c.image, c.frequency, c.height, c.floorPathMatch) for c in clutter] == [
+        ("rocks/rock_0.png", 0.3, 1.0, "grass"), ("shrubbery/bush_0.png", 0.5, 1.0, "grass")]   # proving_grounds.yaml:77-85
+    sheets = {c.image: (3, int(w), int(h)) for c, (w, h) in zip(clutter, g["clutter_image_size"])}
     defs, cls, masks = cl.resolve_clutter(clutter, g["floor_grid"], [str(s) for s in g["floor_images"]], sheets)
-    ctx.upload_clutter(defs, cls, masks, 12345)               # proving_grounds.yaml:5
+    assert int(g["map_seed"]) == 12345                        # proving_grounds.yaml:5
+    ctx.upload_clutter(defs, cls, masks, int(g["map_seed"]))
     return scene, g, defs, cls, masks
 
 
@@ -142,7 +151,7 @@ def test_handler_feeds_the_camera(gpu_ctx):
     scene.sheets = list(scene.sheets) + [rock, bush]
     i_rock, i_bush = len(scene.sheets) - 2, len(scene.sheets) - 1
     gpu_ctx.upload_scene(scene)
-    clutter = [cl.MapClutter("rocks/rock_0.png", 0.3, 1.0, "grass"), cl.MapClutter("shrubbery/bush_0.png", 0.5, 1.0, "grass")]
+    clutter = fixture_clutter(g)
     handler = cl.ClutterHandler(gpu_ctx, clutter, g["floor_grid"], [str(s) for s in g["floor_images"]],
                                 {"rocks/rock_0.png": (i_rock, 18, 18), "shrubbery/bush_0.png": (i_bush, 24, 24)}, 12345, 500)
     pose = (31.5, 3.5, 0.5, W.cardinal_to_angle(45.0), 0.0)

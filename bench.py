@@ -26,6 +26,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -233,6 +234,54 @@ def sweep_c4(ctx, rank, world, dist, torch, dev):
         "hbm_frac_sweep": (fb / (ms * 1e-3)) / 1e9 / peak,
         "checksum_of_checksums": f"{total:016x}",
     }
+
+
+def sweep_c3(ctx):
+    """c3: single camera 3840x2160, synthetic 512x512 map (5 % walls), 3 and 8 raycast levels, infinite render
+    distance, pitch swept over [-pi/8, pi/4] (8 poses, ring of 8 output frames = 265 MB > L2).  A single camera does
+    not shard: every rank would render the same frames, so this is rank 0's GPU (replicas only)."""
+    from pm3d import workloads as Wk
+
+    w, h, ring = 3840, 2160, 8
+    fb = w * h * 4
+    peak, _ = hbm_peak()
+    out = {"workload": "c3: 3840x2160, synthetic 512x512 map 5% walls + boundary, renderDistance -1, pitch swept over "
+                       "[-pi/8, pi/4] (8 poses, 8 output frames = 265 MB > L2), no sprites; one GPU (replicas only)"}
+    d_out = ctx.device_alloc(ring * fb)
+    for levels in (3, 8):
+        cfg = Wk.config_c3(levels=levels, w=w, h=h)
+        x, y, z, heading, _ = cfg["poses"][0]
+        poses = [(x, y, z, heading + 0.37 * i, -math.pi / 8 + (math.pi / 4 + math.pi / 8) * i / (ring - 1)) for i in range(ring)]
+        views = Wk.make_views(cfg["scene"], w, h, poses, render_distance=-1.0)
+        ctx.upload_scene(cfg["scene"])
+        ctx.set_view(w, h, 1, 1)
+        d_views = ctx.device_alloc(views.nbytes)
+        d_off = ctx.device_alloc(8)
+        ctx.h2d(d_views, views); ctx.h2d(d_off, np.zeros(2, dtype=np.int32))
+        frame = lambda i: ctx.render_resident(d_views + (i % ring) * views.itemsize, 1, 0, d_off, 0, d_out + (i % ring) * fb)
+        for i in range(ring):
+            frame(i)
+        ctx.sync()
+        reps = 64
+        ctx.timer_start(7)
+        for i in range(reps):
+            frame(i)
+        ctx.timer_stop(7)
+        ms = ctx.timer_ms(7) / reps
+        ctx.set_option(__import__("pm3d")._lib.OPT_OVERLAP, 0)   # per-kernel durations: one kernel at a time
+        ctx.ktimer_begin(ring)
+        for i in range(ring):
+            frame(i)
+        kt = ctx.ktimer_collect(ring)
+        ctx.set_option(__import__("pm3d")._lib.OPT_OVERLAP, 1)
+        ctx.device_free(d_views); ctx.device_free(d_off)
+        compose_ms = float(kt[:, 2].mean())
+        out[f"levels_{levels}"] = {"frames_per_s": 1e3 / ms, "ms_per_frame": ms, "mrays_per_s": w * levels / (ms * 1e-3) / 1e6,
+                                   "mpixels_per_s": w * h / (ms * 1e-3) / 1e6, "compose_ms": compose_ms,
+                                   "front_ms": float(kt[:, 0].mean()), "hbm_frac_compose": fb / (compose_ms * 1e-3) / 1e9 / peak,
+                                   "hbm_frac_frame": fb / (ms * 1e-3) / 1e9 / peak}
+    ctx.device_free(d_out)
+    return out
 
 
 def sweep_c5(ctx, rank, world, dist, torch, dev):
@@ -560,6 +609,8 @@ def run_ours(args, rank, world, local_rank):
     extra = {}
     if not args.no_sweeps:
         try:
+            if rank == 0:
+                extra["c3"] = sweep_c3(ctx)
             extra["c4"] = sweep_c4(ctx, rank, world, dist, torch, dev)
             extra["c5"] = sweep_c5(ctx, rank, world, dist, torch, dev)
             extra["moves"] = sweep_moves(ctx, rank, world, dist, torch, dev)

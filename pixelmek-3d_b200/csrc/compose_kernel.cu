@@ -775,7 +775,7 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     // rows per warp: enough warps to fill the chip a few times over, otherwise as long as possible
     const long long warps8 = (long long)ctx->n_groups * ((ctx->h + 7) / 8) * n_views;
     const long long resident = (long long)ctx->sm_count * 24;
-    int rows = warps8 >= 64 * resident ? 16 : (warps8 >= 8 * resident ? 8 : (warps8 >= 2 * resident ? 4 : 2));
+    int rows = warps8 >= 64 * resident ? 16 : (warps8 >= 4 * resident ? 8 : (warps8 >= 2 * resident ? 4 : 2));  // 4K single frame: 8
     int minb = rows >= 8 ? 8 : 6;
     if (const char *e = getenv("PM3D_COMPOSE_ROWS")) rows = atoi(e);      // tuning overrides (tools/)
     if (const char *e = getenv("PM3D_COMPOSE_MINB")) minb = atoi(e);

@@ -212,6 +212,19 @@ def test_warp_list_overflow_in_both_sprite_modes(gpu_ctx, rows, monkeypatch):
     assert np.array_equal(fast, slow)
 
 
+@pytest.mark.parametrize("rows,minb", [(2, 6), (2, 8), (4, 6), (4, 8), (8, 6), (8, 8), (16, 8)])
+def test_every_compose_instantiation_gives_the_same_frame(gpu_ctx, rows, minb, monkeypatch):
+    """The launcher picks rows-per-warp, CTA shape and latency/throughput sprite stage by problem size; every
+    instantiation must paint the oracle's frame (c2 scene at 640x360, 200 sprites, two poses)."""
+    c = W.config_c2(w=640, h=360, n_poses=2)
+    monkeypatch.setenv("PM3D_COMPOSE_ROWS", str(rows))
+    monkeypatch.setenv("PM3D_COMPOSE_MINB", str(minb))
+    got, want = render_both(gpu_ctx, c["scene"], 640, 360, c["views"], c["sprites"], c["offsets"], keep_columns=False)
+    for i, ref in enumerate(want):
+        assert_frame_equal(got["rgba"][i], ref["rgba"], f"rows {rows} minb {minb} view {i}")
+        assert int(got["conv"][i]["sprite"]) == ref["convergence"]["sprite"]
+
+
 def test_division_free_floor_weight_is_correctly_rounded(gpu_ctx):
     """The floor cast's weight = currentDist / distWall is evaluated as a Newton sequence on RN(1/distWall)
     (pm3d_internal.cuh div_by_rcp).  It must equal the IEEE quotient bit for bit: 2.1e9 operand pairs

@@ -426,7 +426,8 @@ def sweep_clutter(ctx, rank, world, dist, torch, dev, with_cpu):
     out = {"workload": f"clutter: ClutterHandler.Update for {n_all} cameras on proving_grounds (2 clutter types, seed {int(g['map_seed'])}), "
                        "fov 70, clutterDistance 25 cells = 546 samples per camera, sharded i % n_gpus",
            "updates_per_s": n_all / (ms_max * 1e-3), "ms_per_batch": ms_max, "cameras_per_gpu": n, "clutter_sprites": int(tot.item()),
-           "bytes_per_camera": 360 + 4 + 96 * float(tot.item()) / n_all}
+           "bytes_per_camera": 360 + 4 + 96 * float(tot.item()) / n_all,
+           "hbm_frac": (360 + 4 + 96 * float(tot.item()) / n_all) * n / (ms * 1e-3) / 1e9 / hbm_peak()[0]}
     if with_cpu:
         from oracle import oracle as O
         k, t0 = 0, time.perf_counter()
@@ -614,8 +615,8 @@ def run_ours(args, rank, world, local_rank):
             extra["c4"] = sweep_c4(ctx, rank, world, dist, torch, dev)
             extra["c5"] = sweep_c5(ctx, rank, world, dist, torch, dev)
             extra["moves"] = sweep_moves(ctx, rank, world, dist, torch, dev)
-            extra["present"] = sweep_present(ctx, torch)
             extra["clutter"] = sweep_clutter(ctx, rank, world, dist, torch, dev, rank == 0 and world == 1 and not args.no_cpu)
+            extra["present"] = sweep_present(ctx, torch)
         except Exception as e:  # the headline line must still print
             extra["error"] = repr(e)
     line["extra"] = extra

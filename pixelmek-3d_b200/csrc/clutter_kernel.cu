@@ -116,10 +116,10 @@ struct ClutterParams {
 };
 
 __device__ __forceinline__ uint32_t lehmer_mulmod(uint32_t x, uint32_t t) {
-    const uint64_t p = (uint64_t)x * t;  // < 2^62
-    uint64_t r = (p & LEHMER_M) + (p >> 31);
+    const uint64_t p = (uint64_t)x * t;  // < 2^62 = hi * 2^31 + lo with hi, lo < 2^31, and 2^31 = 1 (mod M)
+    uint32_t r = ((uint32_t)p & LEHMER_M) + (uint32_t)(p >> 31);
     r = (r & LEHMER_M) + (r >> 31);
-    return (uint32_t)(r >= LEHMER_M ? r - LEHMER_M : r);
+    return r >= LEHMER_M ? r - LEHMER_M : r;
 }
 
 __device__ __forceinline__ uint64_t initial_word(uint32_t x0, const uint32_t pw[3], uint64_t cooked) {
@@ -149,17 +149,17 @@ __device__ __forceinline__ int64_t pos_id(uint32_t cx, uint32_t cy, int map_w) {
 constexpr uint32_t NO_CELL = 0xffffffffu;
 constexpr int CLUTTER_THREADS = 128;
 
-// dynamic shared memory: uint32 cell_x[S], cell_y[S] (the cell of every sample), uint32 table[slots] (posId -> first sample)
+// dynamic shared memory: uint32 cell_x[S], cell_y[S] (the cell of every sample), order[S] (first-visit samples in loop
+// order), table[slots] (posId -> first sample)
 __global__ void __launch_bounds__(CLUTTER_THREADS) k_clutter(const __grid_constant__ ClutterParams p) {
     extern __shared__ uint32_t smem[];
     const int view = blockIdx.x, tid = threadIdx.x;
     const pm3d_clutter_query &q = p.queries[view];
     const int n_angles = min(max(q.n_angles, 0), PM3D_CLUTTER_MAX_ANGLES);
     const int S = n_angles * p.n_dist;
-    uint32_t *cell_x = smem, *cell_y = smem + S, *table = smem + 2 * S;
+    uint32_t *cell_x = smem, *cell_y = smem + S, *order = smem + 2 * S, *table = smem + 3 * S;
     const uint32_t mask = (uint32_t)p.slots - 1u;
-    __shared__ int warp_sum[CLUTTER_THREADS / 32];
-    __shared__ int run_base;
+    __shared__ int warp_sum[2][CLUTTER_THREADS / 32];
 
     for (int i = tid; i < p.slots; i += CLUTTER_THREADS) table[i] = NO_CELL;
     // ---- the cell of every sample (clutter.go:46-57)
@@ -191,36 +191,55 @@ __global__ void __launch_bounds__(CLUTTER_THREADS) k_clutter(const __grid_consta
             h = (h + 1u) & mask;
         }
     }
-    if (tid == 0) run_base = 0;
     __syncthreads();
 
-    // ---- cells in first-visit order: count, scan, write
+    // ---- the first-visit samples, compacted in loop order (so the lanes that draw numbers below are all busy)
     const int lane = tid & 31, warp = tid >> 5;
-    for (int s0 = 0; s0 < S; s0 += CLUTTER_THREADS) {
+    constexpr int NW = CLUTTER_THREADS / 32;
+    int n_cells = 0;  // (every thread keeps the same running totals)
+    int pp = 0;       // ping-pong slot of warp_sum: one barrier per chunk
+    for (int s0 = 0; s0 < S; s0 += CLUTTER_THREADS, pp ^= 1) {
         const int s = s0 + tid;
         bool first = false;
-        uint32_t cx = 0, cy = 0, x0 = 0;
-        uint64_t match = 0;
         if (s < S && cell_x[s] != NO_CELL) {
-            cx = cell_x[s]; cy = cell_y[s];
-            const int64_t id = pos_id(cx, cy, p.map_w);
+            const int64_t id = pos_id(cell_x[s], cell_y[s], p.map_w);
             uint32_t h = slot_of(id);
             for (;;) {
                 const uint32_t t = table[h];
                 if (pos_id(cell_x[t], cell_y[t], p.map_w) == id) { first = t == (uint32_t)s; break; }
                 h = (h + 1u) & mask;
             }
-            if (first) {
-                match = __ldg(p.class_mask + __ldg(p.cell_class + (size_t)cx * p.map_h + cy));
-                // rngSource.Seed(Map.Seed + posId): seed %= 2^31-1; negative += 2^31-1; 0 -> 89482311
-                int64_t seed = (int64_t)((uint64_t)p.map_seed + (uint64_t)id) % (int64_t)LEHMER_M;
-                if (seed < 0) seed += (int64_t)LEHMER_M;
-                if (seed == 0) seed = 89482311;
-                x0 = (uint32_t)seed;
-            }
         }
+        const unsigned b = __ballot_sync(0xffffffffu, first);
+        if (lane == 0) warp_sum[pp][warp] = __popc(b);
+        __syncthreads();
+        int base = n_cells;
+        for (int w = 0; w < NW; w++) {
+            const int c = warp_sum[pp][w];
+            if (w < warp) base += c;
+            n_cells += c;
+        }
+        if (first) order[base + __popc(b & ((1u << lane) - 1u))] = (uint32_t)s;
+    }
+    __syncthreads();
+
+    // ---- per cell: seed, draw, count; block scan; draw again and write in creation order
+    int n_out = 0;
+    for (int c0 = 0; c0 < n_cells; c0 += CLUTTER_THREADS, pp ^= 1) {
+        const int c = c0 + tid;
+        const bool live = c < n_cells;
+        uint32_t cx = 0, cy = 0, x0 = 0;
+        uint64_t match = 0;
         int cnt = 0;
-        if (first) {
+        if (live) {
+            const uint32_t s = order[c];
+            cx = cell_x[s]; cy = cell_y[s];
+            match = __ldg(p.class_mask + __ldg(p.cell_class + (size_t)cx * p.map_h + cy));
+            // rngSource.Seed(Map.Seed + posId): seed %= 2^31-1; negative += 2^31-1; 0 -> 89482311
+            int64_t seed = (int64_t)((uint64_t)p.map_seed + (uint64_t)pos_id(cx, cy, p.map_w)) % (int64_t)LEHMER_M;
+            if (seed < 0) seed += (int64_t)LEHMER_M;
+            if (seed == 0) seed = 89482311;
+            x0 = (uint32_t)seed;
             int k = 1;
             for (uint64_t m = match; m; m &= m - 1) {
                 const int i = __ffsll((long long)m) - 1;
@@ -231,19 +250,20 @@ __global__ void __launch_bounds__(CLUTTER_THREADS) k_clutter(const __grid_consta
                 }
             }
         }
-        // block exclusive scan of cnt
         int incl = cnt;
         for (int o = 1; o < 32; o <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
-        if (lane == 31) warp_sum[warp] = incl;
+        if (lane == 31) warp_sum[pp][warp] = incl;
         __syncthreads();
-        int off = run_base + incl - cnt;
-        for (int w = 0; w < warp; w++) off += warp_sum[w];
-        int total = 0;
-        for (int w = 0; w < CLUTTER_THREADS / 32; w++) total += warp_sum[w];
-        if (first && cnt > 0) {
+        int off = n_out + incl - cnt;
+        for (int w = 0; w < NW; w++) {
+            const int t = warp_sum[pp][w];
+            if (w < warp) off += t;
+            n_out += t;
+        }
+        if (cnt > 0) {
             int k = 1;
             for (uint64_t m = match; m; m &= m - 1) {
                 const int i = __ffsll((long long)m) - 1;
@@ -267,11 +287,8 @@ __global__ void __launch_bounds__(CLUTTER_THREADS) k_clutter(const __grid_consta
                 off++;
             }
         }
-        __syncthreads();
-        if (tid == 0) run_base += total;
     }
-    __syncthreads();
-    if (tid == 0) p.out_count[view] = run_base;
+    if (tid == 0) p.out_count[view] = n_out;
 }
 
 int ensure_buf(pm3d_ctx *ctx, void **buf, size_t *have, size_t need) {
@@ -384,7 +401,7 @@ extern "C" int pm3d_clutter_batch(pm3d_ctx *ctx, const pm3d_clutter_query *queri
         int slots = 256;
         while (slots < 2 * max_samples) slots <<= 1;
         p.slots = slots;
-        const size_t smem = ((size_t)2 * max_samples + slots) * sizeof(uint32_t);
+        const size_t smem = ((size_t)3 * max_samples + slots) * sizeof(uint32_t);
         if (smem > 48 * 1024 && !ctx->clutter_smem_optin) {
             PM3D_CUDA(ctx, cudaFuncSetAttribute(k_clutter, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             ctx->clutter_smem_optin = true;

@@ -727,26 +727,42 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
     }
 }
 
-// ---- per-view FNV-1a style checksum (order-independent combine of per-word hashes)
-__global__ void k_checksum(const uint32_t *frames, uint64_t *out, size_t words_per_view) {
-    const int view = blockIdx.x;
+// ---- per-view FNV-1a style checksum (order-independent combine of per-word hashes: a sum mod 2^64, so the split
+//      into chunks and the order of the atomic adds do not matter)
+__device__ __forceinline__ uint64_t word_hash(uint64_t i, uint32_t v) {
+    uint64_t hsh = 1469598103934665603ull ^ i;
+    hsh *= 1099511628211ull;
+    hsh ^= v;
+    hsh *= 1099511628211ull;
+    return hsh;
+}
+constexpr int CHECKSUM_CHUNK = 256 * 4 * 8;  // words per CTA: 8 uint4 per thread
+__global__ void __launch_bounds__(256) k_checksum(const uint32_t *frames, uint64_t *out, size_t words_per_view) {
+    const int view = blockIdx.y;
     const uint32_t *f = frames + (size_t)view * words_per_view;
+    const size_t lo = (size_t)blockIdx.x * CHECKSUM_CHUNK, hi = min(lo + (size_t)CHECKSUM_CHUNK, words_per_view);
     uint64_t acc = 0;
-    for (size_t i = threadIdx.x; i < words_per_view; i += blockDim.x) {
-        uint64_t hsh = 1469598103934665603ull ^ (uint64_t)i;
-        hsh *= 1099511628211ull;
-        hsh ^= f[i];
-        hsh *= 1099511628211ull;
-        acc += hsh;
+    if ((((uintptr_t)f & 15u) == 0) && hi - lo == (size_t)CHECKSUM_CHUNK) {
+        const uint4 *f4 = reinterpret_cast<const uint4 *>(f + lo);
+#pragma unroll 4
+        for (int k = 0; k < 8; k++) {
+            const int q = k * 256 + threadIdx.x;
+            const uint4 v = __ldg(f4 + q);
+            const size_t i = lo + (size_t)q * 4;
+            acc += word_hash(i, v.x) + word_hash(i + 1, v.y) + word_hash(i + 2, v.z) + word_hash(i + 3, v.w);
+        }
+    } else {
+        for (size_t i = lo + threadIdx.x; i < hi; i += 256) acc += word_hash(i, f[i]);
     }
-    __shared__ uint64_t red[256];
-    red[threadIdx.x] = acc;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ uint64_t red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
-    for (int sft = 128; sft > 0; sft >>= 1) {
-        if (threadIdx.x < sft) red[threadIdx.x] += red[threadIdx.x + sft];
-        __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t t = 0;
+        for (int w = 0; w < 8; w++) t += red[w];
+        atomicAdd(reinterpret_cast<unsigned long long *>(out + view), (unsigned long long)t);
     }
-    if (threadIdx.x == 0) out[view] = red[0];
 }
 
 int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
@@ -799,8 +815,10 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
 }
 
 int pm3d_launch_checksum(pm3d_ctx *ctx, int n_views, const uint8_t *frames) {
-    k_checksum<<<n_views, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(frames), ctx->checksums,
-                                                 (size_t)ctx->w * ctx->h);
+    const size_t words = (size_t)ctx->w * ctx->h;
+    PM3D_CUDA(ctx, cudaMemsetAsync(ctx->checksums, 0, (size_t)n_views * sizeof(uint64_t), ctx->stream));
+    dim3 grid((unsigned)((words + CHECKSUM_CHUNK - 1) / CHECKSUM_CHUNK), (unsigned)n_views);
+    k_checksum<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(frames), ctx->checksums, words);
     ctx->launches++;
     PM3D_CUDA(ctx, cudaGetLastError());
     return PM3D_OK;

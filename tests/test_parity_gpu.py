@@ -272,6 +272,27 @@ def test_frame_tolerance_statement(gpu_ctx):
 # --------------------------------------------------------------------------- API behaviour
 
 
+def host_checksum(frame: np.ndarray) -> int:
+    """The per-view checksum pm3d_frame_checksums defines: sum over words of FNV-1a style hash(word index, word)."""
+    words = np.ascontiguousarray(frame).view(np.uint32).reshape(-1).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        h = (np.uint64(1469598103934665603) ^ np.arange(len(words), dtype=np.uint64)) * np.uint64(1099511628211)
+        h = (h ^ words) * np.uint64(1099511628211)
+        return int(h.sum(dtype=np.uint64))
+
+
+@pytest.mark.parametrize("w,h,n", [(320, 200, 3), (64, 128, 2), (61, 7, 2), (1920, 1080, 1)])
+def test_frame_checksum_is_the_documented_hash(gpu_ctx, w, h, n):
+    """Whole chunks (vector loads), a ragged tail and frames smaller than one chunk."""
+    scene = edge_scene()
+    views = W.make_views(scene, w, h, [(5.5, 5.5, 0.5, 0.3 + 0.9 * i, 0.0) for i in range(n)])
+    gpu_ctx.upload_scene(scene)
+    gpu_ctx.set_view(w, h, n, 1)
+    got = gpu_ctx.render(views, None, np.zeros(n + 1, dtype=np.int32))
+    sums = gpu_ctx.frame_checksums(n)
+    assert [int(v) for v in sums] == [host_checksum(got["rgba"][i]) for i in range(n)]
+
+
 def test_batch_equals_single_and_resident_equals_host(gpu_ctx):
     c = W.config_c4(n_views=12)
     ctx = gpu_ctx

@@ -318,6 +318,35 @@ int pm3d_clutter_batch(pm3d_ctx *ctx, const pm3d_clutter_query *queries, int n, 
  * by polynomial jump-ahead); exported so a test can pin it against known answers. */
 int pm3d_go_rand_cooked(uint64_t *out607);
 
+/* ------------------------------------------------------------------ per-frame sprite list
+ * Game.getRaycastSprites (game/sprites.go:102-145): which sprites a camera's Update gets.  For every camera:
+ * the map's sprites that pass `renderDistance < 0 || sprite is the player's target || PointInProximity(
+ * renderDistance, cam, sprite)` (:113-114; the Chebyshev test of game/model/math.go:93-96 with ceil(distance)), in
+ * the order the host walks g.sprites, then all of its clutter (:121-124), then the extras the game appends
+ * (reticle lead, current nav point, the player sprite under a debug camera, :127-142).  The output is exactly the
+ * `sprites` + `sprite_offset` pair pm3d_render / pm3d_render_resident take, so a headless batch can go from camera
+ * poses to frames without the sprite lists ever leaving HBM. */
+typedef struct pm3d_list_query {
+    double cam_x, cam_y;        /* g.player.CameraPosXY()                             */
+    int32_t target;             /* index of g.player.Target() in `world`, -1 = none   */
+    int32_t _pad;
+} pm3d_list_query;              /* 24 bytes */
+/*   world[n_world]: the map's sprites, shared by all cameras.
+ *   clutter (may be NULL): [n][clutter_stride] records with clutter_count[n] valid ones per camera — the out_sprites /
+ *   out_count of pm3d_clutter_batch.   extras (may be NULL): per-camera extra sprites concatenated, extra_offset[n+1].
+ *   out_sprites[max_total], out_offset[n+1]; out_index[max_total] (may be NULL): where each listed sprite came from —
+ *   world index, -1-k for clutter sprite k of that camera, INT32_MIN+k for its extra k (the host maps the rectangles
+ *   pm3d_render returns back to its Sprite objects with it).  *out_total (host, may be NULL) = out_offset[n].  More
+ *   than max_total sprites is PM3D_ERR_CAPACITY (nothing is written past max_total).
+ *   flags: PM3D_IN_DEVICE (world, queries, clutter*, extras* are device memory), PM3D_OUT_DEVICE (out_sprites,
+ *   out_offset, out_index), PM3D_NO_SYNC (enqueue only: needs PM3D_OUT_DEVICE; out_total and the capacity check are
+ *   skipped, the caller reads out_offset[n] when it needs the total). */
+int pm3d_raycast_sprites_batch(pm3d_ctx *ctx, const pm3d_sprite *world, int n_world, const pm3d_list_query *queries,
+                               int n, double render_distance, const pm3d_sprite *clutter, const int32_t *clutter_count,
+                               int clutter_stride, const pm3d_sprite *extras, const int32_t *extra_offset,
+                               int max_total, pm3d_sprite *out_sprites, int32_t *out_offset, int32_t *out_index,
+                               int32_t *out_total, uint32_t flags);
+
 /* ------------------------------------------------------------------ device memory + timing
  * (so a cgo / ctypes host needs no CUDA binding of its own) */
 int pm3d_device_alloc(pm3d_ctx *ctx, int64_t bytes, void **out);

@@ -339,3 +339,20 @@ def clutter_update(level0: np.ndarray, cell_class: np.ndarray, class_mask: np.nd
           C.c_int32(len(defs)), C.c_int64(map_seed), C.c_double(clutter_distance), _ptr(query), _ptr(out), C.c_int64(cap))
     assert 0 <= n <= cap
     return out[:n]
+
+
+def raycast_sprites(world: np.ndarray, cam_x: float, cam_y: float, render_distance: float, target: int = -1,
+                    clutter: np.ndarray | None = None, extras: np.ndarray | None = None):
+    """Game.getRaycastSprites for ONE camera (game/sprites.go:102-145): (sprites, index)."""
+    world = np.ascontiguousarray(world, dtype=SPRITE_DTYPE).reshape(-1)
+    clutter = np.zeros(0, SPRITE_DTYPE) if clutter is None else np.ascontiguousarray(clutter, dtype=SPRITE_DTYPE).reshape(-1)
+    extras = np.zeros(0, SPRITE_DTYPE) if extras is None else np.ascontiguousarray(extras, dtype=SPRITE_DTYPE).reshape(-1)
+    cap = len(world) + len(clutter) + len(extras)
+    out = np.zeros(max(cap, 1), dtype=SPRITE_DTYPE)
+    idx = np.zeros(max(cap, 1), dtype=np.int32)
+    f = lib().orc_raycast_sprites
+    f.restype = C.c_int32
+    n = f(_ptr(world), C.c_int32(len(world)), C.c_double(cam_x), C.c_double(cam_y), C.c_double(render_distance),
+          C.c_int32(target), _ptr(clutter), C.c_int32(len(clutter)), _ptr(extras), C.c_int32(len(extras)), _ptr(out), _ptr(idx),
+          C.c_int32(cap))
+    return out[:n], idx[:n]

@@ -237,6 +237,12 @@ int64_t orc_clutter_update(const uint16_t *level0, int32_t map_w, int32_t map_h,
                            const uint64_t *class_mask, const orc_clutter_def *defs, int32_t n_defs, int64_t map_seed,
                            double clutter_distance, const orc_clutter_query *q, orc_clutter_sprite *out, int64_t cap);
 
+/* Game.getRaycastSprites (game/sprites.go:102-145) for one camera [V]: map sprites passing the proximity test in
+ * world order, then clutter, then extras.  out_index: world index, -1-k for clutter k, INT32_MIN+k for extra k. */
+int32_t orc_raycast_sprites(const orc_sprite *world, int32_t n_world, double cam_x, double cam_y, double render_distance,
+                            int32_t target, const orc_sprite *clutter, int32_t n_clutter, const orc_sprite *extras,
+                            int32_t n_extras, orc_sprite *out, int32_t *out_index, int32_t cap);
+
 /* Go int(float64) on amd64. */
 int64_t orc_go_int(double v);
 

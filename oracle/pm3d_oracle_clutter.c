@@ -253,3 +253,38 @@ int64_t orc_clutter_update(const uint16_t *level0, int32_t map_w, int32_t map_h,
     free(loaded);
     return n_out;
 }
+
+/* ------------------------------------------------------------------ Game.getRaycastSprites [V] */
+
+/* model.PointInProximity (game/model/math.go:93-96) */
+static int point_in_proximity(double distance, double srcX, double srcY, double tgtX, double tgtY) {
+    distance = ceil(distance);
+    return fabs(tgtX - srcX) <= distance && fabs(tgtY - srcY) <= distance;
+}
+
+/* Game.getRaycastSprites (game/sprites.go:102-145) for one camera: the map sprites that pass
+ * `renderDistance < 0 || isTarget || PointInProximity(renderDistance, cam, sprite)` in the order the host walks
+ * g.sprites ([D]: sync.Map.Range has no order), then every clutter sprite (:121-124), then the extras the game
+ * appends (reticle lead, current nav point, player sprite with a debug camera, :127-142).  out_index: world index,
+ * -1-k for clutter k, INT32_MIN+k for extra k.  Returns the count (writes <= cap). */
+int32_t orc_raycast_sprites(const orc_sprite *world, int32_t n_world, double cam_x, double cam_y, double render_distance,
+                            int32_t target, const orc_sprite *clutter, int32_t n_clutter, const orc_sprite *extras,
+                            int32_t n_extras, orc_sprite *out, int32_t *out_index, int32_t cap) {
+    int32_t n = 0;
+    for (int32_t i = 0; i < n_world; i++) {
+        const int doSprite = render_distance < 0 || target == i ||
+                             point_in_proximity(render_distance, cam_x, cam_y, world[i].x, world[i].y);
+        if (!doSprite) continue;
+        if (n < cap) { out[n] = world[i]; out_index[n] = i; }
+        n++;
+    }
+    for (int32_t k = 0; k < n_clutter; k++) {
+        if (n < cap) { out[n] = clutter[k]; out_index[n] = -1 - k; }
+        n++;
+    }
+    for (int32_t k = 0; k < n_extras; k++) {
+        if (n < cap) { out[n] = extras[k]; out_index[n] = INT32_MIN + k; }
+        n++;
+    }
+    return n;
+}

@@ -105,6 +105,9 @@ CLUTTER_SPRITE_DTYPE = np.dtype(
 )
 assert CLUTTER_SPRITE_DTYPE.itemsize == 32
 
+LIST_QUERY_DTYPE = np.dtype([("cam_x", "<f8"), ("cam_y", "<f8"), ("target", "<i4"), ("_pad", "<i4")])
+assert LIST_QUERY_DTYPE.itemsize == 24
+
 # every symbol include/pm3d.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -138,6 +141,8 @@ SYMBOLS = {
     "pm3d_upload_clutter": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int64]),
     "pm3d_clutter_batch": (C.c_int, [_P, _P, C.c_int, C.c_double, C.c_int, _P, _P, _P, C.c_uint32]),
     "pm3d_go_rand_cooked": (C.c_int, [_P]),
+    "pm3d_raycast_sprites_batch": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_double, _P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _P,
+                                             C.POINTER(C.c_int32), C.c_uint32]),
     "pm3d_generate_wall_collision_lines": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double, _P, C.c_int]),
     "pm3d_device_alloc": (C.c_int, [_P, C.c_int64, C.POINTER(_P)]),
     "pm3d_device_free": (C.c_int, [_P, _P]),

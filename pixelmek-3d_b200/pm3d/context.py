@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (CLUTTER_DEF_DTYPE, CLUTTER_QUERY_DTYPE, CLUTTER_SPRITE_DTYPE, COLLIDER_DTYPE, COLUMN_DTYPE, CONV_DTYPE, MOVE_RESULT_DTYPE, MOVER_DTYPE, SPRITE_DTYPE, VIEW_DTYPE,
+from ._lib import (LIST_QUERY_DTYPE, CLUTTER_DEF_DTYPE, CLUTTER_QUERY_DTYPE, CLUTTER_SPRITE_DTYPE, COLLIDER_DTYPE, COLUMN_DTYPE, CONV_DTYPE, MOVE_RESULT_DTYPE, MOVER_DTYPE, SPRITE_DTYPE, VIEW_DTYPE,
                    Pm3dError, ptr)
 from .scene import SceneData
 
@@ -248,6 +248,37 @@ class Context:
         self._check(self.lib.pm3d_clutter_batch(self.h, ptr(queries), n, float(clutter_distance), int(max_per_view),
                                                 ptr(counts), ptr(recs), ptr(sprites), 0), "pm3d_clutter_batch")
         return (counts, recs, sprites) if want_sprites else (counts, recs)
+
+    def raycast_sprites_batch(self, world: np.ndarray, queries: np.ndarray, render_distance: float, clutter=None,
+                              extras=None, max_total: int | None = None):
+        """Game.getRaycastSprites for every camera of `queries`.  clutter = (counts[n], sprites[n][stride]) as
+        clutter_batch(..., want_sprites=True) returns them; extras = list of per-camera pm3d_sprite arrays.
+        Returns (sprites, sprite_offset, index): the concatenated lists pm3d_render takes."""
+        world = np.ascontiguousarray(world, dtype=SPRITE_DTYPE).reshape(-1)
+        queries = np.ascontiguousarray(queries, dtype=LIST_QUERY_DTYPE).reshape(-1)
+        n = len(queries)
+        cl_cnt = cl_spr = ex_off = ex_spr = None
+        stride = 0
+        if clutter is not None:
+            cl_cnt = np.ascontiguousarray(clutter[0], dtype=np.int32).reshape(n)
+            cl_spr = np.ascontiguousarray(clutter[1], dtype=SPRITE_DTYPE).reshape(n, -1)
+            stride = cl_spr.shape[1]
+        if extras is not None:
+            ex_off = np.concatenate([[0], np.cumsum([len(e) for e in extras])]).astype(np.int32)
+            ex_spr = np.ascontiguousarray(np.concatenate(list(extras) + [np.zeros(0, SPRITE_DTYPE)]), dtype=SPRITE_DTYPE)
+        if max_total is None:
+            max_total = n * len(world) + (int(np.minimum(cl_cnt, stride).clip(0).sum()) if cl_cnt is not None else 0) + \
+                (int(ex_off[-1]) if ex_off is not None else 0)
+        max_total = max(int(max_total), 1)
+        out = np.zeros(max_total, dtype=SPRITE_DTYPE)
+        off = np.zeros(n + 1, dtype=np.int32)
+        idx = np.zeros(max_total, dtype=np.int32)
+        total = C.c_int32(0)
+        self._check(self.lib.pm3d_raycast_sprites_batch(self.h, ptr(world) if len(world) else None, len(world), ptr(queries), n,
+                                                        float(render_distance), ptr(cl_spr), ptr(cl_cnt), stride, ptr(ex_spr), ptr(ex_off),
+                                                        max_total, ptr(out), ptr(off), ptr(idx), C.byref(total), 0),
+                    "pm3d_raycast_sprites_batch")
+        return out[:total.value], off, idx[:total.value]
 
     # ------------------------------------------------------------------ device memory + timers
     def device_alloc(self, nbytes: int) -> int:

@@ -1,0 +1,119 @@
+"""GPU parity tests of pm3d_raycast_sprites_batch (csrc/sprite_list_kernel.cu) against the oracle's restatement of
+Game.getRaycastSprites, and of the device-resident chain camera poses -> clutter -> sprite lists -> frames."""
+import numpy as np
+import pytest
+
+import pm3d
+from conftest import orc_camera
+from oracle import oracle as O
+from pm3d import clutter as cl
+from pm3d import sprites as sp
+from pm3d import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rd,n_world", [(25.0, 400), (2.3, 400), (-1.0, 77), (100.0, 1), (7.5, 0), (0.0, 130)])
+def test_lists_equal_the_oracle(gpu_ctx, rd, n_world):
+    scene, g = W.proving_grounds_scene()
+    world = W.golden_sprites(scene, g)[:n_world]
+    rng = W.SplitMix64(int(rd * 10) + n_world + 1000)
+    n = 70
+    u = rng.uniform(n * 4).reshape(n, 4)
+    cams = [(500 * a - 0.5, 500 * b - 0.5) for a, b, _, _ in u]
+    if n_world:
+        cams[3] = (float(world[0]["x"]) - np.ceil(rd), float(world[0]["y"]))        # exactly on the proximity border
+        cams[4] = (float(world[0]["x"]) - np.ceil(rd) - 1e-9, float(world[0]["y"]))  # just outside
+    targets = [int(c * (n_world + 1)) - 1 for _, _, c, _ in u]
+    clutter_n = np.array([int(d * 9) for _, _, _, d in u], dtype=np.int32)
+    clutter_n[5] = 12                                                                # more than the stride: clamped
+    clutter = np.resize(W.golden_sprites(scene, g)[::-1], n * 8).reshape(n, 8).copy()
+    extras = [W.golden_sprites(scene, g)[i:i + (i % 3)] for i in range(n)]
+    q = sp.list_queries(cams, targets)
+    got, off, idx = gpu_ctx.raycast_sprites_batch(world, q, rd, (clutter_n, clutter), extras)
+    assert off[0] == 0 and off[-1] == len(got)
+    for i in range(n):
+        want, widx = O.raycast_sprites(world.astype(O.SPRITE_DTYPE), cams[i][0], cams[i][1], rd, targets[i],
+                                       clutter[i, :min(clutter_n[i], 8)].astype(O.SPRITE_DTYPE), extras[i].astype(O.SPRITE_DTYPE))
+        assert off[i + 1] - off[i] == len(want), f"camera {i}"
+        assert got[off[i]:off[i + 1]].tobytes() == want.tobytes(), f"camera {i}"
+        assert np.array_equal(idx[off[i]:off[i + 1]], widx)
+    # without clutter / extras
+    got2, off2, idx2 = gpu_ctx.raycast_sprites_batch(world, q, rd)
+    for i in range(n):
+        want, widx = O.raycast_sprites(world.astype(O.SPRITE_DTYPE), cams[i][0], cams[i][1], rd, targets[i])
+        assert got2[off2[i]:off2[i + 1]].tobytes() == want.tobytes() and np.array_equal(idx2[off2[i]:off2[i + 1]], widx)
+
+
+def test_capacity_and_arguments(gpu_ctx):
+    scene, g = W.proving_grounds_scene()
+    world = W.golden_sprites(scene, g)
+    q = sp.list_queries([(30.0, 30.0), (31.0, 29.0)])
+    got, off, _ = gpu_ctx.raycast_sprites_batch(world, q, -1.0)
+    assert off.tolist() == [0, len(world), 2 * len(world)]
+    with pytest.raises(pm3d.Pm3dError, match="max_total"):
+        gpu_ctx.raycast_sprites_batch(world, q, -1.0, max_total=2 * len(world) - 1)
+    with pytest.raises(pm3d.Pm3dError):
+        gpu_ctx.raycast_sprites_batch(world, q, float("nan"))
+    one, idx = sp.getRaycastSprites(gpu_ctx, world, 30.0, 30.0, 10.0, target=len(world) - 1, clutter=world[:3], extras=world[5:6])
+    want, widx = O.raycast_sprites(world.astype(O.SPRITE_DTYPE), 30.0, 30.0, 10.0, len(world) - 1, world[:3].astype(O.SPRITE_DTYPE),
+                                   world[5:6].astype(O.SPRITE_DTYPE))
+    assert one.tobytes() == want.tobytes() and np.array_equal(idx, widx)
+
+
+def test_resident_chain_from_poses_to_frames(gpu_ctx):
+    """Camera poses -> pm3d_clutter_batch -> pm3d_raycast_sprites_batch -> pm3d_render_resident with every
+    intermediate in HBM; the frames equal the oracle's frames built from the oracle's clutter and sprite lists."""
+    ctx = gpu_ctx
+    L = pm3d._lib
+    scene, g = W.proving_grounds_scene()
+    scene.sheets = list(scene.sheets) + [W.sprite_sheet(18, 18, 41), W.sprite_sheet(24, 24, 42)]
+    i_rock, i_bush = len(scene.sheets) - 2, len(scene.sheets) - 1
+    ctx.upload_scene(scene)
+    clutter = [cl.MapClutter(str(im), float(f), float(h), str(m) or None) for im, m, f, h in
+               zip(g["clutter_image"], g["clutter_match"], g["clutter_frequency"], g["clutter_height"])]
+    sheets = {clutter[0].image: (i_rock, 18, 18), clutter[1].image: (i_bush, 24, 24)}
+    defs, cls, masks = cl.resolve_clutter(clutter, g["floor_grid"], [str(s) for s in g["floor_images"]], sheets)
+    ctx.upload_clutter(defs, cls, masks, int(g["map_seed"]))
+    world = W.golden_sprites(scene, g)
+    n, w, h, rd, cdist = 6, 256, 144, 40.0, 12.0
+    poses = [(31.5, 3.5, 0.5, W.cardinal_to_angle(45.0), 0.0)] + W.free_cell_poses(scene, n - 1, 99)
+    poses = [(p[0], p[1], 0.5, p[3], 0.0) for p in poses]
+    views = W.make_views(scene, w, h, poses, render_distance=rd)
+    cq = cl.clutter_queries([(p[0], p[1], p[3]) for p in poses], 70.0)
+    lq = sp.list_queries([(p[0], p[1]) for p in poses])
+    stride = 21 * (int(cdist) + 1) * len(clutter)
+    max_total = n * (len(world) + stride)
+    ctx.set_view(w, h, n, max_total)
+    bufs = dict(views=views.nbytes, cq=cq.nbytes, lq=lq.nbytes, world=world.nbytes, cnt=4 * n, rec=32 * n * stride,
+                cspr=64 * n * stride, spr=64 * max_total, off=4 * (n + 1), out=n * w * h * 4)
+    d = {k: ctx.device_alloc(v) for k, v in bufs.items()}
+    try:
+        ctx.h2d(d["views"], views); ctx.h2d(d["cq"], cq); ctx.h2d(d["lq"], lq); ctx.h2d(d["world"], world)
+        flags = L.PM3D_IN_DEVICE | L.PM3D_OUT_DEVICE | L.PM3D_NO_SYNC
+        ctx._check(ctx.lib.pm3d_clutter_batch(ctx.h, d["cq"], n, cdist, stride, d["cnt"], d["rec"], d["cspr"], flags), "clutter")
+        ctx._check(ctx.lib.pm3d_raycast_sprites_batch(ctx.h, d["world"], len(world), d["lq"], n, rd, d["cspr"], d["cnt"], stride,
+                                                      None, None, max_total, d["spr"], d["off"], None, None, flags), "list")
+        off = np.zeros(n + 1, dtype=np.int32)
+        ctx.sync(); ctx.d2h(off, d["off"])               # the one host read: the total the render call is told
+        ctx.render_resident(d["views"], n, d["spr"], d["off"], int(off[-1]), d["out"])
+        frames = np.empty((n, h, w, 4), dtype=np.uint8)
+        ctx.sync(); ctx.d2h(frames, d["out"])
+    finally:
+        for p in d.values():
+            ctx.device_free(p)
+    osc = O.Scene(scene)
+    n_clutter_seen = 0
+    for i, p in enumerate(poses):
+        recs = O.clutter_update(scene.grid[0], cls, masks, defs.astype(O.CLUTTER_DEF_DTYPE), int(g["map_seed"]), cdist,
+                                cq[i:i + 1].astype(O.CLUTTER_QUERY_DTYPE))
+        csp = np.zeros(len(recs), dtype=O.SPRITE_DTYPE)
+        csp["x"], csp["y"], csp["focusable"] = recs["x"], recs["y"], 1
+        for k in ("scale", "sheet", "rx0", "ry0", "rx1", "ry1"):
+            csp[k] = defs[k][recs["def"]]
+        lst, _ = O.raycast_sprites(world.astype(O.SPRITE_DTYPE), p[0], p[1], rd, -1, csp)
+        assert off[i + 1] - off[i] == len(lst)
+        ref = O.render(osc, orc_camera(views[i], w, h), lst, threads=4)
+        assert np.array_equal(frames[i], ref["rgba"]), f"view {i}"
+        n_clutter_seen += len(recs)
+    assert n_clutter_seen > 300

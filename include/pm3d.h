@@ -152,8 +152,16 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
  * i+1; results are valid after pm3d_sync.  Call it after pm3d_set_view.  PM3D_OPT_OVERLAP (default 1): the
  * per-frame intermediate buffers exist twice and the cast/setup launch of frame i+1 runs on a second stream
  * beside the compose launch of frame i (enqueue-only callers: pm3d_render_resident, PM3D_NO_SYNC); 0 = one
- * set of buffers, one stream. */
-enum { PM3D_OPT_KEEP_COLUMNS = 1, PM3D_OPT_FORCE_PAINTER = 2, PM3D_OPT_PIPELINE = 3, PM3D_OPT_OVERLAP = 4 };
+ * set of buffers, one stream.
+ * PM3D_OPT_LANES = n (1..4, default 1; needs PM3D_OPT_OVERLAP = 1): pm3d_render_resident deals successive calls
+ * round-robin to n lanes, each with its own streams and intermediate buffers, so INDEPENDENT frame batches (different
+ * cameras, or frames whose results are only read after pm3d_sync) run concurrently: a single 1080p frame is two
+ * launches that leave most of the chip idle (24 CTAs of serial ray walks, then a compose launch whose tail is a few
+ * sprite-heavy warps), three lanes nearly double the frames per second.  Calls on one lane stay ordered; calls on
+ * different lanes are unordered among themselves, so two in-flight calls must not write the same output buffer.
+ * Results of "the last render" (pm3d_download_results, pm3d_frame_checksums, pm3d_present with d_src NULL) wait for
+ * that call's lane; pm3d_timer_* bracket all lanes.  pm3d_render (host buffers) always uses lane 0. */
+enum { PM3D_OPT_KEEP_COLUMNS = 1, PM3D_OPT_FORCE_PAINTER = 2, PM3D_OPT_PIPELINE = 3, PM3D_OPT_OVERLAP = 4, PM3D_OPT_LANES = 5 };
 int pm3d_set_option(pm3d_ctx *ctx, int option, int value);
 
 /* ------------------------------------------------------------------ frame path

@@ -798,17 +798,18 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     const int cta_warps = rows >= 8 ? 2 : 4;
     const bool with_sprites = ctx->cur_n_sprites > 0;  // latency-mode sprite walk (records in shared memory)
     dim3 block(cta_warps * 32), grid(ctx->n_groups, (ctx->h + cta_warps * rows - 1) / (cta_warps * rows), n_views);
-    pm3d_kt_mark(ctx, 2, 0, ctx->stream);
-    if (rows == 16) k_compose<16, 8, 2><<<grid, block, 0, ctx->stream>>>(p);
-    else if (rows == 8 && minb == 8) k_compose<8, 8, 2><<<grid, block, 0, ctx->stream>>>(p);
-    else if (rows == 8) k_compose<8, 6, 2><<<grid, block, 0, ctx->stream>>>(p);
-    else if (rows == 4 && minb == 8) k_compose<4, 8, 4><<<grid, block, 0, ctx->stream>>>(p);
-    else if (rows == 4 && with_sprites) k_compose<4, 6, 4, true><<<grid, block, 0, ctx->stream>>>(p);
-    else if (rows == 4) k_compose<4, 6, 4><<<grid, block, 0, ctx->stream>>>(p);
-    else if (minb == 8) k_compose<2, 8, 4><<<grid, block, 0, ctx->stream>>>(p);
-    else if (with_sprites) k_compose<2, 6, 4, true><<<grid, block, 0, ctx->stream>>>(p);
-    else k_compose<2, 6, 4><<<grid, block, 0, ctx->stream>>>(p);
-    pm3d_kt_mark(ctx, 2, 1, ctx->stream);
+    cudaStream_t cstream = ctx->cur_cstream ? ctx->cur_cstream : ctx->stream;  // the lane of this frame batch
+    pm3d_kt_mark(ctx, 2, 0, cstream);
+    if (rows == 16) k_compose<16, 8, 2><<<grid, block, 0, cstream>>>(p);
+    else if (rows == 8 && minb == 8) k_compose<8, 8, 2><<<grid, block, 0, cstream>>>(p);
+    else if (rows == 8) k_compose<8, 6, 2><<<grid, block, 0, cstream>>>(p);
+    else if (rows == 4 && minb == 8) k_compose<4, 8, 4><<<grid, block, 0, cstream>>>(p);
+    else if (rows == 4 && with_sprites) k_compose<4, 6, 4, true><<<grid, block, 0, cstream>>>(p);
+    else if (rows == 4) k_compose<4, 6, 4><<<grid, block, 0, cstream>>>(p);
+    else if (minb == 8) k_compose<2, 8, 4><<<grid, block, 0, cstream>>>(p);
+    else if (with_sprites) k_compose<2, 6, 4, true><<<grid, block, 0, cstream>>>(p);
+    else k_compose<2, 6, 4><<<grid, block, 0, cstream>>>(p);
+    pm3d_kt_mark(ctx, 2, 1, cstream);
     ctx->launches++;
     PM3D_CUDA(ctx, cudaGetLastError());
     return PM3D_OK;

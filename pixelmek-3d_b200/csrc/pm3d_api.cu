@@ -31,6 +31,29 @@ static int dev_realloc(pm3d_ctx *ctx, T **ptr, size_t count) {
     return PM3D_OK;
 }
 
+// every stream a frame batch may still be running on
+static cudaError_t sync_frame_streams(pm3d_ctx *ctx) {
+    cudaError_t e = cudaSuccess, r;
+    if (ctx->front_stream && (r = cudaStreamSynchronize(ctx->front_stream)) != cudaSuccess) e = r;
+    if (ctx->front_stream_lo && (r = cudaStreamSynchronize(ctx->front_stream_lo)) != cudaSuccess) e = r;
+    for (int l = 1; l < PM3D_MAX_LANES; l++) {
+        if (ctx->lane_fstream[l] && (r = cudaStreamSynchronize(ctx->lane_fstream[l])) != cudaSuccess) e = r;
+        if (ctx->lane_cstream[l] && (r = cudaStreamSynchronize(ctx->lane_cstream[l])) != cudaSuccess) e = r;
+    }
+    if ((r = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) e = r;
+    return e;
+}
+// readers of the last frame's results (rects, convergence, columns, checksum, presentation) enqueue on the main
+// stream: when that frame ran on another lane they wait for it first
+static cudaError_t wait_last_frame(pm3d_ctx *ctx) {
+    if (ctx->last_cstream && ctx->last_cstream != ctx->stream) return cudaStreamSynchronize(ctx->last_cstream);
+    return cudaSuccess;
+}
+int pm3d_wait_last_frame(pm3d_ctx *ctx) {
+    PM3D_CUDA(ctx, wait_last_frame(ctx));
+    return PM3D_OK;
+}
+
 extern "C" {
 
 int pm3d_version(void) { return PM3D_VERSION; }
@@ -77,9 +100,7 @@ int pm3d_create(int device, void *stream, pm3d_ctx **out) {
 void pm3d_destroy(pm3d_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    if (ctx->front_stream) cudaStreamSynchronize(ctx->front_stream);
-    if (ctx->front_stream_lo) cudaStreamSynchronize(ctx->front_stream_lo);
+    sync_frame_streams(ctx);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     void *ptrs[] = {ctx->grid, ctx->dist, ctx->wall_lut, ctx->atlas, ctx->floor_tiles, ctx->sheet_pixels, ctx->sheet_info,
                     ctx->views, ctx->sprites, ctx->sprite_offset, ctx->frame, ctx->checksums, ctx->segs, ctx->seg_irect,
@@ -97,6 +118,11 @@ void pm3d_destroy(pm3d_ctx *ctx) {
     }
     if (ctx->front_stream) cudaStreamDestroy(ctx->front_stream);
     if (ctx->front_stream_lo) cudaStreamDestroy(ctx->front_stream_lo);
+    for (int l = 1; l < PM3D_MAX_LANES; l++) {
+        if (ctx->lane_fstream[l]) cudaStreamDestroy(ctx->lane_fstream[l]);
+        if (ctx->lane_cstream[l]) cudaStreamDestroy(ctx->lane_cstream[l]);
+        if (ctx->lane_join[l]) cudaEventDestroy(ctx->lane_join[l]);
+    }
     for (int i = 0; i < 16; i++) {
         if (ctx->ev_start[i]) cudaEventDestroy(ctx->ev_start[i]);
         if (ctx->ev_stop[i]) cudaEventDestroy(ctx->ev_stop[i]);
@@ -115,9 +141,7 @@ void pm3d_destroy(pm3d_ctx *ctx) {
 
 int pm3d_sync(pm3d_ctx *ctx) {
     if (!ctx) return PM3D_ERR_ARG;
-    if (ctx->front_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->front_stream));
-    if (ctx->front_stream_lo) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->front_stream_lo));
-    PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PM3D_CUDA(ctx, sync_frame_streams(ctx));
     if (ctx->copy_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     return PM3D_OK;
 }
@@ -297,11 +321,18 @@ int pm3d_set_option(pm3d_ctx *ctx, int option, int value) {
         return PM3D_OK;
     case PM3D_OPT_OVERLAP:
         PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
-        if (ctx->front_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->front_stream));
-    if (ctx->front_stream_lo) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->front_stream_lo));
-        PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        PM3D_CUDA(ctx, sync_frame_streams(ctx));
         ctx->n_sets = value ? 2 : 1;
         ctx->cur_set = 0;
+        if (ctx->w > 0) return pm3d_set_view(ctx, ctx->w, ctx->h, ctx->max_views, ctx->max_sprites);
+        return PM3D_OK;
+    case PM3D_OPT_LANES:
+        if (value < 1 || value > PM3D_MAX_LANES) return pm3d_fail(ctx, PM3D_ERR_ARG, "lanes must be 1..%d", PM3D_MAX_LANES);
+        if (!ctx->own_stream && value > 1) return pm3d_fail(ctx, PM3D_ERR_ARG, "a ctx on a caller stream has one lane");
+        PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+        PM3D_CUDA(ctx, sync_frame_streams(ctx));
+        ctx->n_lanes = value;
+        ctx->lane_pos = 0;
         if (ctx->w > 0) return pm3d_set_view(ctx, ctx->w, ctx->h, ctx->max_views, ctx->max_sprites);
         return PM3D_OK;
     case PM3D_OPT_PIPELINE: {
@@ -337,9 +368,7 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
         return pm3d_fail(ctx, PM3D_ERR_ARG, "bad view size / capacity");
     if (ctx->num_levels < 1) return pm3d_fail(ctx, PM3D_ERR_ARG, "pm3d_upload_grid must precede pm3d_set_view");
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (ctx->front_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->front_stream));
-    if (ctx->front_stream_lo) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->front_stream_lo));
-    PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PM3D_CUDA(ctx, sync_frame_streams(ctx));
     if (ctx->copy_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     ctx->w = width; ctx->h = height; ctx->max_views = max_views; ctx->max_sprites = max_sprites_total;
     ctx->n_groups = (width + 63) / 64;
@@ -356,10 +385,19 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
         PM3D_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->front_stream, cudaStreamNonBlocking, prio_hi));
         PM3D_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->front_stream_lo, cudaStreamNonBlocking));
     }
-    for (int k = 0; k < 2; k++) {
+    for (int l = 1; l < ctx->n_lanes; l++) {
+        if (ctx->lane_cstream[l]) continue;
+        int prio_lo = 0, prio_hi = 0;
+        PM3D_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        PM3D_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lane_cstream[l], cudaStreamNonBlocking));
+        PM3D_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->lane_fstream[l], cudaStreamNonBlocking, prio_hi));
+        PM3D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_join[l], cudaEventDisableTiming));
+    }
+    const int sets_in_use = ctx->n_sets > 1 ? 2 * ctx->n_lanes : 1;
+    for (int k = 0; k < 2 * PM3D_MAX_LANES; k++) {
         pm3d_ctx::FrameSet &fs = ctx->sets[k];
         pm3d_load_set(ctx, k);
-        if (k >= ctx->n_sets) {  // PM3D_OPT_OVERLAP = 0: the second set is released
+        if (k >= sets_in_use) {  // PM3D_OPT_OVERLAP = 0 / fewer lanes: the other sets are released
 #define X(f) if (ctx->f) { PM3D_CUDA(ctx, cudaFree(ctx->f)); ctx->f = nullptr; }
             PM3D_FRAME_FIELDS(X)
 #undef X
@@ -398,6 +436,9 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
         }
     }
     ctx->cur_set = 0;
+    for (int l = 0; l < PM3D_MAX_LANES; l++) ctx->lane_cur[l] = 0;
+    ctx->lane_pos = 0;
+    ctx->cur_cstream = ctx->last_cstream = ctx->stream;
     pm3d_load_set(ctx, 0);
     if ((rc = dev_realloc(ctx, &ctx->frame, V * W * H * 4))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->checksums, V))) return rc;
@@ -416,14 +457,17 @@ static int render_core(pm3d_ctx *ctx, int n_views, int n_sprites, uint8_t *targe
     pm3d_ctx::FrameSet &fs = ctx->sets[ctx->cur_set];
     const bool overlap = ctx->n_sets > 1;
     cudaStream_t fstream = overlap ? ctx->cur_fstream : ctx->stream;
+    cudaStream_t cstream = overlap ? ctx->cur_cstream : ctx->stream;
+    ctx->cur_cstream = cstream;
     ctx->cur_n_sprites = n_sprites;
     if ((rc = pm3d_launch_front(ctx, n_views, fstream))) return rc;
     if (overlap) {
         PM3D_CUDA(ctx, cudaEventRecord(fs.ev_front, fstream));
-        PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, fs.ev_front, 0));
+        PM3D_CUDA(ctx, cudaStreamWaitEvent(cstream, fs.ev_front, 0));
     }
     if ((rc = pm3d_launch_compose(ctx, n_views, target))) return rc;
-    if (overlap) PM3D_CUDA(ctx, cudaEventRecord(fs.ev_compose, ctx->stream));
+    if (overlap) PM3D_CUDA(ctx, cudaEventRecord(fs.ev_compose, cstream));
+    ctx->last_cstream = cstream;
     if (ctx->kt_on && ctx->kt_n < ctx->kt_cap) ctx->kt_n++;
     ctx->last_frame = target;
     ctx->last_views = n_views;
@@ -434,16 +478,24 @@ static int render_core(pm3d_ctx *ctx, int n_views, int n_sprites, uint8_t *targe
 // Select the frame set of the next frame: the named per-frame fields alias it from here on.  Its previous
 // user (the compose kernel two frames back) must be done before the front stream writes into it, and
 // everything enqueued on the main stream so far (uploads, caller-visible ordering) precedes the frame.
-static int pm3d_begin_frame(pm3d_ctx *ctx, int n_views, cudaStream_t *fstream) {
+static int pm3d_begin_frame(pm3d_ctx *ctx, int n_views, cudaStream_t *fstream, int lane = 0) {
     if (ctx->n_sets > 1) {
-        ctx->cur_set = (ctx->cur_set + 1) % ctx->n_sets;
+        ctx->lane_cur[lane] ^= 1;
+        ctx->cur_set = 2 * lane + ctx->lane_cur[lane];
         pm3d_load_set(ctx, ctx->cur_set);
-        // a batch whose front launch fills the chip by itself gains nothing from jumping the queue
-        const long long front_ctas = (long long)n_views * ctx->num_levels * ctx->n_groups / 4;
-        ctx->cur_fstream = front_ctas >= 4LL * ctx->sm_count ? ctx->front_stream_lo : ctx->front_stream;
+        if (lane == 0) {
+            // a batch whose front launch fills the chip by itself gains nothing from jumping the queue
+            const long long front_ctas = (long long)n_views * ctx->num_levels * ctx->n_groups / 4;
+            ctx->cur_fstream = front_ctas >= 4LL * ctx->sm_count ? ctx->front_stream_lo : ctx->front_stream;
+            ctx->cur_cstream = ctx->stream;
+        } else {
+            ctx->cur_fstream = ctx->lane_fstream[lane];
+            ctx->cur_cstream = ctx->lane_cstream[lane];
+        }
         PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->cur_fstream, ctx->sets[ctx->cur_set].ev_compose, 0));
         *fstream = ctx->cur_fstream;
     } else {
+        ctx->cur_cstream = ctx->stream;
         *fstream = ctx->stream;
     }
     return PM3D_OK;
@@ -473,7 +525,12 @@ int pm3d_render_resident(pm3d_ctx *ctx, const pm3d_view *d_views, int n_views, c
     if (n_sprites_total > ctx->max_sprites) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "%d sprites > max_sprites_total %d", n_sprites_total, ctx->max_sprites);
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t fstream;
-    if ((rc = pm3d_begin_frame(ctx, n_views, &fstream))) return rc;
+    int lane = 0;
+    if (ctx->n_lanes > 1 && ctx->n_sets > 1) {  // independent frames: next lane
+        lane = ctx->lane_pos;
+        ctx->lane_pos = (lane + 1) % ctx->n_lanes;
+    }
+    if ((rc = pm3d_begin_frame(ctx, n_views, &fstream, lane))) return rc;
     ctx->cur_views = d_views; ctx->cur_sprites = d_sprites; ctx->cur_offset = d_sprite_offset;
     return render_core(ctx, n_views, n_sprites_total, d_out_rgba);
 }
@@ -482,6 +539,7 @@ int pm3d_download_results(pm3d_ctx *ctx, pm3d_rect *out_rects, pm3d_convergence 
     if (!ctx) return PM3D_ERR_ARG;
     if (ctx->last_views < 1) return pm3d_fail(ctx, PM3D_ERR_ARG, "nothing rendered");
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    PM3D_CUDA(ctx, wait_last_frame(ctx));
     if (out_rects && ctx->last_sprites)
         PM3D_CUDA(ctx, cudaMemcpyAsync(out_rects, ctx->rects, (size_t)ctx->last_sprites * sizeof(pm3d_rect), cudaMemcpyDeviceToHost, ctx->stream));
     if (out_conv)
@@ -617,6 +675,7 @@ int pm3d_download_columns(pm3d_ctx *ctx, int view, pm3d_column *columns, double 
     if (!ctx) return PM3D_ERR_ARG;
     if (view < 0 || view >= ctx->last_views) return pm3d_fail(ctx, PM3D_ERR_ARG, "view %d not rendered", view);
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    PM3D_CUDA(ctx, wait_last_frame(ctx));
     if (columns) {
         if (!ctx->keep_columns || !ctx->dbg_cols) return pm3d_fail(ctx, PM3D_ERR_ARG, "PM3D_OPT_KEEP_COLUMNS is off");
         const size_t cnt = (size_t)ctx->num_levels * ctx->w;
@@ -632,6 +691,7 @@ int pm3d_frame_checksums(pm3d_ctx *ctx, int n_views, uint64_t *out, uint32_t fla
     if (!ctx) return PM3D_ERR_ARG;
     if (!ctx->last_frame || n_views < 1 || n_views > ctx->last_views || !out) return pm3d_fail(ctx, PM3D_ERR_ARG, "nothing rendered / bad arguments");
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    PM3D_CUDA(ctx, wait_last_frame(ctx));
     int rc = pm3d_launch_checksum(ctx, n_views, ctx->last_frame);
     if (rc) return rc;
     if (flags & PM3D_OUT_DEVICE)
@@ -790,10 +850,22 @@ int pm3d_timer_start(pm3d_ctx *ctx, int slot) {
         PM3D_CUDA(ctx, cudaEventCreate(&ctx->ev_stop[slot]));
     }
     PM3D_CUDA(ctx, cudaEventRecord(ctx->ev_start[slot], ctx->stream));
+    // fork: nothing of the timed region may start on another lane before the start event
+    for (int l = 1; l < ctx->n_lanes; l++) {
+        if (!ctx->lane_cstream[l]) continue;
+        PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_cstream[l], ctx->ev_start[slot], 0));
+        PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_fstream[l], ctx->ev_start[slot], 0));
+    }
     return PM3D_OK;
 }
 int pm3d_timer_stop(pm3d_ctx *ctx, int slot) {
     if (!ctx || slot < 0 || slot >= 16 || !ctx->ev_stop[slot]) return PM3D_ERR_ARG;
+    // join: the stop event follows the last frame of every lane
+    for (int l = 1; l < ctx->n_lanes; l++) {
+        if (!ctx->lane_cstream[l]) continue;
+        PM3D_CUDA(ctx, cudaEventRecord(ctx->lane_join[l], ctx->lane_cstream[l]));
+        PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lane_join[l], 0));
+    }
     PM3D_CUDA(ctx, cudaEventRecord(ctx->ev_stop[slot], ctx->stream));
     return PM3D_OK;
 }

@@ -62,6 +62,7 @@ struct SheetInfo {
 
 // ------------------------------------------------------------------ ctx
 
+#define PM3D_MAX_LANES 4
 struct pm3d_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -135,8 +136,18 @@ struct pm3d_ctx {
         cudaEvent_t ev_stage = nullptr;    // the H2D out of `stage` has executed
         cudaEvent_t ev_front = nullptr;    // front kernel done (recorded on front_stream)
         cudaEvent_t ev_compose = nullptr;  // compose done and the set's results read: the set may be rewritten
-    } sets[2];
+    } sets[2 * PM3D_MAX_LANES];
     int n_sets = 2, cur_set = 0;
+    // PM3D_OPT_LANES: independent frames of enqueue-only callers (pm3d_render_resident) are dealt round-robin to
+    // n_lanes lanes, each with its own compose stream, front stream and pair of frame sets (lane l owns sets 2l and
+    // 2l+1; lane 0 is `stream` / `front_stream`), so the tail of one frame's compose launch and the 24-CTA front
+    // launch of another no longer leave most of the chip idle.
+    int n_lanes = 1, lane_pos = 0;
+    int lane_cur[PM3D_MAX_LANES] = {};
+    cudaStream_t lane_cstream[PM3D_MAX_LANES] = {}, lane_fstream[PM3D_MAX_LANES] = {};
+    cudaEvent_t lane_join[PM3D_MAX_LANES] = {};
+    cudaStream_t cur_cstream = nullptr;      // compose stream of the frame batch being enqueued
+    cudaStream_t last_cstream = nullptr;     // ... of the frame rendered last (readers of its results wait for it)
     cudaStream_t front_stream = nullptr;     // highest priority: single frames (a handful of long-running front CTAs)
     cudaStream_t front_stream_lo = nullptr;  // default priority: large batches (both launches fill the chip)
     cudaStream_t cur_fstream = nullptr;      // the one the frame batch being enqueued uses
@@ -217,6 +228,7 @@ inline void pm3d_save_set(pm3d_ctx *ctx, int k) {
 int pm3d_launch_front(pm3d_ctx *ctx, int n_views, cudaStream_t stream);  // column cast + per-view setup, one launch
 int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out);
 int pm3d_launch_checksum(pm3d_ctx *ctx, int n_views, const uint8_t *frames);
+int pm3d_wait_last_frame(pm3d_ctx *ctx);  // host-waits for the lane the last frame batch ran on (if not the main stream)
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__

@@ -178,6 +178,8 @@ extern "C" int pm3d_present(pm3d_ctx *ctx, const uint8_t *d_src, int n_views, in
     if (!d_src) {
         d_src = ctx->last_frame;
         if (n_views < 1) n_views = ctx->last_views;
+        int rc = pm3d_wait_last_frame(ctx);  // it may have run on another lane
+        if (rc) return rc;
     }
     if (!d_src || n_views < 1 || !out) return pm3d_fail(ctx, PM3D_ERR_ARG, "nothing to present / null output");
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -18,6 +18,7 @@ OPT_KEEP_COLUMNS = 1
 OPT_FORCE_PAINTER = 2
 OPT_PIPELINE = 3
 OPT_OVERLAP = 4
+OPT_LANES = 5
 PRESENT_COPY, PRESENT_CRT, PRESENT_CRT_CURVE = 0, 1, 2
 
 

@@ -272,6 +272,52 @@ def test_frame_tolerance_statement(gpu_ctx):
 # --------------------------------------------------------------------------- API behaviour
 
 
+@pytest.mark.parametrize("lanes", [2, 3, 4])
+def test_frame_lanes_give_the_same_frames(gpu_ctx, lanes):
+    """PM3D_OPT_LANES: independent resident frames dealt to several lanes (streams + intermediate buffers of their own)
+    must be the frames a single lane renders; the readers of "the last render" follow the lane it ran on."""
+    ctx = gpu_ctx
+    c = W.config_c2(w=640, h=360, n_poses=7)
+    views, sprites, off = c["views"], c["sprites"], c["offsets"]
+    n, fb = len(views), 640 * 360 * 4
+    ctx.upload_scene(c["scene"])
+    ctx.set_view(640, 360, 1, 200)
+    dv, ds, do = ctx.device_alloc(views.nbytes), ctx.device_alloc(sprites.nbytes), ctx.device_alloc(8)
+    dout = ctx.device_alloc(3 * n * fb)
+    ctx.h2d(dv, views); ctx.h2d(ds, sprites); ctx.h2d(do, np.array([0, 200], np.int32))
+
+    def run(reps):
+        outs = []
+        for i in range(reps * n):
+            r = i % n
+            ctx.render_resident(dv + r * 104, 1, ds + int(off[r]) * 64, do, 200, dout + i * fb)
+        rects, conv = ctx.download_results(200, 1)          # of the LAST call, whichever lane it ran on
+        sums = ctx.frame_checksums(1)
+        ctx.sync()
+        frames = np.empty((reps * n, 360, 640, 4), dtype=np.uint8)
+        ctx.d2h(frames, dout)
+        return frames, rects.copy(), conv.copy(), int(sums[0])
+
+    try:
+        want, wrects, wconv, wsum = run(1)
+        ctx.set_option(pm3d._lib.OPT_LANES, lanes)
+        ctx.timer_start(9)
+        got, grects, gconv, gsum = run(3)
+        ctx.timer_stop(9)
+        assert ctx.timer_ms(9) > 0
+        for i in range(3 * n):
+            assert np.array_equal(got[i], want[i % n]), f"frame {i} (lane {i % lanes})"
+        # 3 * n - 1 frames precede the last one: it is pose n - 1 again
+        assert np.array_equal(grects, wrects) and gconv.tobytes() == wconv.tobytes() and gsum == wsum
+        # the host-buffer path keeps working next to the lanes (lane 0)
+        one = ctx.render(views[2:3], sprites[off[2]:off[3]])
+        assert np.array_equal(one["rgba"][0], want[2])
+    finally:
+        ctx.set_option(pm3d._lib.OPT_LANES, 1)
+        for p_ in (dv, ds, do, dout):
+            ctx.device_free(p_)
+
+
 def host_checksum(frame: np.ndarray) -> int:
     """The per-view checksum pm3d_frame_checksums defines: sum over words of FNV-1a style hash(word index, word)."""
     words = np.ascontiguousarray(frame).view(np.uint32).reshape(-1).astype(np.uint64)

@@ -260,15 +260,22 @@ def sweep_c3(ctx):
         d_off = ctx.device_alloc(8)
         ctx.h2d(d_views, views); ctx.h2d(d_off, np.zeros(2, dtype=np.int32))
         frame = lambda i: ctx.render_resident(d_views + (i % ring) * views.itemsize, 1, 0, d_off, 0, d_out + (i % ring) * fb)
-        for i in range(ring):
-            frame(i)
-        ctx.sync()
         reps = 64
-        ctx.timer_start(7)
-        for i in range(reps):
-            frame(i)
-        ctx.timer_stop(7)
-        ms = ctx.timer_ms(7) / reps
+
+        def timed(lanes):
+            ctx.set_option(__import__("pm3d")._lib.OPT_LANES, lanes)
+            for i in range(ring):
+                frame(i)
+            ctx.sync()
+            ctx.timer_start(7)
+            for i in range(reps):
+                frame(i)
+            ctx.timer_stop(7)
+            return ctx.timer_ms(7) / reps
+
+        ms = timed(1)
+        ms_lanes = timed(LANES)
+        ctx.set_option(__import__("pm3d")._lib.OPT_LANES, 1)
         ctx.set_option(__import__("pm3d")._lib.OPT_OVERLAP, 0)   # per-kernel durations: one kernel at a time
         ctx.ktimer_begin(ring)
         for i in range(ring):
@@ -280,7 +287,9 @@ def sweep_c3(ctx):
         out[f"levels_{levels}"] = {"frames_per_s": 1e3 / ms, "ms_per_frame": ms, "mrays_per_s": w * levels / (ms * 1e-3) / 1e6,
                                    "mpixels_per_s": w * h / (ms * 1e-3) / 1e6, "compose_ms": compose_ms,
                                    "front_ms": float(kt[:, 0].mean()), "hbm_frac_compose": fb / (compose_ms * 1e-3) / 1e9 / peak,
-                                   "hbm_frac_frame": fb / (ms * 1e-3) / 1e9 / peak}
+                                   "hbm_frac_frame": fb / (ms * 1e-3) / 1e9 / peak,
+                                   f"frames_per_s_{LANES}_lanes": 1e3 / ms_lanes,
+                                   f"hbm_frac_frame_{LANES}_lanes": fb / (ms_lanes * 1e-3) / 1e9 / peak}
     ctx.device_free(d_out)
     return out
 

@@ -51,8 +51,10 @@ for lanes in (1, 2, 3, 4):
     t0 = time.perf_counter()
     c.timer_start(0)
     for i in range(n): frame1(i)
+    t_enq = time.perf_counter() - t0
     c.timer_stop(0)
     ms = c.timer_ms(0); c.sync()
+    print(f"   host enqueue loop {t_enq / n * 1e6:.1f} us per frame, device {ms / n * 1e3:.1f} us per frame")
     wall = time.perf_counter() - t0
     print(f"lanes={lanes}: {n / (ms * 1e-3):8.0f} frames/s by events, {n / wall:8.0f} by wall clock")
     c.close()

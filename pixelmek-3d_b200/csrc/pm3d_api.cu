@@ -567,7 +567,7 @@ int pm3d_ktimer_begin(pm3d_ctx *ctx, int max_frames) {
 int pm3d_ktimer_collect(pm3d_ctx *ctx, float *out_ms, int cap_frames) {
     if (!ctx || !out_ms) return PM3D_ERR_ARG;
     ctx->kt_on = 0;
-    PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PM3D_CUDA(ctx, sync_frame_streams(ctx));  // every lane: the event pairs sit on the streams their frames ran on
     const int n = ctx->kt_n < cap_frames ? ctx->kt_n : cap_frames;
     for (int f = 0; f < n; f++)
         for (int k = 0; k < 3; k++) {

@@ -149,7 +149,8 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
  * shortcut of the compose kernel (A/B check: output must not change); PM3D_OPT_PIPELINE = n
  * (1..4, default 1) keeps n internal frame slots so that, for PM3D_NO_SYNC renders into HOST
  * memory, the device-to-host copy of frame i (on a second stream) overlaps the kernels of frame
- * i+1; results are valid after pm3d_sync.  Call it after pm3d_set_view.  PM3D_OPT_OVERLAP (default 1): the
+ * i+1; results are valid after pm3d_sync (the rectangles and convergence travel through mapped
+ * pinned memory, not the copy engine, and are handed to out_rects / out_conv by pm3d_sync).  Call it after pm3d_set_view.  PM3D_OPT_OVERLAP (default 1): the
  * per-frame intermediate buffers exist twice and the cast/setup launch of frame i+1 runs on a second stream
  * beside the compose launch of frame i (enqueue-only callers: pm3d_render_resident, PM3D_NO_SYNC); 0 = one
  * set of buffers, one stream.

@@ -31,6 +31,25 @@ static int dev_realloc(pm3d_ctx *ctx, T **ptr, size_t count) {
     return PM3D_OK;
 }
 
+// ---- small results of pipelined host renders (see pm3d_ctx::SmallPending)
+__global__ void k_export_small(const uint4 *rects, int n_rects, const uint4 *conv, int n_conv16, uint4 *dst, size_t rect_cap) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_rects) dst[i] = rects[i];
+    if (i < n_conv16) dst[rect_cap + i] = conv[i];
+}
+static void small_flush(pm3d_ctx *ctx, int s) {
+    pm3d_ctx::SmallPending &sp = ctx->small[s];
+    if (!sp.active) return;
+    const uint8_t *src = ctx->small_ring + (size_t)s * ctx->small_slot_bytes;
+    if (sp.dst_rects && sp.n_rects) memcpy(sp.dst_rects, src, (size_t)sp.n_rects * sizeof(pm3d_rect));
+    if (sp.dst_conv && sp.n_conv) memcpy(sp.dst_conv, src + ctx->small_rect_cap * sizeof(pm3d_rect), (size_t)sp.n_conv * sizeof(pm3d_convergence));
+    sp.active = false;
+}
+// after the main stream was synchronised: oldest first, so a buffer handed out twice ends with the newest result
+static void small_flush_all(pm3d_ctx *ctx) {
+    for (int k = 0; k < PM3D_SMALL_SLOTS; k++) small_flush(ctx, (ctx->small_pos + k) % PM3D_SMALL_SLOTS);
+}
+
 // every stream a frame batch may still be running on
 static cudaError_t sync_frame_streams(pm3d_ctx *ctx) {
     cudaError_t e = cudaSuccess, r;
@@ -133,6 +152,9 @@ void pm3d_destroy(pm3d_ctx *ctx) {
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->small_ring) cudaFreeHost(ctx->small_ring);
+    for (auto &sp : ctx->small)
+        if (sp.done) cudaEventDestroy(sp.done);
     for (int i = 0; i < ctx->kt_cap * 6; i++) cudaEventDestroy(ctx->kt_ev[i]);
     delete[] ctx->kt_ev;
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -143,6 +165,7 @@ int pm3d_sync(pm3d_ctx *ctx) {
     if (!ctx) return PM3D_ERR_ARG;
     PM3D_CUDA(ctx, sync_frame_streams(ctx));
     if (ctx->copy_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    small_flush_all(ctx);
     return PM3D_OK;
 }
 
@@ -370,6 +393,7 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
     PM3D_CUDA(ctx, sync_frame_streams(ctx));
     if (ctx->copy_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    small_flush_all(ctx);
     ctx->w = width; ctx->h = height; ctx->max_views = max_views; ctx->max_sprites = max_sprites_total;
     ctx->n_groups = (width + 63) / 64;
     const size_t V = max_views, L = ctx->num_levels, W = width, H = height, S = std::max(max_sprites_total, 1);
@@ -646,26 +670,57 @@ int pm3d_render(pm3d_ctx *ctx, const pm3d_view *views, int n_views, const pm3d_s
     if ((rc = render_core(ctx, n_views, n_sprites, target))) return rc;
 
     const size_t fb = (size_t)n_views * ctx->w * ctx->h * 4;
-    // pipelined: every D2H of this frame goes to the copy stream (small results first), so the main stream
-    // never waits for the copy engine and the next frame's kernels start at once
-    cudaStream_t cs = ctx->stream;
     if (piped) {
+        // pipelined: the frame copy goes to the copy stream, so the main stream never waits for the copy engine and the
+        // next frame's kernels start at once.  The small results do not go through the copy engine at all (a few-KB
+        // copy costs microseconds of DMA set-up between the 8 MB frame copies that bound this path): a kernel stores
+        // them into mapped pinned memory and pm3d_sync hands them to the caller's buffers.
         PM3D_CUDA(ctx, cudaEventRecord(ctx->ev_rendered[slot], ctx->stream));
         PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[slot], 0));
-        cs = ctx->copy_stream;
-    }
-    if (out_rects && n_sprites)
-        PM3D_CUDA(ctx, cudaMemcpyAsync(out_rects, ctx->rects, (size_t)n_sprites * sizeof(pm3d_rect), cudaMemcpyDeviceToHost, cs));
-    if (out_conv)
-        PM3D_CUDA(ctx, cudaMemcpyAsync(out_conv, ctx->conv, (size_t)n_views * sizeof(pm3d_convergence), cudaMemcpyDeviceToHost, cs));
-    // the set's rects/conv have now been read: only after this point may its next frame rewrite them
-    if (ctx->n_sets > 1) PM3D_CUDA(ctx, cudaEventRecord(fs.ev_compose, cs));
-    if (piped) {
-        PM3D_CUDA(ctx, cudaMemcpyAsync(out_rgba, target, fb, cudaMemcpyDeviceToHost, cs));
-        PM3D_CUDA(ctx, cudaEventRecord(ctx->ev_copied[slot], cs));
+        const int nr = out_rects ? n_sprites : 0, nc = out_conv ? n_views : 0;
+        if (nr || nc) {
+            const size_t rect_cap = (size_t)std::max(ctx->max_sprites, 1), need = rect_cap * sizeof(pm3d_rect) + (size_t)ctx->max_views * sizeof(pm3d_convergence);
+            if (ctx->small_slot_bytes < need || ctx->small_rect_cap != rect_cap) {
+                PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                small_flush_all(ctx);
+                if (ctx->small_ring) PM3D_CUDA(ctx, cudaFreeHost(ctx->small_ring));
+                ctx->small_ring = nullptr;
+                PM3D_CUDA(ctx, cudaHostAlloc((void **)&ctx->small_ring, need * PM3D_SMALL_SLOTS, cudaHostAllocMapped));
+                ctx->small_slot_bytes = need;
+                ctx->small_rect_cap = rect_cap;
+            }
+            const int s = ctx->small_pos;
+            ctx->small_pos = (s + 1) % PM3D_SMALL_SLOTS;
+            pm3d_ctx::SmallPending &sp = ctx->small[s];
+            if (!sp.done) PM3D_CUDA(ctx, cudaEventCreateWithFlags(&sp.done, cudaEventDisableTiming));
+            if (sp.active) {  // PM3D_SMALL_SLOTS frames ago: long finished
+                PM3D_CUDA(ctx, cudaEventSynchronize(sp.done));
+                small_flush(ctx, s);
+            }
+            uint4 *d_slot = nullptr;
+            PM3D_CUDA(ctx, cudaHostGetDevicePointer((void **)&d_slot, ctx->small_ring + (size_t)s * need, 0));
+            const int n16 = std::max(nr, nc * 2);
+            k_export_small<<<(n16 + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const uint4 *>(ctx->rects), nr,
+                                                                       reinterpret_cast<const uint4 *>(ctx->conv), nc * 2, d_slot, rect_cap);
+            ctx->launches++;
+            PM3D_CUDA(ctx, cudaGetLastError());
+            PM3D_CUDA(ctx, cudaEventRecord(sp.done, ctx->stream));
+            sp.dst_rects = out_rects; sp.dst_conv = out_conv; sp.n_rects = nr; sp.n_conv = nc; sp.active = true;
+        }
+        // the set's rects/conv have now been read: only after this point may its next frame rewrite them
+        if (ctx->n_sets > 1) PM3D_CUDA(ctx, cudaEventRecord(fs.ev_compose, ctx->stream));
+        PM3D_CUDA(ctx, cudaMemcpyAsync(out_rgba, target, fb, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        PM3D_CUDA(ctx, cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
         ctx->ring_pos = (slot + 1) % ctx->ring_n;
-    } else if (out_rgba && !(flags & PM3D_OUT_DEVICE)) {
-        PM3D_CUDA(ctx, cudaMemcpyAsync(out_rgba, ctx->frame, fb, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        if (out_rects && n_sprites)
+            PM3D_CUDA(ctx, cudaMemcpyAsync(out_rects, ctx->rects, (size_t)n_sprites * sizeof(pm3d_rect), cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_conv)
+            PM3D_CUDA(ctx, cudaMemcpyAsync(out_conv, ctx->conv, (size_t)n_views * sizeof(pm3d_convergence), cudaMemcpyDeviceToHost, ctx->stream));
+        // the set's rects/conv have now been read: only after this point may its next frame rewrite them
+        if (ctx->n_sets > 1) PM3D_CUDA(ctx, cudaEventRecord(fs.ev_compose, ctx->stream));
+        if (out_rgba && !(flags & PM3D_OUT_DEVICE))
+            PM3D_CUDA(ctx, cudaMemcpyAsync(out_rgba, ctx->frame, fb, cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (!(flags & PM3D_NO_SYNC)) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PM3D_OK;

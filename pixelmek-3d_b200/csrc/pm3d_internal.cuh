@@ -63,6 +63,7 @@ struct SheetInfo {
 // ------------------------------------------------------------------ ctx
 
 #define PM3D_MAX_LANES 4
+#define PM3D_SMALL_SLOTS 8
 struct pm3d_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -123,6 +124,19 @@ struct pm3d_ctx {
     uint8_t *frame_ring[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_rendered[4] = {}, ev_copied[4] = {};
     uint64_t *checksums = nullptr;   // [max_views]
+    // Small results (rectangles, convergence) of pipelined host renders: a kernel stores them into mapped pinned
+    // memory right after compose, so no few-KB copy-engine operation sits between the 8 MB frame copies; the host
+    // hands them to the caller's buffers at pm3d_sync (or when the slot comes round again).
+    struct SmallPending {
+        pm3d_rect *dst_rects = nullptr;
+        pm3d_convergence *dst_conv = nullptr;
+        int n_rects = 0, n_conv = 0;
+        cudaEvent_t done = nullptr;
+        bool active = false;
+    } small[PM3D_SMALL_SLOTS];
+    uint8_t *small_ring = nullptr;   // [PM3D_SMALL_SLOTS][small_slot_bytes], cudaHostAllocMapped
+    size_t small_slot_bytes = 0, small_rect_cap = 0;
+    int small_pos = 0;
 
     // Two sets of the per-frame buffers above (PM3D_FRAME_FIELDS) + input staging, so that the front kernel of
     // frame i+1 (front_stream) overlaps the compose kernel of frame i (stream).  The named fields above always

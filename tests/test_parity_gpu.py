@@ -465,6 +465,34 @@ def test_pipelined_frames_equal_synchronous_frames(gpu_ctx):
         ctx.set_option(pm3d._lib.OPT_PIPELINE, 1)
 
 
+def test_pipelined_small_results_survive_slot_reuse(gpu_ctx):
+    """The rectangles and convergence of pipelined renders reach the host through a ring of 8 mapped slots that the
+    library flushes into the caller's buffers at pm3d_sync or when a slot comes round again: 27 frames in flight
+    between two syncs, every frame with result buffers of its own."""
+    c = W.config_c2(w=320, h=180, n_poses=9)
+    ctx = gpu_ctx
+    ctx.upload_scene(c["scene"])
+    ctx.set_view(320, 180, 1, 200)
+    off = c["offsets"]
+    want = [ctx.render(c["views"][i:i + 1], c["sprites"][off[i]:off[i + 1]]) for i in range(9)]
+    want = [{k: v.copy() for k, v in r.items()} for r in want]
+    ctx.set_option(pm3d._lib.OPT_PIPELINE, 3)
+    ring, ctx._res_ring = ctx._res_ring, []          # every call gets fresh (pageable) rect / convergence arrays
+    try:
+        bufs = [ctx.host_alloc(320 * 180 * 4, np.uint8, (1, 180, 320, 4)) for _ in range(27)]
+        got = [ctx.render(c["views"][i % 9:i % 9 + 1], c["sprites"][off[i % 9]:off[i % 9 + 1]], out=bufs[i], no_sync=True)
+               for i in range(27)]
+        ctx.sync()
+        for i in range(27):
+            w_ = want[i % 9]
+            assert np.array_equal(got[i]["rgba"], w_["rgba"]), f"frame {i}"
+            assert np.array_equal(got[i]["rects"], w_["rects"]), f"rects of frame {i}"
+            assert got[i]["conv"].tobytes() == w_["conv"].tobytes(), f"convergence of frame {i}"
+    finally:
+        ctx._res_ring = ring
+        ctx.set_option(pm3d._lib.OPT_PIPELINE, 1)
+
+
 def test_overlapped_frames_equal_serial_frames(gpu_ctx):
     """PM3D_OPT_OVERLAP (default on): the cast/setup launch of frame i+1 runs beside the compose launch of frame i
     on a second stream with a second set of intermediate buffers.  Many frames enqueued back to back (resident

@@ -236,7 +236,8 @@ __device__ __forceinline__ void cast_ray(const CastParams &p, const int view, co
     }
     if ((threadIdx.x & 31) == 0) {
         const int half = (threadIdx.x >> 5) & 1;
-        p.agg[(((size_t)view * p.num_levels + level) * p.n_groups + group) * 2 + half] =
+        // [view][group][level][half]: the 2*L records of a group are contiguous for the compose warps that read them all
+        p.agg[(((size_t)view * p.n_groups + group) * p.num_levels + level) * 2 + half] =
             make_int4(agg_ya, agg_fs_min, agg_fs_max, __float_as_int(agg_zmax));
     }
 }

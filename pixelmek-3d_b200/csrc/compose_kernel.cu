@@ -263,15 +263,27 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
     int fs_max = 0, sky_below = 0x7fffffff;
     double zmax_group = INFINITY;  // no column of the group has a z-buffer value above this
     {
-        // every lane reads the same 2*L records (one broadcast transaction each): cheaper than a strided read
-        // followed by ten shuffles
-        const int4 *ag = p.agg + ((size_t)view * p.num_levels * p.n_groups + group) * 2;
+        // every lane reads the same 2*L contiguous records (broadcast transactions at immediate offsets from one base:
+        // cheaper than a strided read followed by ten shuffles); level 0 carries the floor starts and the z bound
+        const int4 *ag = p.agg + ((size_t)view * p.n_groups + group) * p.num_levels * 2;
+        const int4 a0 = __ldg(ag), a1 = __ldg(ag + 1);
+        fs_max = max(a0.z, a1.z);
+        sky_below = min(min(a0.x, a0.y), min(a1.x, a1.y));
+        zmax_group = (double)fmaxf(__int_as_float(a0.w), __int_as_float(a1.w));
+        const int L = p.num_levels;
+        if (L <= 4) {  // the usual stacks (the bundled maps have 3 levels): no loop, predicated loads
+            int4 u[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) u[k] = (k + 2 < 2 * L) ? __ldg(ag + 2 + k) : make_int4(0x7fffffff, 0x7fffffff, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 6; k++) { sky_below = min(sky_below, min(u[k].x, u[k].y)); fs_max = max(fs_max, u[k].z); }
+        } else {
 #pragma unroll 2
-        for (int l = 0; l < p.num_levels; l++) {
-            const int4 a0 = __ldg(ag + (size_t)l * p.n_groups * 2), a1 = __ldg(ag + (size_t)l * p.n_groups * 2 + 1);
-            fs_max = max(fs_max, max(a0.z, a1.z));
-            sky_below = min(sky_below, min(min(a0.x, a0.y), min(a1.x, a1.y)));
-            if (l == 0) zmax_group = (double)fmaxf(__int_as_float(a0.w), __int_as_float(a1.w));
+            for (int k = 2; k < 2 * L; k++) {
+                const int4 a = __ldg(ag + k);
+                sky_below = min(sky_below, min(a.x, a.y));
+                fs_max = max(fs_max, a.z);
+            }
         }
     }
 

@@ -101,7 +101,7 @@ struct pm3d_ctx {
     ulonglong2 *col_ps = nullptr;
     double *flo_xw = nullptr, *flo_yw = nullptr, *flo_dw = nullptr, *flo_rc = nullptr, *flo_dx = nullptr, *flo_dy = nullptr;  // [views][w]
     int32_t *flo_fs = nullptr;
-    int4 *agg = nullptr;             // [views][levels][n_groups][2]
+    int4 *agg = nullptr;             // [views][n_groups][levels][2]
     double *zbuf = nullptr;          // [views][w]
     RowRec *row_rec = nullptr;      // [views][h]
     pm3d_column *dbg_cols = nullptr;  // [views][levels][w] when keep_columns

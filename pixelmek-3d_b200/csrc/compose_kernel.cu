@@ -253,7 +253,6 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
     if (wrow0 >= p.h) return;
     const int wrow1 = min(wrow0 + WARP_ROWS, p.h);
     const int gx0 = group * GROUP_COLS;
-    const double posx = c.pos_x, posy = c.pos_y;
     const uint32_t box_tint = (uint32_t)c.max_light[0] | ((uint32_t)c.max_light[1] << 8) |
                               ((uint32_t)c.max_light[2] << 16) | 0xff000000u;
     WarpList<MAX_WARP_SPRITES, LATENCY> &wl = s_list[warp];
@@ -265,18 +264,22 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
     {
         // every lane reads the same 2*L contiguous records (broadcast transactions at immediate offsets from one base:
         // cheaper than a strided read followed by ten shuffles); level 0 carries the floor starts and the z bound
-        const int4 *ag = p.agg + ((size_t)view * p.n_groups + group) * p.num_levels * 2;
+        const int L = p.num_levels;
+        const int4 *ag = p.agg + (size_t)((unsigned)(view * p.n_groups + group) * (unsigned)(2 * L));
         const int4 a0 = __ldg(ag), a1 = __ldg(ag + 1);
         fs_max = max(a0.z, a1.z);
         sky_below = min(min(a0.x, a0.y), min(a1.x, a1.y));
         zmax_group = (double)fmaxf(__int_as_float(a0.w), __int_as_float(a1.w));
-        const int L = p.num_levels;
-        if (L <= 4) {  // the usual stacks (the bundled maps have 3 levels): no loop, predicated loads
-            int4 u[6];
+        if (L <= 4) {
+            // the usual stacks (the bundled maps have 3 levels): no loop; a slot past the last record re-reads the last
+            // one (min / max do not mind), so there is nothing to predicate
+            const int last = 2 * L - 1;
 #pragma unroll
-            for (int k = 0; k < 6; k++) u[k] = (k + 2 < 2 * L) ? __ldg(ag + 2 + k) : make_int4(0x7fffffff, 0x7fffffff, 0, 0);
-#pragma unroll
-            for (int k = 0; k < 6; k++) { sky_below = min(sky_below, min(u[k].x, u[k].y)); fs_max = max(fs_max, u[k].z); }
+            for (int k = 2; k < 8; k++) {
+                const int4 a = __ldg(ag + min(k, last));
+                sky_below = min(sky_below, min(a.x, a.y));
+                fs_max = max(fs_max, a.z);
+            }
         } else {
 #pragma unroll 2
             for (int k = 2; k < 2 * L; k++) {
@@ -408,7 +411,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
 
     // fast floor cast: texel-unit camera position, map bounds in texels, and the largest row distance for which
     // every column of this lane keeps |weight| <= 4 (negative when a column is not eligible)
-    const double ptx = posx * texd, pty = posy * texd;
+    // (the camera position is read where a floor row needs it: half the warps of a frame never do)
     const uint32_t boundx = (uint32_t)min((uint64_t)p.map_w << p.tex_shift, (uint64_t)0x80000000u);
     const uint32_t boundy = (uint32_t)min((uint64_t)p.map_h << p.tex_shift, (uint64_t)0x80000000u);
     double lane_cd_max = -2.0;  // -2: not computed yet (only warps that reach a floor row need it)
@@ -577,6 +580,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                 load4(p.flo_dy, fi0, vec, 4, dy);
                 uint32_t tx[4], ty[4];
                 bool ok = true;
+                const double ptx = c.pos_x * texd, pty = c.pos_y * texd;  // texel-unit camera position
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const double wq = r.cd * cr[j];
@@ -634,7 +638,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         if (!((pending >> j) & 1u)) continue;
-                        const uint32_t t = floor_texel(p, cx[j], cy[j], cw[j], cr[j], fs[j], r, posx, posy, y);
+                        const uint32_t t = floor_texel(p, cx[j], cy[j], cw[j], cr[j], fs[j], r, c.pos_x, c.pos_y, y);
                         const uint32_t a = t >> 24;
                         if (a == 255u) { px[j] = t; pending &= ~(1u << j); }  // (t*255 + 127)/255 == t
                         else if (a != 0u) { slow |= 1u << j; pending &= ~(1u << j); }

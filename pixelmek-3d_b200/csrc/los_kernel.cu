@@ -268,10 +268,18 @@ __global__ void __launch_bounds__(LOS_THREADS, LOS_MIN_BLOCKS) k_los(LosParams p
         }
         const int total = __shfl_sync(0xffffffffu, off, 31);
         off -= n_put;
-        for (int k = 0; k < n_put; k++) {
-            const int c = cbase + k;
-            const int id = cur.x <= 3 ? (c == 0 ? cur.y : (c == 1 ? cur.z : cur.w)) : __ldg(p.cell_items + cur.y + c);
-            wq[off + k] = ((uint32_t)lane << 27) | (uint32_t)id;
+        if (n_put > 0) {
+            const uint32_t tag = (uint32_t)lane << 27;
+            if (cur.x <= 3) {
+                // the usual cell: its (<= 3) candidate ids sit in the record itself and go out in one round
+                // (cbase == 0): three predicated stores instead of a loop the whole warp would walk
+                wq[off] = tag | (uint32_t)cur.y;
+                if (n_put > 1) wq[off + 1] = tag | (uint32_t)cur.z;
+                if (n_put > 2) wq[off + 2] = tag | (uint32_t)cur.w;
+            } else {
+                const int32_t *items = p.cell_items + cur.y + cbase;
+                for (int k = 0; k < n_put; k++) wq[off + k] = tag | (uint32_t)__ldg(items + k);
+            }
         }
         __syncwarp();
         for (int q = lane; q < total; q += 32) {

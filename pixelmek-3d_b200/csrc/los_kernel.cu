@@ -62,11 +62,11 @@ __device__ __forceinline__ bool segments_intersect(const double4 &a, const doubl
     const double tNum = (x1 - x3) * (y3 - y4) - (y1 - y3) * (x3 - x4);
     const double uNum = -((x1 - x2) * (y1 - y3) - (y1 - y2) * (x1 - x3));
     if (exp_mid(denom) && (tNum == 0 || exp_mid(tNum)) && (uNum == 0 || exp_mid(uNum))) {
+        // (the guard keeps every exponent within 2^+-500, so the products below neither overflow nor underflow:
+        //  a product is negative exactly when the numerator is non-zero and its sign differs from denom's)
         const double ad = fabs(denom);
-        if (tNum != 0 && ((tNum < 0) != (denom < 0))) return false;
-        if (fabs(tNum) > ad) return false;
-        if (uNum != 0 && ((uNum < 0) != (denom < 0))) return false;
-        if (fabs(uNum) > ad) return false;
+        if (tNum * denom < 0.0 || fabs(tNum) > ad) return false;
+        if (uNum * denom < 0.0 || fabs(uNum) > ad) return false;
         return true;
     }
     if (denom == 0) return false;

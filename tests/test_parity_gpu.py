@@ -376,6 +376,34 @@ def test_full_size_4k_frame_properties(gpu_ctx):
     assert (got["rgba"][0][..., 3] == 255).all()
 
 
+def test_full_size_c4_sweep_properties(gpu_ctx, monkeypatch):
+    """C4 at its full size: 4096 views of 320x200 with 50 sprites each, frames kept in HBM.  Every 64th view's
+    device checksum equals the checksum of the ORACLE's frame of that view; the literal painter loop and another
+    compose instantiation give the same 4096 checksums."""
+    c = W.config_c4()
+    ctx = gpu_ctx
+    n = len(c["views"])
+    assert n == 4096
+    ctx.upload_scene(c["scene"])
+    ctx.set_view(320, 200, n, len(c["sprites"]))
+    ctx.render(c["views"], c["sprites"], c["offsets"], want_frame=False)
+    sums = ctx.frame_checksums(n).copy()
+    osc, off = O.Scene(c["scene"]), c["offsets"]
+    for i in range(0, n, 64):
+        ref = O.render(osc, orc_camera(c["views"][i], 320, 200), c["sprites"][off[i]:off[i + 1]].astype(O.SPRITE_DTYPE), threads=4)
+        assert int(sums[i]) == host_checksum(ref["rgba"]), f"view {i}"
+    ctx.set_option(pm3d._lib.OPT_FORCE_PAINTER, 1)
+    try:
+        ctx.render(c["views"], c["sprites"], c["offsets"], want_frame=False)
+        assert np.array_equal(ctx.frame_checksums(n), sums)
+    finally:
+        ctx.set_option(pm3d._lib.OPT_FORCE_PAINTER, 0)
+    monkeypatch.setenv("PM3D_COMPOSE_ROWS", "4")
+    ctx.render(c["views"], c["sprites"], c["offsets"], want_frame=False)
+    assert np.array_equal(ctx.frame_checksums(n), sums)
+    ctx.set_view(320, 200, 1, 1)   # release the 4096-view buffers
+
+
 def test_errors_are_reported_not_swallowed(gpu_ctx):
     ctx = pm3d.Context(0)
     v = np.zeros(1, dtype=pm3d._lib.VIEW_DTYPE)

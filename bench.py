@@ -40,7 +40,7 @@ for _p in (ROOT, os.path.join(ROOT, "pixelmek-3d_b200")):
         sys.path.insert(0, _p)
 
 W_PX, H_PX, N_SPRITES, RING = 1920, 1080, 200, 24
-LANES = 3  # PM3D_OPT_LANES of the resident throughput measurement (independent frames in flight)
+LANES = 4  # PM3D_OPT_LANES of the resident throughput measurement (independent frames in flight)
 FRAME_BYTES = 4 * W_PX * H_PX  # algorithmic bytes of one frame
 
 

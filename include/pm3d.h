@@ -158,7 +158,7 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
  * round-robin to n lanes, each with its own streams and intermediate buffers, so INDEPENDENT frame batches (different
  * cameras, or frames whose results are only read after pm3d_sync) run concurrently: a single 1080p frame is two
  * launches that leave most of the chip idle (24 CTAs of serial ray walks, then a compose launch whose tail is a few
- * sprite-heavy warps), three lanes nearly double the frames per second.  Calls on one lane stay ordered; calls on
+ * sprite-heavy warps), three to four lanes double the frames per second.  Calls on one lane stay ordered; calls on
  * different lanes are unordered among themselves, so two in-flight calls must not write the same output buffer.
  * Results of "the last render" (pm3d_download_results, pm3d_frame_checksums, pm3d_present with d_src NULL) wait for
  * that call's lane; pm3d_timer_* bracket all lanes.  pm3d_render (host buffers) always uses lane 0. */

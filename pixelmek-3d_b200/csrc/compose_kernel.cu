@@ -222,7 +222,7 @@ __device__ __forceinline__ void load4(const int2 *base, size_t i, bool vec, int 
 // ends, and small CTAs waste fewer warp slots); MIN_BLOCKS is given for 4-warp CTAs and scaled.
 // LATENCY: single frames with sprites (see the sprite list above)
 #ifndef LATENCY_LIST
-#define LATENCY_LIST 96
+#define LATENCY_LIST 64  // 24 KB of shared memory per 4-warp CTA: 8 CTAs per SM fit (96 entries cap it at 6)
 #endif
 template <int WARP_ROWS, int MIN_BLOCKS, int COMPOSE_WARPS, bool LATENCY = false>
 __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_WARPS) k_compose(const __grid_constant__ ComposeParams p) {
@@ -808,7 +808,11 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     const long long warps8 = (long long)ctx->n_groups * ((ctx->h + 7) / 8) * n_views;
     const long long resident = (long long)ctx->sm_count * 24;
     int rows = warps8 >= 64 * resident ? 16 : (warps8 >= 4 * resident ? 8 : (warps8 >= 2 * resident ? 4 : 2));  // 4K single frame: 8
-    int minb = rows >= 8 ? 8 : 6;
+    // 64 registers / 8 CTAs per SM for the >= 8-row (large batch) shapes, and for single frames when several of them
+    // share the chip (PM3D_OPT_LANES > 1): a few spills buy a third more resident warps, which is what hides the texel
+    // latency at saturation (3-4 lanes: +12 % frames/s); a frame that has the chip to itself is 3 % faster with 80
+    const bool shared_chip = ctx->n_lanes > 1 && ctx->n_sets > 1;
+    int minb = (rows >= 8 || (rows == 2 && shared_chip)) ? 8 : 6;
     if (const char *e = getenv("PM3D_COMPOSE_ROWS")) rows = atoi(e);      // tuning overrides (tools/)
     if (const char *e = getenv("PM3D_COMPOSE_MINB")) minb = atoi(e);
     const int cta_warps = rows >= 8 ? 2 : 4;
@@ -822,6 +826,7 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     else if (rows == 4 && minb == 8) k_compose<4, 8, 4><<<grid, block, 0, cstream>>>(p);
     else if (rows == 4 && with_sprites) k_compose<4, 6, 4, true><<<grid, block, 0, cstream>>>(p);
     else if (rows == 4) k_compose<4, 6, 4><<<grid, block, 0, cstream>>>(p);
+    else if (minb == 8 && with_sprites) k_compose<2, 8, 4, true><<<grid, block, 0, cstream>>>(p);
     else if (minb == 8) k_compose<2, 8, 4><<<grid, block, 0, cstream>>>(p);
     else if (with_sprites) k_compose<2, 6, 4, true><<<grid, block, 0, cstream>>>(p);
     else k_compose<2, 6, 4><<<grid, block, 0, cstream>>>(p);

@@ -187,7 +187,7 @@ def test_many_overlapping_sprites_and_duplicates(gpu_ctx):
 
 @pytest.mark.parametrize("rows", [2, 4, 8, 16])
 def test_warp_list_overflow_in_both_sprite_modes(gpu_ctx, rows, monkeypatch):
-    """700 billboards stacked on one patch overflow the warp-private sprite list in latency mode (96 entries, 2/4 rows
+    """700 billboards stacked on one patch overflow the warp-private sprite list in latency mode (64 entries, 2/4 rows
     per warp) and in throughput mode (256 entries, 8/16 rows per warp): the nearest entries are listed, the farther
     ones are reached through the group list.  Pixels, rectangles and convergence must equal the oracle's, and the
     literal painter loop must give the same bytes."""

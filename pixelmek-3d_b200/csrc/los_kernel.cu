@@ -414,7 +414,10 @@ __device__ __forceinline__ void z_min_max(double z, double height, int anchor, d
 
 #define MOVE_MAX_WALL_HITS 8
 #define MOVE_MAX_CANDIDATES 16
-__global__ void __launch_bounds__(128) k_valid_move(MoveParams q) {
+#ifndef MOVE_MIN_BLOCKS
+#define MOVE_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, MOVE_MIN_BLOCKS) k_valid_move(MoveParams q) {
     const LosParams &p = q.los;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;

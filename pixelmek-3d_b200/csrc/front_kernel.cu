@@ -5,8 +5,11 @@
 #include "cast_kernel.cuh"
 #include "view_kernel.cuh"
 
+#ifndef FRONT_MIN_BLOCKS
+#define FRONT_MIN_BLOCKS 4
+#endif
 template <bool DEBUG>
-__global__ void __launch_bounds__(VIEW_THREADS, 4) k_front(CastParams cp, ViewParams vp, int n_cast_blocks, long long n_pairs) {
+__global__ void __launch_bounds__(VIEW_THREADS, FRONT_MIN_BLOCKS) k_front(CastParams cp, ViewParams vp, int n_cast_blocks, long long n_pairs) {
     if ((int)blockIdx.x < n_cast_blocks) {
         // a pair of warps = the 64 columns of one (view, level, group)
         const long long pair = (long long)blockIdx.x * (VIEW_THREADS / 64) + (threadIdx.x >> 6);

@@ -39,20 +39,25 @@ def test_struct_sizes_match_the_header(ensure_built):
     assert pm3d._lib.MOVER_DTYPE.itemsize == 80
     assert pm3d._lib.COLLIDER_DTYPE.itemsize == 48
     assert pm3d._lib.MOVE_RESULT_DTYPE.itemsize == 80
+    assert pm3d._lib.CLUTTER_DEF_DTYPE.itemsize == 40
+    assert pm3d._lib.CLUTTER_QUERY_DTYPE.itemsize == 360
+    assert pm3d._lib.CLUTTER_SPRITE_DTYPE.itemsize == 32
+    assert pm3d._lib.LIST_QUERY_DTYPE.itemsize == 24
     # ... and the header says the same (the sizes are written next to each struct) and C agrees
     with open(os.path.join(ROOT, "include", "pm3d.h")) as f:
         header = f.read()
     for name, size in (("pm3d_view", 104), ("pm3d_sprite", 64), ("pm3d_column", 56), ("pm3d_mover", 80), ("pm3d_collider", 48),
-                       ("pm3d_move_result", 80)):
+                       ("pm3d_move_result", 80), ("pm3d_clutter_def", 40), ("pm3d_clutter_query", 360), ("pm3d_clutter_sprite", 32),
+                       ("pm3d_list_query", 24)):
         assert re.search(r"\}\s*%s;\s*/\*\s*%d bytes" % (name, size), header), name
     import subprocess, tempfile
-    src = '#include "pm3d.h"\n#include <stdio.h>\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pm3d_view), sizeof(pm3d_sprite), sizeof(pm3d_column), sizeof(pm3d_convergence), sizeof(pm3d_mover), sizeof(pm3d_collider), sizeof(pm3d_move_result), sizeof(pm3d_rect));return 0;}\n'
+    src = '#include "pm3d.h"\n#include <stdio.h>\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pm3d_view), sizeof(pm3d_sprite), sizeof(pm3d_column), sizeof(pm3d_convergence), sizeof(pm3d_mover), sizeof(pm3d_collider), sizeof(pm3d_move_result), sizeof(pm3d_rect), sizeof(pm3d_clutter_def), sizeof(pm3d_clutter_query), sizeof(pm3d_clutter_sprite), sizeof(pm3d_list_query));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         with open(os.path.join(d, "s.c"), "w") as f:
             f.write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "s"), os.path.join(d, "s.c")])
         out = subprocess.check_output([os.path.join(d, "s")]).decode().split()
-    assert [int(x) for x in out] == [104, 64, 56, 32, 80, 48, 80, 16]
+    assert [int(x) for x in out] == [104, 64, 56, 32, 80, 48, 80, 16, 40, 360, 32, 24]
 
 
 def test_no_cpu_fallback(ensure_built):

@@ -318,6 +318,46 @@ def test_frame_lanes_give_the_same_frames(gpu_ctx, lanes):
             ctx.device_free(p_)
 
 
+def test_frame_lanes_stress_with_interleaved_readers(gpu_ctx):
+    """400 resident frames on 4 lanes; every few frames a reader of "the last render" (checksum, rectangles) or a
+    host-buffer render cuts in.  Every reading must be that of the pose just rendered."""
+    ctx = gpu_ctx
+    c = W.config_c2(w=320, h=180, n_sprites=40, n_poses=11)
+    views, sprites, off = c["views"], c["sprites"], c["offsets"]
+    n, fb = len(views), 320 * 180 * 4
+    ctx.upload_scene(c["scene"])
+    ctx.set_view(320, 180, 1, 40)
+    want_sum, want_rects = [], []
+    for i in range(n):
+        r = ctx.render(views[i:i + 1], sprites[off[i]:off[i + 1]])
+        want_sum.append(int(ctx.frame_checksums(1)[0]))
+        want_rects.append(r["rects"].copy())
+    dv, ds, do = ctx.device_alloc(views.nbytes), ctx.device_alloc(sprites.nbytes), ctx.device_alloc(8)
+    dout = ctx.device_alloc(16 * fb)
+    ctx.h2d(dv, views); ctx.h2d(ds, sprites); ctx.h2d(do, np.array([0, 40], np.int32))
+    rng = W.SplitMix64(2024)
+    pick = (rng.uniform(400) * n).astype(int)
+    act = (rng.uniform(400) * 10).astype(int)
+    ctx.set_option(pm3d._lib.OPT_LANES, 4)
+    try:
+        for i in range(400):
+            r = int(pick[i])
+            ctx.render_resident(dv + r * 104, 1, ds + int(off[r]) * 64, do, 40, dout + (i % 16) * fb)
+            if act[i] == 0:
+                assert int(ctx.frame_checksums(1)[0]) == want_sum[r], f"frame {i}"
+            elif act[i] == 1:
+                rects, _ = ctx.download_results(40, 1)
+                assert np.array_equal(rects, want_rects[r]), f"frame {i}"
+            elif act[i] == 2:
+                h = ctx.render(views[r:r + 1], sprites[off[r]:off[r + 1]])
+                assert np.array_equal(h["rects"], want_rects[r]) and int(ctx.frame_checksums(1)[0]) == want_sum[r]
+        ctx.sync()
+    finally:
+        ctx.set_option(pm3d._lib.OPT_LANES, 1)
+        for p_ in (dv, ds, do, dout):
+            ctx.device_free(p_)
+
+
 def host_checksum(frame: np.ndarray) -> int:
     """The per-view checksum pm3d_frame_checksums defines: sum over words of FNV-1a style hash(word index, word)."""
     words = np.ascontiguousarray(frame).view(np.uint32).reshape(-1).astype(np.uint64)

@@ -725,8 +725,19 @@ def run_ours(args, rank, world, local_rank):
             extra["clutter"] = sweep_clutter(ctx, rank, world, dist, torch, dev, rank == 0 and world == 1 and not args.no_cpu)
             extra["tick"] = sweep_tick(ctx, rank, world, dist, torch, dev)
             extra["present"] = sweep_present(ctx, torch)
-        except Exception as e:  # the headline line must still print
+        except Exception as e:
+            # a failed sweep is a failed run: the headline line is still printed (with the error), then every rank
+            # leaves with a non-zero status WITHOUT tearing NCCL down over a possibly poisoned CUDA context
+            import traceback
+
+            traceback.print_exc()
             extra["error"] = repr(e)
+            line["extra"] = extra
+            line["error"] = f"sweep failed on rank {rank}: {e!r}"
+            if rank == 0:
+                print(json.dumps(line), flush=True)
+            sys.stderr.flush()
+            os._exit(1)
     line["extra"] = extra
 
     # ---- CPU baseline beside it (rank 0, N=1 only)

@@ -18,7 +18,12 @@
  *     evaluated (Go's math.Sin/Cos are software routines that differ from CUDA's in the
  *     last ulp); the device path uses only + - * / sqrt in IEEE binary64 without FMA
  *     contraction so hit cells, sides and texture columns are bit-exact.
- *   - a ctx is single-threaded (one CUDA stream); use one ctx per GPU.
+ *   - a ctx is single-threaded and behaves like ONE CUDA stream towards its caller: calls take effect in the
+ *     order they are made.  Internally frames run on further streams (the cast/setup launch of a frame beside
+ *     the compose launch of the previous one; PM3D_OPT_LANES); the library orders those streams against the ctx
+ *     stream itself — a frame call waits for everything enqueued before it (sprite lists, clutter, copies), and
+ *     every later non-frame call waits for the frames enqueued before it.  Only frames dealt to different LANES
+ *     are unordered among themselves.  Use one ctx per GPU.
  */
 #ifndef PM3D_H
 #define PM3D_H
@@ -178,9 +183,15 @@ int pm3d_render(pm3d_ctx *ctx, const pm3d_view *views, int n_views, const pm3d_s
                 const int32_t *sprite_offset, uint8_t *out_rgba, pm3d_rect *out_rects,
                 pm3d_convergence *out_conv, uint32_t flags);
 /* Same frame path with every argument already resident in HBM (device pointers) and nothing
- * copied or synchronised: the call only enqueues the kernels on the ctx stream.  Per-sprite
- * rectangles and per-view convergence stay on the device until pm3d_download_results.
- * n_sprites_total = d_sprite_offset[n_views] (the caller knows it; the host cannot read it). */
+ * copied or synchronised: the call only enqueues the kernels, ordered after everything enqueued on
+ * the ctx before it (e.g. the PM3D_NO_SYNC pm3d_raycast_sprites_batch that writes d_sprites /
+ * d_sprite_offset) — see "Conventions".  Per-sprite rectangles and per-view convergence stay on the
+ * device until pm3d_download_results.
+ * n_sprites_total = d_sprite_offset[n_views], or an upper bound of it (e.g. the max_total given to
+ * pm3d_raycast_sprites_batch) when the host has not read the total.  The offsets live in HBM, so the
+ * host cannot validate them: the view setup does, on the device — a view whose entries are negative,
+ * not monotone, list more than 2048 sprites or reach past n_sprites_total is rendered WITHOUT sprites
+ * and the next pm3d_sync / pm3d_download_results returns PM3D_ERR_CAPACITY naming the view. */
 int pm3d_render_resident(pm3d_ctx *ctx, const pm3d_view *d_views, int n_views, const pm3d_sprite *d_sprites,
                          const int32_t *d_sprite_offset, int n_sprites_total, uint8_t *d_out_rgba);
 /* rects (n_sprites of the last render) and convergence (n_views) of the last render; either may be NULL */
@@ -348,8 +359,9 @@ typedef struct pm3d_list_query {
  *   pm3d_render returns back to its Sprite objects with it).  *out_total (host, may be NULL) = out_offset[n].  More
  *   than max_total sprites is PM3D_ERR_CAPACITY (nothing is written past max_total).
  *   flags: PM3D_IN_DEVICE (world, queries, clutter*, extras* are device memory), PM3D_OUT_DEVICE (out_sprites,
- *   out_offset, out_index), PM3D_NO_SYNC (enqueue only: needs PM3D_OUT_DEVICE; out_total and the capacity check are
- *   skipped, the caller reads out_offset[n] when it needs the total). */
+ *   out_offset, out_index), PM3D_NO_SYNC (enqueue only: needs PM3D_OUT_DEVICE; out_total is not written, the caller
+ *   reads out_offset[n] when it needs the total; more than max_total sprites cuts the lists at max_total and the
+ *   next pm3d_sync returns PM3D_ERR_CAPACITY). */
 int pm3d_raycast_sprites_batch(pm3d_ctx *ctx, const pm3d_sprite *world, int n_world, const pm3d_list_query *queries,
                                int n, double render_distance, const pm3d_sprite *clutter, const int32_t *clutter_count,
                                int clutter_stride, const pm3d_sprite *extras, const int32_t *extra_offset,

@@ -361,6 +361,7 @@ extern "C" int pm3d_clutter_batch(pm3d_ctx *ctx, const pm3d_clutter_query *queri
         return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "clutter_distance %g > %g cells", clutter_distance, PM3D_CLUTTER_MAX_DISTANCE);
     if (n == 0) return PM3D_OK;
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    { int rc_ = pm3d_main_enter(ctx); if (rc_) return rc_; }
     const bool in_dev = flags & PM3D_IN_DEVICE, out_dev = flags & PM3D_OUT_DEVICE;
     const size_t per = (size_t)n * max_per_view;
     const size_t b_cnt = ((size_t)n * sizeof(int32_t) + 255) & ~(size_t)255, b_rec = per * sizeof(pm3d_clutter_sprite),
@@ -415,6 +416,7 @@ extern "C" int pm3d_clutter_batch(pm3d_ctx *ctx, const pm3d_clutter_query *queri
         PM3D_CUDA(ctx, cudaMemcpyAsync(out_records, d_rec, b_rec, cudaMemcpyDeviceToHost, ctx->stream));
         if (out_sprites) PM3D_CUDA(ctx, cudaMemcpyAsync(out_sprites, d_spr, b_spr, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    pm3d_main_touch(ctx);
     if (!(flags & PM3D_NO_SYNC)) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PM3D_OK;
 }

@@ -813,8 +813,14 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     // latency at saturation (3-4 lanes: +12 % frames/s); a frame that has the chip to itself is 3 % faster with 80
     const bool shared_chip = ctx->n_lanes > 1 && ctx->n_sets > 1;
     int minb = (rows >= 8 || (rows == 2 && shared_chip)) ? 8 : 6;
-    if (const char *e = getenv("PM3D_COMPOSE_ROWS")) rows = atoi(e);      // tuning overrides (tools/)
-    if (const char *e = getenv("PM3D_COMPOSE_MINB")) minb = atoi(e);
+    if (const char *e = getenv("PM3D_COMPOSE_ROWS")) {  // tuning overrides (tools/); anything but a built shape is ignored
+        const int v = atoi(e);
+        if (v == 2 || v == 4 || v == 8 || v == 16) rows = v;
+    }
+    if (const char *e = getenv("PM3D_COMPOSE_MINB")) {
+        const int v = atoi(e);
+        if (v == 6 || v == 8) minb = v;
+    }
     const int cta_warps = rows >= 8 ? 2 : 4;
     const bool with_sprites = ctx->cur_n_sprites > 0;  // latency-mode sprite walk (records in shared memory)
     dim3 block(cta_warps * 32), grid(ctx->n_groups, (ctx->h + cta_warps * rows - 1) / (cta_warps * rows), n_views);

@@ -52,6 +52,7 @@ int pm3d_launch_front(pm3d_ctx *ctx, int n_views, cudaStream_t stream) {
     v.conv = ctx->conv;
     v.w = ctx->w; v.h = ctx->h; v.tex_size = ctx->tex_size; v.n_sheets = ctx->n_sheets; v.n_groups = ctx->n_groups;
     v.sky_tile = ctx->sky_tile; v.floorbox_tile = ctx->floorbox_tile;
+    v.status = ctx->status_d; v.n_sprites_total = ctx->cur_n_sprites;
 
     const long long n_pairs = (long long)n_views * ctx->num_levels * ctx->n_groups;
     const long long n_cast = (n_pairs + VIEW_THREADS / 64 - 1) / (VIEW_THREADS / 64);

@@ -666,6 +666,8 @@ static int run_batch(pm3d_ctx *ctx, bool is_move, const double *rays, int64_t n,
     if (is_move && !ctx->grid) return pm3d_fail(ctx, PM3D_ERR_ARG, "pm3d_upload_grid must be called first");
     if (n == 0) return PM3D_OK;
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    { int rc_ = pm3d_main_enter(ctx); if (rc_) return rc_; }
+    pm3d_main_touch(ctx);
     const bool in_dev = flags & PM3D_IN_DEVICE, out_dev = flags & PM3D_OUT_DEVICE;
     const double *d_rays = rays;
     if (!in_dev) {
@@ -799,6 +801,8 @@ extern "C" int pm3d_valid_move_batch(pm3d_ctx *ctx, const pm3d_mover *movers, in
     if (!ctx->colliders) return pm3d_fail(ctx, PM3D_ERR_ARG, "pm3d_upload_colliders must be called first (n = 0 is fine)");
     if (n == 0) return PM3D_OK;
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    { int rc_ = pm3d_main_enter(ctx); if (rc_) return rc_; }
+    pm3d_main_touch(ctx);
     const bool in_dev = flags & PM3D_IN_DEVICE, out_dev = flags & PM3D_OUT_DEVICE;
     const pm3d_mover *d_in = movers;
     pm3d_move_result *d_out = out;

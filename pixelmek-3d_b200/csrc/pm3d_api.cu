@@ -68,9 +68,40 @@ static cudaError_t wait_last_frame(pm3d_ctx *ctx) {
     if (ctx->last_cstream && ctx->last_cstream != ctx->stream) return cudaStreamSynchronize(ctx->last_cstream);
     return cudaSuccess;
 }
-int pm3d_wait_last_frame(pm3d_ctx *ctx) {
-    PM3D_CUDA(ctx, wait_last_frame(ctx));
+int pm3d_wait_last_frame(pm3d_ctx *ctx) { return pm3d_main_enter(ctx); }  // a stream-side join, no host wait
+
+// frame -> main: non-frame work enqueued on the main stream follows every frame dealt to another lane
+int pm3d_main_enter(pm3d_ctx *ctx) {
+    if (!ctx->lanes_dirty) return PM3D_OK;
+    for (int l = 1; l < PM3D_MAX_LANES; l++) {
+        if (!ctx->lane_cstream[l]) continue;
+        PM3D_CUDA(ctx, cudaEventRecord(ctx->lane_join[l], ctx->lane_cstream[l]));
+        PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lane_join[l], 0));
+    }
+    ctx->lanes_dirty = false;
     return PM3D_OK;
+}
+// main -> frame: the front stream of the frame being enqueued waits for everything the main stream holds, once
+// per change of the main stream (a loop of frame calls alone never records or waits)
+static int order_after_main(pm3d_ctx *ctx, cudaStream_t s, uint64_t *seen) {
+    if (!ctx->own_stream) ctx->main_seq++;  // the caller may have enqueued anything on its stream
+    if (s == ctx->stream || *seen == ctx->main_seq) return PM3D_OK;
+    PM3D_CUDA(ctx, cudaEventRecord(ctx->ev_main, ctx->stream));
+    PM3D_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_main, 0));
+    *seen = ctx->main_seq;
+    return PM3D_OK;
+}
+// device-side error words (mapped pinned memory), read once the streams have drained
+int pm3d_check_status(pm3d_ctx *ctx) {
+    if (!ctx->status_h) return PM3D_OK;
+    volatile uint32_t *st = ctx->status_h;
+    const uint32_t bad_view = st[PM3D_STATUS_VIEW_SPRITES], bad_list = st[PM3D_STATUS_LIST_TOTAL];
+    if (!bad_view && !bad_list) return PM3D_OK;
+    st[PM3D_STATUS_VIEW_SPRITES] = 0; st[PM3D_STATUS_LIST_TOTAL] = 0;
+    if (bad_view)
+        return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "view %u: sprite_offset entries out of range (negative, not monotone, more than 2048 sprites "
+                         "in the view, or past n_sprites_total); the view was rendered without sprites", bad_view - 1);
+    return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "pm3d_raycast_sprites_batch listed more sprites than max_total; the lists were cut");
 }
 
 extern "C" {
@@ -112,6 +143,13 @@ int pm3d_create(int device, void *stream, pm3d_ctx **out) {
         }
         ctx->own_stream = true;
     }
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaHostAlloc((void **)&ctx->status_h, PM3D_STATUS_WORDS * sizeof(uint32_t), cudaHostAllocMapped)) != cudaSuccess ||
+        (e = cudaHostGetDevicePointer((void **)&ctx->status_d, ctx->status_h, 0)) != cudaSuccess) {
+        pm3d_destroy(ctx);
+        return pm3d_fail(nullptr, PM3D_ERR_CUDA, "ctx ordering event / status words: %s", cudaGetErrorString(e));
+    }
+    memset(ctx->status_h, 0, PM3D_STATUS_WORDS * sizeof(uint32_t));
     *out = ctx;
     return PM3D_OK;
 }
@@ -153,6 +191,8 @@ void pm3d_destroy(pm3d_ctx *ctx) {
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->small_ring) cudaFreeHost(ctx->small_ring);
+    if (ctx->status_h) cudaFreeHost(ctx->status_h);
+    if (ctx->ev_main) cudaEventDestroy(ctx->ev_main);
     for (auto &sp : ctx->small)
         if (sp.done) cudaEventDestroy(sp.done);
     for (int i = 0; i < ctx->kt_cap * 6; i++) cudaEventDestroy(ctx->kt_ev[i]);
@@ -166,7 +206,8 @@ int pm3d_sync(pm3d_ctx *ctx) {
     PM3D_CUDA(ctx, sync_frame_streams(ctx));
     if (ctx->copy_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     small_flush_all(ctx);
-    return PM3D_OK;
+    ctx->lanes_dirty = false;
+    return pm3d_check_status(ctx);
 }
 
 // ------------------------------------------------------------------ uploads
@@ -243,7 +284,10 @@ int pm3d_upload_grid(pm3d_ctx *ctx, const uint16_t *grid, int stored_levels, int
         PM3D_CUDA(ctx, cudaMemcpy(ctx->sparse_cells, cells.data(), cells.size() * 8, cudaMemcpyHostToDevice));
         PM3D_CUDA(ctx, cudaMemcpy(ctx->sparse_count, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice));
     }
+    // the clutter classes are per cell of the map they were uploaded for
+    if (ctx->map_w != map_w || ctx->map_h != map_h) ctx->clutter_ready = false;
     ctx->stored_levels = stored_levels; ctx->map_w = map_w; ctx->map_h = map_h;
+    pm3d_main_touch(ctx);
     const bool levels_changed = ctx->num_levels != num_raycast_levels;
     ctx->num_levels = num_raycast_levels;
     if (levels_changed && ctx->w > 0) return pm3d_set_view(ctx, ctx->w, ctx->h, ctx->max_views, ctx->max_sprites);
@@ -428,31 +472,36 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
             pm3d_save_set(ctx, k);
             continue;
         }
-        if ((rc = dev_realloc(ctx, &ctx->col_span, V * L * W))) return rc;
-        if ((rc = dev_realloc(ctx, &ctx->col_tt, V * L * W))) return rc;
-        if ((rc = dev_realloc(ctx, &ctx->col_ps, V * L * W))) return rc;
-        if ((rc = dev_realloc(ctx, &ctx->flo_xw, V * W))) return rc;
-        if ((rc = dev_realloc(ctx, &ctx->flo_yw, V * W))) return rc;
-        if ((rc = dev_realloc(ctx, &ctx->flo_dw, V * W))) return rc;
-        if ((rc = dev_realloc(ctx, &ctx->flo_rc, V * W))) return rc;
-        if ((rc = dev_realloc(ctx, &ctx->flo_dx, V * W))) return rc;
-        if ((rc = dev_realloc(ctx, &ctx->flo_dy, V * W))) return rc;
-        if ((rc = dev_realloc(ctx, &ctx->flo_fs, V * W))) return rc;
-        if ((rc = dev_realloc(ctx, &ctx->agg, V * L * ctx->n_groups * 2))) return rc;
-        if ((rc = dev_realloc(ctx, &ctx->zbuf, V * W))) return rc;
-        if ((rc = dev_realloc(ctx, &ctx->row_rec, V * H))) return rc;
-        if (ctx->keep_columns) {
-            if ((rc = dev_realloc(ctx, &ctx->dbg_cols, V * L * W))) return rc;
-            ctx->dbg_levels = (int)L; ctx->dbg_views = (int)V;
-        }
-        if ((rc = dev_realloc(ctx, &ctx->draw_rec, S))) return rc;
-        if ((rc = dev_realloc(ctx, &ctx->n_draw, V))) return rc;
-        if ((rc = dev_realloc(ctx, &ctx->bin_list, S * ctx->n_groups))) return rc;
-        if ((rc = dev_realloc(ctx, &ctx->bin_rect, S * ctx->n_groups))) return rc;
-        if ((rc = dev_realloc(ctx, &ctx->bin_count, V * ctx->n_groups))) return rc;
-        if ((rc = dev_realloc(ctx, &ctx->rects, S))) return rc;
-        if ((rc = dev_realloc(ctx, &ctx->conv, V))) return rc;
-        pm3d_save_set(ctx, k);
+        auto alloc_set = [&]() -> int {
+            if ((rc = dev_realloc(ctx, &ctx->col_span, V * L * W))) return rc;
+            if ((rc = dev_realloc(ctx, &ctx->col_tt, V * L * W))) return rc;
+            if ((rc = dev_realloc(ctx, &ctx->col_ps, V * L * W))) return rc;
+            if ((rc = dev_realloc(ctx, &ctx->flo_xw, V * W))) return rc;
+            if ((rc = dev_realloc(ctx, &ctx->flo_yw, V * W))) return rc;
+            if ((rc = dev_realloc(ctx, &ctx->flo_dw, V * W))) return rc;
+            if ((rc = dev_realloc(ctx, &ctx->flo_rc, V * W))) return rc;
+            if ((rc = dev_realloc(ctx, &ctx->flo_dx, V * W))) return rc;
+            if ((rc = dev_realloc(ctx, &ctx->flo_dy, V * W))) return rc;
+            if ((rc = dev_realloc(ctx, &ctx->flo_fs, V * W))) return rc;
+            if ((rc = dev_realloc(ctx, &ctx->agg, V * L * ctx->n_groups * 2))) return rc;
+            if ((rc = dev_realloc(ctx, &ctx->zbuf, V * W))) return rc;
+            if ((rc = dev_realloc(ctx, &ctx->row_rec, V * H))) return rc;
+            if (ctx->keep_columns) {
+                if ((rc = dev_realloc(ctx, &ctx->dbg_cols, V * L * W))) return rc;
+                ctx->dbg_levels = (int)L; ctx->dbg_views = (int)V;
+            }
+            if ((rc = dev_realloc(ctx, &ctx->draw_rec, S))) return rc;
+            if ((rc = dev_realloc(ctx, &ctx->n_draw, V))) return rc;
+            if ((rc = dev_realloc(ctx, &ctx->bin_list, S * ctx->n_groups))) return rc;
+            if ((rc = dev_realloc(ctx, &ctx->bin_rect, S * ctx->n_groups))) return rc;
+            if ((rc = dev_realloc(ctx, &ctx->bin_count, V * ctx->n_groups))) return rc;
+            if ((rc = dev_realloc(ctx, &ctx->rects, S))) return rc;
+            if ((rc = dev_realloc(ctx, &ctx->conv, V))) return rc;
+            return PM3D_OK;
+        };
+        rc = alloc_set();
+        pm3d_save_set(ctx, k);  // on failure too: the set must not keep pointers dev_realloc already freed
+        if (rc) return rc;
         if (!fs.ev_front) {
             PM3D_CUDA(ctx, cudaEventCreateWithFlags(&fs.ev_front, cudaEventDisableTiming));
             PM3D_CUDA(ctx, cudaEventCreateWithFlags(&fs.ev_compose, cudaEventDisableTiming));
@@ -501,7 +550,8 @@ static int render_core(pm3d_ctx *ctx, int n_views, int n_sprites, uint8_t *targe
 
 // Select the frame set of the next frame: the named per-frame fields alias it from here on.  Its previous
 // user (the compose kernel two frames back) must be done before the front stream writes into it, and
-// everything enqueued on the main stream so far (uploads, caller-visible ordering) precedes the frame.
+// everything enqueued on the main stream so far (sprite lists, clutter, uploads, timers: whatever the caller
+// ordered before this frame) precedes the frame: order_after_main.
 static int pm3d_begin_frame(pm3d_ctx *ctx, int n_views, cudaStream_t *fstream, int lane = 0) {
     if (ctx->n_sets > 1) {
         ctx->lane_cur[lane] ^= 1;
@@ -517,6 +567,10 @@ static int pm3d_begin_frame(pm3d_ctx *ctx, int n_views, cudaStream_t *fstream, i
             ctx->cur_cstream = ctx->lane_cstream[lane];
         }
         PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->cur_fstream, ctx->sets[ctx->cur_set].ev_compose, 0));
+        uint64_t *seen = lane ? &ctx->seen_lane[lane] : (ctx->cur_fstream == ctx->front_stream ? &ctx->seen_front : &ctx->seen_front_lo);
+        int rc = order_after_main(ctx, ctx->cur_fstream, seen);
+        if (rc) return rc;
+        if (lane) ctx->lanes_dirty = true;
         *fstream = ctx->cur_fstream;
     } else {
         ctx->cur_cstream = ctx->stream;
@@ -569,7 +623,7 @@ int pm3d_download_results(pm3d_ctx *ctx, pm3d_rect *out_rects, pm3d_convergence 
     if (out_conv)
         PM3D_CUDA(ctx, cudaMemcpyAsync(out_conv, ctx->conv, (size_t)ctx->last_views * sizeof(pm3d_convergence), cudaMemcpyDeviceToHost, ctx->stream));
     PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return PM3D_OK;
+    return pm3d_check_status(ctx);
 }
 
 int pm3d_ktimer_begin(pm3d_ctx *ctx, int max_frames) {
@@ -747,8 +801,10 @@ int pm3d_frame_checksums(pm3d_ctx *ctx, int n_views, uint64_t *out, uint32_t fla
     if (!ctx->last_frame || n_views < 1 || n_views > ctx->last_views || !out) return pm3d_fail(ctx, PM3D_ERR_ARG, "nothing rendered / bad arguments");
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
     PM3D_CUDA(ctx, wait_last_frame(ctx));
-    int rc = pm3d_launch_checksum(ctx, n_views, ctx->last_frame);
+    int rc = pm3d_main_enter(ctx);
     if (rc) return rc;
+    if ((rc = pm3d_launch_checksum(ctx, n_views, ctx->last_frame))) return rc;
+    pm3d_main_touch(ctx);
     if (flags & PM3D_OUT_DEVICE)
         PM3D_CUDA(ctx, cudaMemcpyAsync(out, ctx->checksums, (size_t)n_views * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     else
@@ -885,15 +941,19 @@ int pm3d_host_free(pm3d_ctx *ctx, void *ptr) {
 int pm3d_memcpy_h2d(pm3d_ctx *ctx, void *dst, const void *src, int64_t bytes) {
     if (!ctx) return PM3D_ERR_ARG;
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    { int rc = pm3d_main_enter(ctx); if (rc) return rc; }
     PM3D_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
     PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    pm3d_main_touch(ctx);
     return PM3D_OK;
 }
 int pm3d_memcpy_d2h(pm3d_ctx *ctx, void *dst, const void *src, int64_t bytes) {
     if (!ctx) return PM3D_ERR_ARG;
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    { int rc = pm3d_main_enter(ctx); if (rc) return rc; }
     PM3D_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
     PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    pm3d_main_touch(ctx);
     return PM3D_OK;
 }
 
@@ -904,24 +964,21 @@ int pm3d_timer_start(pm3d_ctx *ctx, int slot) {
         PM3D_CUDA(ctx, cudaEventCreate(&ctx->ev_start[slot]));
         PM3D_CUDA(ctx, cudaEventCreate(&ctx->ev_stop[slot]));
     }
+    int rc = pm3d_main_enter(ctx);  // the start event follows the frames already enqueued on every lane
+    if (rc) return rc;
     PM3D_CUDA(ctx, cudaEventRecord(ctx->ev_start[slot], ctx->stream));
-    // fork: nothing of the timed region may start on another lane before the start event
-    for (int l = 1; l < ctx->n_lanes; l++) {
-        if (!ctx->lane_cstream[l]) continue;
-        PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_cstream[l], ctx->ev_start[slot], 0));
-        PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_fstream[l], ctx->ev_start[slot], 0));
-    }
+    // fork: nothing of the timed region may start on a front stream or another lane before the start event —
+    // the next frame of every lane (lane 0's front streams included) waits for the main stream
+    pm3d_main_touch(ctx);
     return PM3D_OK;
 }
 int pm3d_timer_stop(pm3d_ctx *ctx, int slot) {
     if (!ctx || slot < 0 || slot >= 16 || !ctx->ev_stop[slot]) return PM3D_ERR_ARG;
     // join: the stop event follows the last frame of every lane
-    for (int l = 1; l < ctx->n_lanes; l++) {
-        if (!ctx->lane_cstream[l]) continue;
-        PM3D_CUDA(ctx, cudaEventRecord(ctx->lane_join[l], ctx->lane_cstream[l]));
-        PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lane_join[l], 0));
-    }
+    int rc = pm3d_main_enter(ctx);
+    if (rc) return rc;
     PM3D_CUDA(ctx, cudaEventRecord(ctx->ev_stop[slot], ctx->stream));
+    pm3d_main_touch(ctx);
     return PM3D_OK;
 }
 int pm3d_timer_elapsed_ms(pm3d_ctx *ctx, int slot, float *ms) {
@@ -940,7 +997,9 @@ int pm3d_flush_l2(pm3d_ctx *ctx) {
         ctx->flush_bytes = (size_t)256 << 20;  // 256 MiB > 126 MB L2
         PM3D_CUDA(ctx, cudaMalloc((void **)&ctx->flush_buf, ctx->flush_bytes));
     }
+    { int rc = pm3d_main_enter(ctx); if (rc) return rc; }
     PM3D_CUDA(ctx, cudaMemsetAsync(ctx->flush_buf, 0, ctx->flush_bytes, ctx->stream));
+    pm3d_main_touch(ctx);
     return PM3D_OK;
 }
 

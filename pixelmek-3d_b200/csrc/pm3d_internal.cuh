@@ -166,6 +166,25 @@ struct pm3d_ctx {
     cudaStream_t front_stream_lo = nullptr;  // default priority: large batches (both launches fill the chip)
     cudaStream_t cur_fstream = nullptr;      // the one the frame batch being enqueued uses
 
+    // ---- ordering between the main stream and the frame streams.  The ctx promises ONE stream's semantics to its
+    // caller (include/pm3d.h): whatever was enqueued on `stream` before a frame call precedes that frame, and
+    // whatever is enqueued on `stream` after frame calls follows them.  Frames run on other streams (front streams,
+    // lanes), so the two directions are made explicit:
+    //   main -> frame: every entry point that enqueues non-frame work on `stream` bumps main_seq (pm3d_main_touch);
+    //                  pm3d_begin_frame records ev_main on `stream` and makes the frame's front stream wait for it
+    //                  whenever that stream has not yet seen the current main_seq (a pure frame loop pays nothing);
+    //   frame -> main: pm3d_main_enter joins the compose streams of lanes >= 1 into `stream` when frames were
+    //                  dealt to them since the last join.
+    // A ctx on a CALLER stream cannot see what the caller enqueues there: every frame then counts as "main touched".
+    cudaEvent_t ev_main = nullptr;
+    uint64_t main_seq = 1;
+    uint64_t seen_front = 0, seen_front_lo = 0, seen_lane[PM3D_MAX_LANES] = {};
+    bool lanes_dirty = false;
+    // device -> host error words in mapped pinned memory (kernels store, pm3d_sync reads after the streams drained):
+    //   [0] 1 + index of a view whose sprite_offset entries are out of range (resident path: offsets live in HBM)
+    //   [1] 1 when pm3d_raycast_sprites_batch listed more than max_total sprites (PM3D_NO_SYNC path)
+    uint32_t *status_h = nullptr, *status_d = nullptr;
+
     // inputs the kernels read this call (ctx-owned copies, or caller device memory)
     const pm3d_view *cur_views = nullptr;
     const pm3d_sprite *cur_sprites = nullptr;
@@ -212,6 +231,10 @@ struct pm3d_ctx {
 };
 
 int pm3d_fail(pm3d_ctx *ctx, int code, const char *fmt, ...);
+enum { PM3D_STATUS_VIEW_SPRITES = 0, PM3D_STATUS_LIST_TOTAL = 1, PM3D_STATUS_WORDS = 16 };
+int pm3d_main_enter(pm3d_ctx *ctx);                 // before enqueueing non-frame work on ctx->stream (see ev_main)
+inline void pm3d_main_touch(pm3d_ctx *ctx) { ctx->main_seq++; }  // after it
+int pm3d_check_status(pm3d_ctx *ctx);               // after a host sync: device error words -> PM3D_ERR_CAPACITY
 // event pair around kernel `k` (0 cast, 1 view setup, 2 compose) of the frame being sampled
 inline void pm3d_kt_mark(pm3d_ctx *ctx, int k, int end, cudaStream_t stream) {
     if (ctx->kt_on && ctx->kt_n < ctx->kt_cap) cudaEventRecord(ctx->kt_ev[(ctx->kt_n * 3 + k) * 2 + end], stream);

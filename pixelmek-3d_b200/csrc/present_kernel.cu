@@ -201,7 +201,9 @@ extern "C" int pm3d_present(pm3d_ctx *ctx, const uint8_t *d_src, int n_views, in
     p.n_quads = (long long)n_views * p.oh * ((p.ow + 3) / 4);
     if (p.oh > 65535 || n_views > 65535) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "present: too many rows / views for one launch");
     const dim3 grid((unsigned)(((p.ow + 3) / 4 + 255) / 256), (unsigned)p.oh, (unsigned)n_views);
+    { int rc_ = pm3d_main_enter(ctx); if (rc_) return rc_; }
     k_present<<<grid, 256, 0, ctx->stream>>>(p);
+    pm3d_main_touch(ctx);
     ctx->launches++;
     PM3D_CUDA(ctx, cudaGetLastError());
     if (!(flags & PM3D_OUT_DEVICE)) PM3D_CUDA(ctx, cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, ctx->stream));

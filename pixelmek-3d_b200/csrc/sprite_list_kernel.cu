@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(LIST_THREADS) k_list_count(const __grid_consta
 }
 
 // exclusive scan of the counts in place: out_offset[0] = 0, out_offset[v + 1] = sum of the counts of cameras <= v
-__global__ void __launch_bounds__(1024) k_list_scan(int32_t *off, int n) {
+__global__ void __launch_bounds__(1024) k_list_scan(int32_t *off, int n, int max_total, uint32_t *status) {
     __shared__ int warp_tot[32];
     __shared__ int carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -86,6 +86,12 @@ __global__ void __launch_bounds__(1024) k_list_scan(int32_t *off, int n) {
         __syncthreads();
         if (threadIdx.x == 0) carry += warp_tot[31];
         __syncthreads();
+    }
+    // an enqueue-only caller (PM3D_NO_SYNC) never sees the total: more sprites than max_total raises the ctx's error
+    // word (k_list_write cuts the lists at max_total; pm3d_sync returns PM3D_ERR_CAPACITY)
+    if (threadIdx.x == 0 && carry > max_total) {
+        *reinterpret_cast<volatile uint32_t *>(status + PM3D_STATUS_LIST_TOTAL) = 1u;
+        __threadfence_system();
     }
 }
 
@@ -157,6 +163,7 @@ extern "C" int pm3d_raycast_sprites_batch(pm3d_ctx *ctx, const pm3d_sprite *worl
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool in_dev = flags & PM3D_IN_DEVICE, out_dev = flags & PM3D_OUT_DEVICE;
     int rc;
+    if ((rc = pm3d_main_enter(ctx))) return rc;
     ListParams p;
     p.world = world; p.queries = queries; p.clutter = clutter; p.clutter_count = clutter_count;
     p.extras = extras; p.extra_offset = extra_offset;
@@ -203,10 +210,11 @@ extern "C" int pm3d_raycast_sprites_batch(pm3d_ctx *ctx, const pm3d_sprite *worl
     p.reach = ceil(render_distance);
     p.n_world = n_world; p.n = n; p.clutter_stride = clutter_stride; p.max_total = max_total;
     k_list_count<<<n, LIST_THREADS, 0, ctx->stream>>>(p);
-    k_list_scan<<<1, 1024, 0, ctx->stream>>>(p.out_offset, n);
+    k_list_scan<<<1, 1024, 0, ctx->stream>>>(p.out_offset, n, max_total, ctx->status_d);
     k_list_write<<<n, LIST_THREADS, 0, ctx->stream>>>(p);
     ctx->launches += 3;
     PM3D_CUDA(ctx, cudaGetLastError());
+    pm3d_main_touch(ctx);
     if (flags & PM3D_NO_SYNC) {
         if (!out_dev) return pm3d_fail(ctx, PM3D_ERR_ARG, "PM3D_NO_SYNC needs PM3D_OUT_DEVICE here (the copy size is the device-side total)");
         return PM3D_OK;
@@ -215,6 +223,7 @@ extern "C" int pm3d_raycast_sprites_batch(pm3d_ctx *ctx, const pm3d_sprite *worl
     PM3D_CUDA(ctx, cudaMemcpyAsync(&total, p.out_offset + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
     PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (out_total) *out_total = total;
+    if (total > max_total) ctx->status_h[PM3D_STATUS_LIST_TOTAL] = 0;  // reported right here
     if (total > max_total) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "the cameras list %d sprites, max_total is %d", total, max_total);
     if (!out_dev) {
         PM3D_CUDA(ctx, cudaMemcpyAsync(out_offset, p.out_offset, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -26,6 +26,8 @@ struct ViewParams {
     int4 *bin_count;   // per (view, group): x = entries, y = min dsy, z = max dey
     pm3d_rect *rects;
     pm3d_convergence *conv;
+    uint32_t *status;     // device error words (pm3d_ctx::status_d)
+    int n_sprites_total;  // what the caller declared for this batch: offsets must stay inside it
     int w, h, tex_size, n_sheets, n_groups, sky_tile, floorbox_tile;
 };
 
@@ -81,8 +83,19 @@ __device__ __forceinline__ void view_setup(const ViewParams &p, const int view) 
     }
 
     // ---------------- (b) sprites
-    const int s0 = p.sprite_offset[view];
-    const int n = p.sprite_offset[view + 1] - s0;
+    // pm3d_render validates the offsets on the host; pm3d_render_resident cannot (they live in HBM, written by
+    // pm3d_raycast_sprites_batch or by the caller), so they are checked here: a view whose entries are negative, not
+    // monotone, hold more sprites than the shared-memory sort takes or point past the declared total renders without
+    // sprites and raises the ctx's error word (pm3d_sync / pm3d_download_results then return PM3D_ERR_CAPACITY).
+    int s0 = p.sprite_offset[view];
+    int n = p.sprite_offset[view + 1] - s0;
+    if (s0 < 0 || n < 0 || n > MAX_VIEW_SPRITES || s0 > p.n_sprites_total - n) {
+        if (tid == 0) {
+            *reinterpret_cast<volatile uint32_t *>(p.status + PM3D_STATUS_VIEW_SPRITES) = 1u + (uint32_t)view;
+            __threadfence_system();
+        }
+        s0 = 0; n = 0;
+    }
     const pm3d_sprite *sprites = p.sprites + s0;
     DrawRec *draw = p.draw_rec + s0;
 

@@ -117,3 +117,139 @@ def test_resident_chain_from_poses_to_frames(gpu_ctx):
         assert np.array_equal(frames[i], ref["rgba"]), f"view {i}"
         n_clutter_seen += len(recs)
     assert n_clutter_seen > 300
+
+
+def _tick_setup(ctx, n, w, h, n_sets, rd=60.0, cdist=12.0):
+    """Device-resident inputs of `n_sets` different pose sets for the chain clutter -> sprite list -> frames."""
+    scene, g = W.proving_grounds_scene()
+    scene.sheets = list(scene.sheets) + [W.sprite_sheet(18, 18, 41), W.sprite_sheet(24, 24, 42)]
+    ctx.upload_scene(scene)
+    clutter = [cl.MapClutter(str(im), float(f), float(hh), str(m) or None) for im, m, f, hh in
+               zip(g["clutter_image"], g["clutter_match"], g["clutter_frequency"], g["clutter_height"])]
+    sheets = {clutter[0].image: (len(scene.sheets) - 2, 18, 18), clutter[1].image: (len(scene.sheets) - 1, 24, 24)}
+    defs, cls, masks = cl.resolve_clutter(clutter, g["floor_grid"], [str(s) for s in g["floor_images"]], sheets)
+    ctx.upload_clutter(defs, cls, masks, int(g["map_seed"]))
+    world = W.golden_sprites(scene, g)
+    stride = 21 * (int(cdist) + 1) * len(clutter)
+    max_total = n * (len(world) + stride)
+    ctx.set_view(w, h, n, max_total)
+    poses = W.free_cell_poses(scene, n * n_sets, 2024)
+    views = W.make_views(scene, w, h, poses, render_distance=rd)
+    cq = cl.clutter_queries([(p[0], p[1], p[3]) for p in poses], 70.0)
+    lq = sp.list_queries([(p[0], p[1]) for p in poses])
+    bufs = dict(views=views.nbytes, cq=cq.nbytes, lq=lq.nbytes, world=world.nbytes, cnt=4 * n, rec=32 * n * stride,
+                cspr=64 * n * stride, spr=64 * max_total, off=4 * (n + 1), out=n * w * h * 4)
+    d = {k: ctx.device_alloc(v) for k, v in bufs.items()}
+    ctx.h2d(d["views"], views); ctx.h2d(d["cq"], cq); ctx.h2d(d["lq"], lq); ctx.h2d(d["world"], world)
+    return dict(d=d, n=n, stride=stride, max_total=max_total, n_world=len(world), rd=rd, cdist=cdist,
+                sz=(views.itemsize, cq.itemsize, lq.itemsize))
+
+
+def _run_ticks(ctx, s, ticks, n_sets, d_sums, synced):
+    """`ticks` ticks; tick t uses pose set t % n_sets and leaves its per-view checksums at d_sums[t].  The render call
+    is told the CAPACITY of the list (the host never reads the total of an unsynced tick)."""
+    L = pm3d._lib
+    d, n = s["d"], s["n"]
+    flags = L.PM3D_IN_DEVICE | L.PM3D_OUT_DEVICE | L.PM3D_NO_SYNC
+    vsz, csz, lsz = s["sz"]
+    for t in range(ticks):
+        k = (t % n_sets) * n
+        ctx._check(ctx.lib.pm3d_clutter_batch(ctx.h, d["cq"] + k * csz, n, s["cdist"], s["stride"], d["cnt"], d["rec"], d["cspr"], flags), "clutter")
+        if synced:
+            ctx.sync()
+        ctx._check(ctx.lib.pm3d_raycast_sprites_batch(ctx.h, d["world"], s["n_world"], d["lq"] + k * lsz, n, s["rd"], d["cspr"], d["cnt"],
+                                                      s["stride"], None, None, s["max_total"], d["spr"], d["off"], None, None, flags), "list")
+        if synced:
+            ctx.sync()
+        ctx.render_resident(d["views"] + k * vsz, n, d["spr"], d["off"], s["max_total"], d["out"])
+        if synced:
+            ctx.sync()
+        ctx._check(ctx.lib.pm3d_frame_checksums(ctx.h, n, d_sums + t * n * 8, L.PM3D_OUT_DEVICE | L.PM3D_NO_SYNC), "checksums")
+        if synced:
+            ctx.sync()
+
+
+@pytest.mark.parametrize("n,w,h", [(8, 320, 200), (64, 320, 200), (512, 160, 100)])
+@pytest.mark.parametrize("lanes", [1, 3])
+def test_unsynced_chain_equals_the_synced_chain(gpu_ctx, n, w, h, lanes):
+    """200 ticks of poses -> clutter -> sprite list -> frames -> checksums with NO pm3d_sync between any two calls and
+    poses that change every tick (consecutive ticks list different numbers of sprites, so a front kernel that ran
+    beside the list kernels of its own tick would read counts instead of offsets).  Every tick's per-view checksums
+    must equal those of the same chain run with a sync after every call.  Regression test of the round-1 N=8 crash:
+    the frame's front stream did not wait for the ctx stream."""
+    ctx = gpu_ctx
+    ticks, n_sets = 200, 5
+    ctx.set_option(pm3d._lib.OPT_LANES, lanes)
+    s = _tick_setup(ctx, n, w, h, n_sets)
+    d_a, d_b = ctx.device_alloc(ticks * n * 8), ctx.device_alloc(n_sets * n * 8)
+    try:
+        _run_ticks(ctx, s, ticks, n_sets, d_a, synced=False)
+        ctx.sync()
+        a = np.zeros((ticks, n), dtype=np.uint64)
+        ctx.d2h(a, d_a)
+        _run_ticks(ctx, s, n_sets, n_sets, d_b, synced=True)
+        b = np.zeros((n_sets, n), dtype=np.uint64)
+        ctx.d2h(b, d_b)
+        off = np.zeros(n + 1, dtype=np.int32)
+        ctx.d2h(off, s["d"]["off"])
+    finally:
+        for p in list(s["d"].values()) + [d_a, d_b]:
+            ctx.device_free(p)
+        ctx.set_option(pm3d._lib.OPT_LANES, 1)
+        ctx.set_view(w, h, 1, 1)
+    assert off[-1] > n * 50 and len(set(np.diff(off).tolist())) > 1   # the lists are not trivial
+    assert len({tuple(r) for r in b.tolist()}) == n_sets               # ... and the pose sets give different frames
+    for t in range(ticks):
+        assert np.array_equal(a[t], b[t % n_sets]), f"tick {t}: {int((a[t] != b[t % n_sets]).sum())} of {n} views differ"
+
+
+def test_resident_render_rejects_bad_offsets(gpu_ctx):
+    """pm3d_render_resident cannot validate offsets that live in HBM: the view setup does, on the device — a view whose
+    offsets are out of range renders without sprites and pm3d_sync reports PM3D_ERR_CAPACITY."""
+    ctx = gpu_ctx
+    cfg = W.config_c2(320, 200, 40, n_poses=1)
+    ctx.upload_scene(cfg["scene"])
+    ctx.set_view(320, 200, 1, 4096)
+    views, sprites = cfg["views"], cfg["sprites"]
+    big = np.resize(sprites, 4096)
+    d_v, d_s, d_o, d_out = ctx.device_alloc(views.nbytes), ctx.device_alloc(big.nbytes), ctx.device_alloc(8), ctx.device_alloc(320 * 200 * 4)
+    try:
+        ctx.h2d(d_v, views); ctx.h2d(d_s, big)
+        ctx.render(views, None)
+        plain = ctx.frame_checksums(1)[0]
+        for bad in ([0, 3000], [5, 2], [-4, 10], [4000, 4200]):   # > 2048 per view, not monotone, negative, past the total
+            ctx.h2d(d_o, np.array(bad, dtype=np.int32))
+            ctx.render_resident(d_v, 1, d_s, d_o, 4096, d_out)
+            with pytest.raises(pm3d.Pm3dError, match="sprite_offset"):
+                ctx.sync()
+            assert ctx.frame_checksums(1)[0] == plain              # rendered, without sprites
+            ctx.sync()                                              # the error was reported once
+        ctx.h2d(d_o, np.array([0, 40], dtype=np.int32))
+        ctx.render_resident(d_v, 1, d_s, d_o, 4096, d_out)
+        ctx.sync()
+        assert ctx.frame_checksums(1)[0] != plain
+    finally:
+        for p in (d_v, d_s, d_o, d_out):
+            ctx.device_free(p)
+
+
+def test_unsynced_list_overflow_is_reported(gpu_ctx):
+    ctx = gpu_ctx
+    L = pm3d._lib
+    scene, g = W.proving_grounds_scene()
+    world = W.golden_sprites(scene, g)
+    q = sp.list_queries([(30.0, 30.0), (31.0, 29.0)])
+    d_w, d_q = ctx.device_alloc(world.nbytes), ctx.device_alloc(q.nbytes)
+    cap = len(world) + 3
+    d_s, d_o = ctx.device_alloc(64 * cap), ctx.device_alloc(12)
+    try:
+        ctx.h2d(d_w, world); ctx.h2d(d_q, q)
+        flags = L.PM3D_IN_DEVICE | L.PM3D_OUT_DEVICE | L.PM3D_NO_SYNC
+        ctx._check(ctx.lib.pm3d_raycast_sprites_batch(ctx.h, d_w, len(world), d_q, 2, -1.0, None, None, 0, None, None, cap, d_s, d_o,
+                                                      None, None, flags), "list")
+        with pytest.raises(pm3d.Pm3dError, match="max_total"):
+            ctx.sync()
+        ctx.sync()
+    finally:
+        for p in (d_w, d_q, d_s, d_o):
+            ctx.device_free(p)

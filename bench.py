@@ -148,8 +148,6 @@ def base_line(args, world, value, ms_per_step):
             "workload": "c2: proving_grounds 500x500x3, 1920x1080, floor cast, 200 sprites, fov 70, render distance 100 cells",
             "rays_per_frame": W_PX * 3, "pixels_per_frame": W_PX * H_PX, "ring": RING,
             "l2": f"ring of {RING} distinct poses and output framebuffers = {RING * FRAME_BYTES / 1e6:.0f} MB > 126 MB L2",
-            "parallelism": f"{world} independent camera(s), one per GPU; no data-path collective; frames are enqueued "
-                           "back to back, the cast/setup launch of frame i+1 overlaps the compose launch of frame i",
         },
     }
 
@@ -170,7 +168,7 @@ def run_reference(args, rank, world):
     line = base_line(args, world, value, 1e3 * sec / n)
     line["impl"] = "reference"
     line["n_gpus"] = world
-    line["config"]["parallelism"] = f"CPU oracle port, {threads} OpenMP threads (rank 0 only)"
+    line["parallelism"] = f"CPU oracle port, {threads} OpenMP threads (rank 0 only)"
     line["cpu_baseline"] = {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
                             "sample": f"{n} full 1920x1080 frames of the c2 ring; the Go reference cannot be built here (no Go toolchain), this is the C restatement in oracle/"}
     line["e2e"] = {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
@@ -182,7 +180,9 @@ def run_reference(args, rank, world):
 
 
 def sweep_c4(ctx, rank, world, dist, torch, dev):
-    """4096 views of 320x200 sharded i % world; returns dict for 'extra'."""
+    """4096 views of 320x200 sharded i % world through pm3d_comm_render_views: every rep renders this rank's views,
+    checksums them and all-gathers (convergence, checksum) of ALL views to every rank — the gather is inside the
+    timed region, enqueued by the library behind the kernels."""
     from pm3d import shard, workloads as Wk
 
     n_views, w, h = 4096, 320, 200
@@ -200,8 +200,10 @@ def sweep_c4(ctx, rank, world, dist, torch, dev):
     ctx.h2d(d_views, views); ctx.h2d(d_spr, sprites); ctx.h2d(d_off, offs)
     fb = nv * w * h * 4
     d_out = ctx.device_alloc(fb)
+    d_conv, d_sums = ctx.device_alloc(n_views * 32), ctx.device_alloc(n_views * 8)
+    call = lambda: ctx.comm_render_views(d_views, nv, d_spr, d_off, ns, d_out, n_views, d_conv, d_sums)
     for _ in range(3):
-        ctx.render_resident(d_views, nv, d_spr, d_off, ns, d_out)
+        call()
     ctx.sync()
     reps = 5
     if world > 1:
@@ -210,25 +212,29 @@ def sweep_c4(ctx, rank, world, dist, torch, dev):
     ctx.ktimer_begin(reps)
     ctx.timer_start(2)
     for _ in range(reps):
-        ctx.render_resident(d_views, nv, d_spr, d_off, ns, d_out)
+        call()
     ctx.timer_stop(2)
     ms = ctx.timer_ms(2) / reps
     kt = ctx.ktimer_collect(reps)
-    sums = ctx.frame_checksums(nv)
+    sums = np.zeros(n_views, dtype=np.uint64)   # every rank holds every view's checksum
+    ctx.sync(); ctx.d2h(sums, d_sums)
+    total = int(sums.view(np.int64).sum()) & 0xFFFFFFFFFFFFFFFF
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    tot = torch.tensor([total & 0x7FFFFFFFFFFFFFFF], device=dev, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        g = shard.gather_views(torch.from_numpy(sums.view(np.int64)).to(dev), n_views, rank, world)
-        total = int(g.sum().item()) & 0xFFFFFFFFFFFFFFFF
-    else:
-        total = int(sums.view(np.int64).sum()) & 0xFFFFFFFFFFFFFFFF
-    for p in (d_views, d_spr, d_off, d_out):
+        lo_, hi_ = tot.clone(), tot.clone()
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN); dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        if int(lo_.item()) != int(hi_.item()):
+            raise RuntimeError("c4: the ranks hold different gathered checksums")
+    for p in (d_views, d_spr, d_off, d_out, d_conv, d_sums):
         ctx.device_free(p)
     ms_max = float(t.item())
     peak, _ = hbm_peak()
     compose_ms = float(kt[:, 2].mean())
     return {
-        "workload": "c4: 4096 views 320x200, 50 nearest sprites each, sharded i % n_gpus",
+        "workload": "c4: 4096 views 320x200, 50 nearest sprites each, sharded i % n_gpus; per rep render + checksum + "
+                    "ncclAllGather of (convergence, checksum) of all views to every rank (pm3d_comm_render_views), gather timed",
         "views_per_s": n_views / (ms_max * 1e-3), "ms_per_sweep": ms_max, "views_per_gpu": nv,
         "compose_ms": compose_ms, "front_ms": float(kt[:, 0].mean()),
         "hbm_frac_compose": (fb / (compose_ms * 1e-3)) / 1e9 / peak,
@@ -295,7 +301,8 @@ def sweep_c3(ctx):
 
 
 def sweep_c5(ctx, rank, world, dist, torch, dev):
-    """16 Mi LOS rays on a 256x256 map, contiguous shards; returns dict for 'extra'."""
+    """16 Mi LOS rays on a 256x256 map, contiguous shards, through pm3d_comm_los_batch: every rep answers this rank's
+    range and all-gathers the 1 B/ray answers of ALL rays to every rank inside the timed region."""
     from pm3d import shard, workloads as Wk
 
     n_rays = 1 << 24
@@ -307,34 +314,36 @@ def sweep_c5(ctx, rank, world, dist, torch, dev):
     rays = Wk.los_rays(grid[0], n_rays, 43)[lo:hi]
     n = len(rays)
     ctx.upload_segments(segs)
-    d_rays, d_out = ctx.device_alloc(rays.nbytes), ctx.device_alloc(n)
+    d_rays, d_out = ctx.device_alloc(rays.nbytes), ctx.device_alloc(n_rays)
     ctx.h2d(d_rays, rays)
-    lib, C = ctx.lib, __import__("ctypes")
-    flags = 1 | 2 | 4  # OUT_DEVICE | IN_DEVICE | NO_SYNC
+    call = lambda: ctx.comm_los_batch(d_rays, n, n_rays, d_out)
     for _ in range(2):
-        ctx._check(lib.pm3d_los_batch(ctx.h, C.c_void_p(d_rays), n, C.c_void_p(d_out), flags), "pm3d_los_batch")
+        call()
     ctx.sync()
     if world > 1:
         dist.barrier()
     reps = 3
     ctx.timer_start(3)
     for _ in range(reps):
-        ctx._check(lib.pm3d_los_batch(ctx.h, C.c_void_p(d_rays), n, C.c_void_p(d_out), flags), "pm3d_los_batch")
+        call()
     ctx.timer_stop(3)
     ms = ctx.timer_ms(3) / reps
-    out = np.zeros(n, dtype=np.uint8)
+    out = np.zeros(n_rays, dtype=np.uint8)   # every rank holds every ray's answer
     ctx.d2h(out, d_out)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     visible = torch.tensor([int(out.sum())], device=dev, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        g = shard.gather_rays(torch.from_numpy(out).to(dev), n_rays, rank, world)
-        visible = g.sum(dtype=torch.int64).reshape(1)
+        vlo, vhi = visible.clone(), visible.clone()
+        dist.all_reduce(vlo, op=dist.ReduceOp.MIN); dist.all_reduce(vhi, op=dist.ReduceOp.MAX)
+        if int(vlo.item()) != int(vhi.item()):
+            raise RuntimeError("c5: the ranks hold different gathered answers")
     ctx.device_free(d_rays); ctx.device_free(d_out)
     ms_max = float(t.item())
     peak, _ = hbm_peak()
     return {
-        "workload": f"c5: 16777216 LOS rays, 256x256 map 10% walls, {len(segs)} collision segments, contiguous shards",
+        "workload": f"c5: 16777216 LOS rays, 256x256 map 10% walls, {len(segs)} collision segments, contiguous shards; per rep "
+                    "k_los + all-gather of the 16 MiB of answers to every rank (pm3d_comm_los_batch), gather timed",
         "mrays_per_s": n_rays / (ms_max * 1e-3) / 1e6, "ms_per_batch": ms_max, "rays_per_gpu": n,
         "hbm_frac": (33.0 * n / (ms * 1e-3)) / 1e9 / peak, "visible_rays": int(visible.item()),
     }
@@ -478,7 +487,7 @@ def sweep_tick(ctx, rank, world, dist, torch, dev):
     ctx.upload_clutter(defs, cls, masks, int(g["map_seed"]))
     ctx.set_view(w, h, n, max_total)
     sizes = dict(views=views.nbytes, cq=cq.nbytes, lq=lq.nbytes, world=world_sprites.nbytes, cnt=4 * n, rec=32 * n * stride,
-                 cspr=64 * n * stride, spr=64 * max_total, off=4 * (n + 1), out=n * w * h * 4)
+                 cspr=64 * n * stride, spr=64 * max_total, off=4 * (n + 1), out=n * w * h * 4, conv=32 * n_all, sums=8 * n_all)
     d = {k: ctx.device_alloc(v) for k, v in sizes.items()}
     ctx.h2d(d["views"], views); ctx.h2d(d["cq"], cq); ctx.h2d(d["lq"], lq); ctx.h2d(d["world"], world_sprites)
     flags = L.PM3D_IN_DEVICE | L.PM3D_OUT_DEVICE | L.PM3D_NO_SYNC
@@ -492,7 +501,7 @@ def sweep_tick(ctx, rank, world, dist, torch, dev):
             off = np.zeros(n + 1, dtype=np.int32)
             ctx.sync(); ctx.d2h(off, d["off"])
             total[0] = int(off[-1])
-        ctx.render_resident(d["views"], n, d["spr"], d["off"], total[0], d["out"])
+        ctx.comm_render_views(d["views"], n, d["spr"], d["off"], total[0], d["out"], n_all, d["conv"], d["sums"])
 
     tick(first=True); tick(); ctx.sync()
     if world > 1:
@@ -503,7 +512,8 @@ def sweep_tick(ctx, rank, world, dist, torch, dev):
         tick()
     ctx.timer_stop(8)
     ms = ctx.timer_ms(8) / reps
-    sums = ctx.frame_checksums(n)
+    sums = np.zeros(n_all, dtype=np.uint64)
+    ctx.sync(); ctx.d2h(sums, d["sums"])       # gathered by the library: every rank holds all of them
     for p_ in d.values():
         ctx.device_free(p_)
     ctx.set_view(w, h, 1, 1)
@@ -512,13 +522,10 @@ def sweep_tick(ctx, rank, world, dist, torch, dev):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        gsum = shard.gather_views(torch.from_numpy(sums.view(np.int64)).to(dev), n_all, rank, world)
-        csum = int(gsum.sum().item()) & 0xFFFFFFFFFFFFFFFF
-    else:
-        csum = int(sums.view(np.int64).sum()) & 0xFFFFFFFFFFFFFFFF
+    csum = int(sums.view(np.int64).sum()) & 0xFFFFFFFFFFFFFFFF
     ms_max = float(t.item())
     return {"workload": f"tick: {n_all} cameras at {w}x{h} on proving_grounds, per tick clutter update -> sprite list (408 map sprites within "
-                        f"{rd:.0f} cells + clutter) -> frame, all resident in HBM, sharded i % n_gpus",
+                        f"{rd:.0f} cells + clutter) -> frame -> all-gather of every view's (convergence, checksum), all resident in HBM, sharded i % n_gpus",
             "ticks_per_s": 1e3 / ms_max, "views_per_s": n_all / (ms_max * 1e-3), "ms_per_tick": ms_max,
             "sprites_listed": int(tot.item()), "checksum_of_checksums": f"{csum:016x}"}
 
@@ -566,6 +573,12 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     ctx = pm3d.Context(local_rank)
+    # the library's own NCCL communicator (csrc/comm.cu) gathers the compact results of the sharded sweeps; torch only
+    # carries the 128-byte id from rank 0 to the others (and reduces the timings)
+    uid = [pm3d.comm_unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(uid, src=0)
+    ctx.comm_init(uid[0], rank, world)
 
     # ---- workload: every rank its own ring of cameras
     cfg = Wk.config_c2(W_PX, H_PX, N_SPRITES, n_poses=RING, seed=12345 + 1000 * rank)
@@ -686,8 +699,8 @@ def run_ours(args, rank, world, local_rank):
             traffic = None
 
     line = base_line(args, world, value, elapsed_ms / args.steps)
-    line["config"]["lanes"] = LANES
-    line["config"]["parallelism"] = (f"{world} independent ring(s) of {RING} camera poses, one per GPU; no data-path collective; frames are "
+    line["lanes"] = LANES
+    line["parallelism"] = (f"{world} independent ring(s) of {RING} camera poses, one per GPU; no data-path collective; frames are "
                                      f"enqueued back to back and dealt round-robin to {LANES} lanes of one ctx (PM3D_OPT_LANES: own streams "
                                      "and intermediate buffers per lane, so the cast/setup and compose launches of several frames overlap)")
     line["single_lane"] = {"value": world * args.steps / (single_ms * 1e-3), "unit": "frames/s", "ms_per_step": single_ms / args.steps,
@@ -738,6 +751,29 @@ def run_ours(args, rank, world, local_rank):
                 print(json.dumps(line), flush=True)
             sys.stderr.flush()
             os._exit(1)
+    if extra:
+        # the sharded sweeps as first-class numbers: short, numeric, ahead of `extra` (which a tail-truncating reader
+        # may lose), repeated inside `roofline` and on stderr
+        sw = {"n_gpus": world}
+        if "c4" in extra:
+            sw.update(c4_views_per_s=round(extra["c4"]["views_per_s"], 1), c4_ms_per_sweep=round(extra["c4"]["ms_per_sweep"], 4),
+                      c4_hbm_frac_sweep=round(extra["c4"]["hbm_frac_sweep"], 4), c4_views_per_gpu=extra["c4"]["views_per_gpu"])
+        if "c5" in extra:
+            sw.update(c5_grays_per_s=round(extra["c5"]["mrays_per_s"] / 1e3, 3), c5_ms_per_batch=round(extra["c5"]["ms_per_batch"], 4),
+                      c5_hbm_frac=round(extra["c5"]["hbm_frac"], 4))
+        if "tick" in extra:
+            sw.update(tick_views_per_s=round(extra["tick"]["views_per_s"], 1), tick_ms=round(extra["tick"]["ms_per_tick"], 4))
+        if "moves" in extra:
+            sw.update(moves_g_per_s=round(extra["moves"]["mmoves_per_s"] / 1e3, 3))
+        if "clutter" in extra:
+            sw.update(clutter_m_updates_per_s=round(extra["clutter"]["updates_per_s"] / 1e6, 2))
+        if "astar" in extra:
+            sw.update(astar_k_paths_per_s=round(extra["astar"]["paths_per_s"] / 1e3, 2))
+        sw["gather"] = "in the timed region (library-owned NCCL communicator, pm3d_comm_*)"
+        line["sharded"] = sw
+        line["roofline"]["sweeps"] = sw
+        if rank == 0:
+            print("[pm3d-sweeps] " + json.dumps(sw), file=sys.stderr, flush=True)
     line["extra"] = extra
 
     # ---- CPU baseline beside it (rank 0, N=1 only)

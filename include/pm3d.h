@@ -42,7 +42,7 @@ typedef enum pm3d_status {
     PM3D_ERR_ARG = -1,      /* bad argument / call order */
     PM3D_ERR_CUDA = -2,     /* CUDA runtime failure (incl. "no device": no CPU fallback) */
     PM3D_ERR_CAPACITY = -3, /* exceeds a limit fixed by pm3d_set_view */
-    PM3D_ERR_NCCL = -4
+    PM3D_ERR_NCCL = -4      /* pm3d_comm_* / pm3d_group_*: libnccl missing, no communicator, or an NCCL failure */
 } pm3d_status;
 
 /* raycaster.SpriteAnchor as used at game/model/map.go:143-155 */
@@ -367,6 +367,58 @@ int pm3d_raycast_sprites_batch(pm3d_ctx *ctx, const pm3d_sprite *world, int n_wo
                                int clutter_stride, const pm3d_sprite *extras, const int32_t *extra_offset,
                                int max_total, pm3d_sprite *out_sprites, int32_t *out_offset, int32_t *out_index,
                                int32_t *out_total, uint32_t flags);
+
+/* ------------------------------------------------------------------ multi-GPU: sharded batches + gathers
+ * the path shards without an exchange step.  Unit cameras are independent (one per AI unit,
+ * game/ai_combat.go / game/update_units.go drive one entity each), so a batch of views is dealt round-robin
+ * (view i -> rank i % n); LOS rays are independent (game/collision.go:40-65), so a batch is cut into contiguous
+ * ranges; grid, atlases, sheets and collision segments are replicated on every GPU (a few MB: upload them to every
+ * ctx).  What travels is the COMPACT result of every unit — convergence record + 64-bit frame checksum per view,
+ * one byte per ray — gathered to EVERY rank over NVLink by a collective the library enqueues on the ctx stream right
+ * behind the kernels (no host round trip between compute and gather).  The framebuffers stay where they were
+ * rendered.  The library owns the NCCL communicator (libnccl.so.2 is dlopen'ed on first use, PM3D_NCCL_LIB
+ * overrides the name), so the Go host needs no NCCL binding:
+ *   one process per GPU:  rank 0 calls pm3d_comm_unique_id and hands the 128 bytes to the other ranks (any channel
+ *                         the host has), every rank calls pm3d_comm_init on its ctx;
+ *   one process, n GPUs:  pm3d_group_create makes one ctx per device plus the communicator over them. */
+#define PM3D_COMM_ID_BYTES 128
+#define PM3D_GROUP_MAX 8
+int pm3d_comm_unique_id(uint8_t *id128);
+int pm3d_comm_init(pm3d_ctx *ctx, const uint8_t *id128, int rank, int n_ranks); /* collective: every rank calls it */
+int pm3d_comm_destroy(pm3d_ctx *ctx);                                           /* also done by pm3d_destroy     */
+int pm3d_comm_rank(const pm3d_ctx *ctx);
+int pm3d_comm_size(const pm3d_ctx *ctx);                                        /* 1 without a communicator      */
+/* the sharding arithmetic: how many of n_views rank owns (views rank, rank + n, ...); the ray range [lo, hi) */
+int64_t pm3d_shard_view_count(int64_t n_views, int rank, int n_ranks);
+int pm3d_shard_ray_range(int64_t n_rays, int rank, int n_ranks, int64_t *lo, int64_t *hi);
+/* raw all-gather of bytes_per_rank bytes from every rank (device memory, rank-major in d_recv), enqueue only */
+int pm3d_comm_all_gather(pm3d_ctx *ctx, const void *d_send, void *d_recv, int64_t bytes_per_rank);
+/* pm3d_render_resident for THIS rank's n_local views of a batch of n_views_global (its views in shard order:
+ * global view rank + k * n_ranks is local view k), then the gather: on return (enqueue only, pm3d_sync to wait)
+ * d_all_conv[n_views_global] and d_all_checksums[n_views_global] (device memory, either may be NULL) hold the
+ * convergence record and the frame checksum of EVERY view of the batch, in global view order, on every rank. */
+int pm3d_comm_render_views(pm3d_ctx *ctx, const pm3d_view *d_views, int n_local, const pm3d_sprite *d_sprites,
+                           const int32_t *d_sprite_offset, int n_sprites_total, uint8_t *d_out_rgba, int n_views_global,
+                           pm3d_convergence *d_all_conv, uint64_t *d_all_checksums);
+/* pm3d_los_batch for THIS rank's contiguous range of a batch of n_global rays (d_rays holds rays [lo, hi) of
+ * pm3d_shard_ray_range), written straight into d_all_out + lo, then the gather: d_all_out[n_global] holds every
+ * ray's answer on every rank (enqueue only). */
+int pm3d_comm_los_batch(pm3d_ctx *ctx, const double *d_rays, int64_t n_local, int64_t n_global, uint8_t *d_all_out);
+
+/* One process driving n GPUs (what a single Go game-server process does). */
+typedef struct pm3d_group pm3d_group;
+int pm3d_group_create(const int *devices, int n, pm3d_group **out);
+void pm3d_group_destroy(pm3d_group *g);
+const char *pm3d_group_last_error(const pm3d_group *g); /* g may be NULL for pm3d_group_create failures */
+int pm3d_group_size(const pm3d_group *g);
+pm3d_ctx *pm3d_group_ctx(pm3d_group *g, int i);         /* for the replicated uploads, pm3d_set_view, ... */
+int pm3d_group_sync(pm3d_group *g);
+/* HOST arrays in, compact results of all views out (host): the views are dealt i % n, rendered on their device
+ * (frames stay in that device's frame buffer), gathered, and read back from device 0.  Synchronous. */
+int pm3d_group_render_views(pm3d_group *g, const pm3d_view *views, int n_views, const pm3d_sprite *sprites,
+                            const int32_t *sprite_offset, pm3d_convergence *out_conv, uint64_t *out_checksums);
+/* Game.lineOfSight for n host rays cut into contiguous ranges over the group's devices.  Synchronous. */
+int pm3d_group_los_batch(pm3d_group *g, const double *rays, int64_t n_rays, uint8_t *out);
 
 /* ------------------------------------------------------------------ device memory + timing
  * (so a cgo / ctypes host needs no CUDA binding of its own) */

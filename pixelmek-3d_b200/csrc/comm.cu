@@ -199,7 +199,7 @@ static int group_fail_ctx(pm3d_group *g, int i, int code) {
 extern "C" {
 
 int pm3d_comm_unique_id(uint8_t *id128) {
-    NcclApi *api;
+    NcclApi *api = nullptr;
     if (!id128) return PM3D_ERR_ARG;
     int rc = need_nccl(nullptr, &api);
     if (rc) return rc;
@@ -213,7 +213,7 @@ int pm3d_comm_init(pm3d_ctx *ctx, const uint8_t *id128, int rank, int n_ranks) {
     if (!ctx) return PM3D_ERR_ARG;
     if (!id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return pm3d_fail(ctx, PM3D_ERR_ARG, "pm3d_comm_init: bad rank %d of %d", rank, n_ranks);
     if (ctx->comm) return pm3d_fail(ctx, PM3D_ERR_ARG, "the ctx already belongs to a communicator");
-    NcclApi *api;
+    NcclApi *api = nullptr;
     int rc = need_nccl(ctx, &api);
     if (rc) return rc;
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -257,7 +257,7 @@ int pm3d_comm_all_gather(pm3d_ctx *ctx, const void *d_send, void *d_recv, int64_
     if (!ctx) return PM3D_ERR_ARG;
     if (!ctx->comm) return pm3d_fail(ctx, PM3D_ERR_NCCL, "pm3d_comm_init must be called first");
     if (!d_send || !d_recv || bytes_per_rank < 0) return pm3d_fail(ctx, PM3D_ERR_ARG, "pm3d_comm_all_gather: null buffer");
-    NcclApi *api;
+    NcclApi *api = nullptr;
     int rc = need_nccl(ctx, &api);
     if (rc) return rc;
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -273,7 +273,7 @@ int pm3d_comm_render_views(pm3d_ctx *ctx, const pm3d_view *d_views, int n_local,
     if (!ctx) return PM3D_ERR_ARG;
     if (!ctx->comm) return pm3d_fail(ctx, PM3D_ERR_NCCL, "pm3d_comm_init must be called first");
     if (n_views_global < 1 || n_local < 0) return pm3d_fail(ctx, PM3D_ERR_ARG, "pm3d_comm_render_views: no views");
-    NcclApi *api;
+    NcclApi *api = nullptr;
     int rc = need_nccl(ctx, &api);
     if (rc) return rc;
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -289,7 +289,7 @@ int pm3d_comm_los_batch(pm3d_ctx *ctx, const double *d_rays, int64_t n_local, in
     int64_t lo, hi;
     ray_range(n_global, ctx->comm_rank, ctx->comm_size, &lo, &hi);
     if (n_local != hi - lo) return pm3d_fail(ctx, PM3D_ERR_ARG, "rank %d of %d owns rays [%lld, %lld) of %lld, got %lld", ctx->comm_rank, ctx->comm_size, (long long)lo, (long long)hi, (long long)n_global, (long long)n_local);
-    NcclApi *api;
+    NcclApi *api = nullptr;
     int rc = need_nccl(ctx, &api);
     if (rc) return rc;
     if (n_local > 0 && (rc = pm3d_los_batch(ctx, d_rays, n_local, d_all_out + lo, PM3D_IN_DEVICE | PM3D_OUT_DEVICE | PM3D_NO_SYNC))) return rc;
@@ -394,8 +394,9 @@ int pm3d_group_render_views(pm3d_group *g, const pm3d_view *views, int n_views, 
         }
         pm3d_ctx *ctx = g->ctx[r];
         if (!v.empty()) {
-            // host arrays in, the frames stay in the device's own frame buffer
-            if ((rc = pm3d_render(ctx, v.data(), (int)v.size(), s.empty() ? nullptr : s.data(), off.data(), nullptr, nullptr, nullptr, 0)))
+            // host arrays in (copied to the ctx's pinned staging before the call returns), the frames stay in the device's
+            // own frame buffer; enqueue only, so the devices render side by side
+            if ((rc = pm3d_render(ctx, v.data(), (int)v.size(), s.empty() ? nullptr : s.data(), off.data(), nullptr, nullptr, nullptr, PM3D_NO_SYNC)))
                 return group_fail_ctx(g, r, rc);
         }
         cudaSetDevice(ctx->device);

@@ -224,6 +224,13 @@ struct pm3d_ctx {
     void *io_a = nullptr, *io_b = nullptr, *io_c = nullptr;  // batch staging on device
     size_t io_a_bytes = 0, io_b_bytes = 0, io_c_bytes = 0;
 
+    // multi-GPU (comm.cu): the NCCL communicator this ctx belongs to (ncclComm_t, opaque here) and the gather staging
+    void *comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+    bool comm_owned = false;
+    void *comm_send = nullptr, *comm_recv = nullptr;
+    size_t comm_send_bytes = 0, comm_recv_bytes = 0;
+
     // timers / L2 flush
     cudaEvent_t ev_start[16] = {}, ev_stop[16] = {};
     uint8_t *flush_buf = nullptr;

@@ -7,5 +7,5 @@ synthetic workloads.  It never computes the path on the CPU: without the library
 every compute call raises.
 """
 from ._lib import LIB_PATH, Pm3dError, load  # noqa: F401
-from .context import Context, generate_wall_collision_lines  # noqa: F401
+from .context import Context, Group, comm_unique_id, generate_wall_collision_lines  # noqa: F401
 from .scene import SceneData, premultiply  # noqa: F401

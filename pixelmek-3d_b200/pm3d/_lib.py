@@ -158,6 +158,24 @@ SYMBOLS = {
     "pm3d_ktimer_collect": (C.c_int, [_P, _P, C.c_int]),
     "pm3d_launch_count": (C.c_int64, [_P]),
     "pm3d_flush_l2": (C.c_int, [_P]),
+    "pm3d_comm_unique_id": (C.c_int, [_P]),
+    "pm3d_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "pm3d_comm_destroy": (C.c_int, [_P]),
+    "pm3d_comm_rank": (C.c_int, [_P]),
+    "pm3d_comm_size": (C.c_int, [_P]),
+    "pm3d_shard_view_count": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
+    "pm3d_shard_ray_range": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "pm3d_comm_all_gather": (C.c_int, [_P, _P, _P, C.c_int64]),
+    "pm3d_comm_render_views": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, _P, _P]),
+    "pm3d_comm_los_batch": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
+    "pm3d_group_create": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
+    "pm3d_group_destroy": (None, [_P]),
+    "pm3d_group_last_error": (C.c_char_p, [_P]),
+    "pm3d_group_size": (C.c_int, [_P]),
+    "pm3d_group_ctx": (_P, [_P, C.c_int]),
+    "pm3d_group_sync": (C.c_int, [_P]),
+    "pm3d_group_render_views": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P]),
+    "pm3d_group_los_batch": (C.c_int, [_P, _P, C.c_int64, _P]),
     "pm3d_selfcheck_floor": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pm3d_selfcheck_division": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 }

@@ -344,3 +344,105 @@ def generate_wall_collision_lines(level0: np.ndarray, has_boundary_wall: bool, c
     out = np.zeros((max(n, 1), 4), dtype=np.float64)
     lib.pm3d_generate_wall_collision_lines(ptr(level0), w, h, int(bool(has_boundary_wall)), float(clip), ptr(out), n)
     return out[:n]
+
+
+# ---------------------------------------------------------------------- multi-GPU (csrc/comm.cu)
+def comm_unique_id() -> bytes:
+    """pm3d_comm_unique_id: 128 bytes rank 0 hands to the other ranks."""
+    lib = _lib.load()
+    buf = (C.c_uint8 * 128)()
+    rc = lib.pm3d_comm_unique_id(buf)
+    if rc != 0:
+        raise Pm3dError(f"pm3d_comm_unique_id failed ({rc}): {lib.pm3d_last_error(None).decode()}")
+    return bytes(buf)
+
+
+def _comm_init(self, unique_id: bytes, rank: int, n_ranks: int):
+    """Collective: every rank's ctx joins the library-owned NCCL communicator."""
+    buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+    self._check(self.lib.pm3d_comm_init(self.h, buf, int(rank), int(n_ranks)), "pm3d_comm_init")
+
+
+def _comm_render_views(self, d_views: int, n_local: int, d_sprites: int, d_offsets: int, n_sprites_total: int, d_out: int,
+                       n_views_global: int, d_all_conv: int | None, d_all_sums: int | None):
+    self._check(self.lib.pm3d_comm_render_views(self.h, C.c_void_p(d_views), n_local, C.c_void_p(d_sprites) if d_sprites else None,
+                                                C.c_void_p(d_offsets), n_sprites_total, C.c_void_p(d_out), n_views_global,
+                                                C.c_void_p(d_all_conv) if d_all_conv else None,
+                                                C.c_void_p(d_all_sums) if d_all_sums else None), "pm3d_comm_render_views")
+
+
+def _comm_los_batch(self, d_rays: int, n_local: int, n_global: int, d_all_out: int):
+    self._check(self.lib.pm3d_comm_los_batch(self.h, C.c_void_p(d_rays), n_local, n_global, C.c_void_p(d_all_out)), "pm3d_comm_los_batch")
+
+
+def _comm_all_gather(self, d_send: int, d_recv: int, bytes_per_rank: int):
+    self._check(self.lib.pm3d_comm_all_gather(self.h, C.c_void_p(d_send), C.c_void_p(d_recv), int(bytes_per_rank)), "pm3d_comm_all_gather")
+
+
+Context.comm_init = _comm_init
+Context.comm_render_views = _comm_render_views
+Context.comm_los_batch = _comm_los_batch
+Context.comm_all_gather = _comm_all_gather
+Context.comm_size = property(lambda self: int(self.lib.pm3d_comm_size(self.h)))
+Context.comm_rank = property(lambda self: int(self.lib.pm3d_comm_rank(self.h)))
+
+
+class Group:
+    """pm3d_group: one process driving n GPUs — one ctx per device plus the communicator over them."""
+
+    def __init__(self, devices):
+        self.lib = _lib.load()
+        devs = (C.c_int * len(devices))(*[int(x) for x in devices])
+        g = C.c_void_p()
+        rc = self.lib.pm3d_group_create(devs, len(devices), C.byref(g))
+        if rc != 0:
+            raise Pm3dError(f"pm3d_group_create failed ({rc}): {self.lib.pm3d_group_last_error(None).decode()}")
+        self.g = g
+        self.ctxs = []
+        for i in range(len(devices)):
+            c = Context.__new__(Context)
+            c.lib, c.h, c.device, c.scene, c.w, c.h_px = self.lib, C.c_void_p(self.lib.pm3d_group_ctx(g, i)), devices[i], None, 0, 0
+            c._keep, c._no_sprites, c._res_ring, c._res_pos = [], np.zeros(0, dtype=SPRITE_DTYPE), [], 0
+            c.close = lambda: None   # owned by the group
+            self.ctxs.append(c)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise Pm3dError(f"{what} failed ({rc}): {self.lib.pm3d_group_last_error(self.g).decode()}")
+
+    def close(self):
+        if getattr(self, "g", None):
+            for c in self.ctxs:
+                c.h = None
+            self.lib.pm3d_group_destroy(self.g)
+            self.g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def each(self, fn):
+        """Replicated set-up: fn(ctx) on every device's ctx (uploads, set_view, options)."""
+        for c in self.ctxs:
+            fn(c)
+
+    def render_views(self, views: np.ndarray, sprites: np.ndarray | None, sprite_offset: np.ndarray | None):
+        views = np.ascontiguousarray(views, dtype=VIEW_DTYPE).reshape(-1)
+        n = len(views)
+        conv = np.zeros(n, dtype=CONV_DTYPE)
+        sums = np.zeros(n, dtype=np.uint64)
+        if sprites is not None:
+            sprites = np.ascontiguousarray(sprites, dtype=SPRITE_DTYPE).reshape(-1)
+            sprite_offset = np.ascontiguousarray(sprite_offset, dtype=np.int32)
+        self._check(self.lib.pm3d_group_render_views(self.g, ptr(views), n, ptr(sprites) if sprites is not None and len(sprites) else None,
+                                                     ptr(sprite_offset) if sprites is not None else None, ptr(conv), ptr(sums)),
+                    "pm3d_group_render_views")
+        return conv, sums
+
+    def los_batch(self, rays: np.ndarray) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 4)
+        out = np.zeros(len(rays), dtype=np.uint8)
+        self._check(self.lib.pm3d_group_los_batch(self.g, ptr(rays), len(rays), ptr(out)), "pm3d_group_los_batch")
+        return out

@@ -233,3 +233,17 @@ def test_shard_helpers():
         lo, hi = shard.ray_shard(11, r, 3)
         seen += list(range(lo, hi))
     assert seen == list(range(11))
+
+
+def test_library_shard_arithmetic_equals_the_host_helpers(ensure_built):
+    import ctypes as C
+
+    from pm3d import shard
+    lib = pm3d.load()
+    for n, world in ((4096, 8), (37, 3), (5, 8), (0, 2), (16777216, 7)):
+        for r in range(world):
+            assert lib.pm3d_shard_view_count(n, r, world) == len(shard.view_shard(n, r, world))
+            lo, hi = C.c_int64(), C.c_int64()
+            assert lib.pm3d_shard_ray_range(n, r, world, C.byref(lo), C.byref(hi)) == 0
+            assert (lo.value, hi.value) == shard.ray_shard(n, r, world)
+    assert lib.pm3d_shard_view_count(10, 3, 3) == -1

@@ -31,6 +31,11 @@ struct LosParams {
     double clip;
     uint8_t *out_flag;
     double2 *out_pos;
+    // two-pass line of sight (k_los_fast -> k_los): per-cell code bytes, the list of rays the first pass left
+    // undecided and its length (device memory; k_los reads its work from it when list != nullptr)
+    const uint8_t *cell_code;
+    uint32_t *list;
+    unsigned *list_count;
 };
 
 // geom.LineIntersection (raycaster-go geom; endpoints inclusive), boolean + point
@@ -155,8 +160,16 @@ __device__ bool any_hit(const LosParams &p, const double4 &ray) {
 __global__ void __launch_bounds__(LOS_THREADS, LOS_MIN_BLOCKS) k_los(LosParams p, long long rays_per_warp) {
     const int lane = threadIdx.x & 31;
     const long long warp_id = (long long)blockIdx.x * (LOS_THREADS / 32) + (threadIdx.x >> 5);
+    long long n_work = p.n;
+    if (p.list) {
+        // second pass: the rays k_los_fast could not decide; their number is only known on the device
+        n_work = (long long)*p.list_count;
+        const long long warps = (long long)gridDim.x * (LOS_THREADS / 32);
+        rays_per_warp = (n_work + warps - 1) / warps;
+        if (rays_per_warp < 32) rays_per_warp = 32;
+    }
     long long next = warp_id * rays_per_warp;                      // warp-uniform: next unassigned ray
-    const long long end = min(next + rays_per_warp, (long long)p.n);
+    const long long end = min(next + rays_per_warp, n_work);
     if (next >= end) return;
 
     const double gx0 = (double)p.bin_x0, gy0 = (double)p.bin_y0;
@@ -197,7 +210,7 @@ __global__ void __launch_bounds__(LOS_THREADS, LOS_MIN_BLOCKS) k_los(LosParams p
             const long long mine = next + __popc(idle & ((1u << lane) - 1u));
             next += __popc(idle);
             if (!active && mine < end) {
-                idx = mine;
+                idx = p.list ? (long long)p.list[mine] : mine;
                 ray = p.rays[idx];
                 lr = go_rect(go_int(ray.x), go_int(ray.y), go_int(ray.z), go_int(ray.w));
                 const bool inside = ray.x >= gx0 && ray.x < gx1 && ray.z >= gx0 && ray.z < gx1 && ray.y >= gy0 &&
@@ -311,6 +324,188 @@ __global__ void __launch_bounds__(LOS_THREADS, LOS_MIN_BLOCKS) k_los(LosParams p
                 cx = ncx; cy = ncy; tx = ntx; ty = nty;
                 cur = nrec;
                 cbase = 0;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// First pass of pm3d_los_batch: decide a ray WITHOUT touching a collision segment whenever that is provable.
+//
+// pm3d_upload_segments derives one code byte per bin cell from the segment list:
+//   bit 0      the cell has candidate segments (cell_rec.x > 0; bins are dilated by BIN_EPS)
+//   bits 1..4  the cell's W / E / S / N unit edge (x = cx, x = cx + 1, y = cy, y = cy + 1 between the two lattice
+//              points) is COVERED: some axis-parallel segment lies on that lattice line and contains the whole edge.
+// The pass walks the cells of the ray (same Amanatides-Woo order as k_los, in the division-free cross-multiplied
+// form: tX = ax*|dy| against tY = ay*|dx|) and looks only at these bytes (staged in shared memory when the bin
+// area fits, north_star's "map grid staged in shared memory"):
+//
+// BLOCKED proof.  The walk is about to leave a cell through a covered edge, say the edge on x = c between
+// (c, k) and (c, k+1), covered by the segment S = (c, a)-(c, b) with [k, k+1] inside [min(a,b), max(a,b)].
+// c lies between x1 and x2 (x1 < c <= x2 walking right, x2 < c <= x1 walking left: the walk only steps in x
+// while the target column is not reached).  The test `lo < P < hi` below proves that the TRUE ray crosses x = c at
+// yc with k + m/2 < yc < k + 1 - m/2 (m = 2^-20; P, lo, hi carry relative errors <= 4u, u = 2^-53, coordinates
+// are below 2^15, so the slack it can lose is < 2^-36).  Then geom.LineIntersection(ray, S) as the reference
+// evaluates it in binary64 returns true:
+//   * x3 - x4 = 0 exactly, so denom = RN(RN(x1-x2)*L), tNum = RN(RN(x1-c)*L) with the same L = RN(a-b);
+//     |x1-c| <= |x1-x2| and RN is monotone, so |tNum| <= |denom|, both have the sign of L*(x1-x2) (or tNum = 0):
+//     0 <= t = RN(tNum/denom) <= 1;
+//   * u_true = (yc - a)/(b - a) lies in [m/2|L|, 1 - m/2|L|]; the computed uNum carries an absolute error
+//     <= 3.1u(|x1-x2||y1-a| + |y1-y2||x1-c|) + u|uNum|, i.e. after the division an error <= (6.2u*2^16 + 3u|L|)/|L|
+//     < 2^-33/|L|, far inside the margin: 0 <= u <= 1.
+//   and lineOfSight's integer bounding-rect pre-filter cannot skip S (int() is monotone: int(c) lies between the
+//   truncated ray endpoints in x), so the reference's loop returns false: not visible.  (Mirror image for edges on
+//   y = c.)  |dx| >= 1e-90 keeps denom normal and makes an underflowing product an absolute error far below the margin.
+// VISIBLE proof.  No visited cell has a candidate: no segment can intersect (the k_los argument).
+// Everything else — a failed margin (the ray grazes a lattice corner), candidates seen but the target reached, a ray
+// outside the binned area — is appended to the undecided list and decided by k_los with the exact predicate.
+#define LOSF_THREADS 512
+#define LOSF_MARGIN 9.5367431640625e-07  // 2^-20
+#define LOSF_CAND 1u
+#define LOSF_W 2u
+#define LOSF_E 4u
+#define LOSF_S 8u
+#define LOSF_N 16u
+
+// Lane states between two refills: a lane that stops walking only RECORDS why (LOSF_ST_*); the margin test, the
+// answer byte and the append to the undecided list run later for all stopped lanes of the warp together, in the
+// same convergent block that hands them their next rays (a lane finishing alone ran that tail at 1.7 of 32 lanes).
+#define LOSF_ST_NONE 0     // nothing to finalize
+#define LOSF_ST_EDGE_X 1   // stopped in front of a covered W/E edge: margin test pending
+#define LOSF_ST_EDGE_Y 2   // ... S/N edge
+#define LOSF_ST_END 3      // reached the target cell
+#define LOSF_ST_OUT 4      // outside the binned area: undecided
+
+template <bool SMEM>
+__global__ void __launch_bounds__(LOSF_THREADS, 2) k_los_fast(LosParams p, long long rays_per_warp) {
+    extern __shared__ uint8_t s_code[];
+    const int n_cells = p.bin_w * p.bin_h;
+    if (SMEM) {
+        const int words = (n_cells + 3) >> 2;  // the code array is padded to a multiple of 16 bytes
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(p.cell_code);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_code);
+        for (int i = threadIdx.x; i < words; i += LOSF_THREADS) dst[i] = __ldg(src + i);
+        __syncthreads();
+    }
+    const uint8_t *code = SMEM ? s_code : p.cell_code;
+    auto code_at = [&](int cell) -> unsigned { return SMEM ? (unsigned)code[cell] : (unsigned)__ldg(code + cell); };
+
+    const int lane = threadIdx.x & 31;
+    const unsigned below = (1u << lane) - 1u;
+    const long long warp_id = (long long)blockIdx.x * (LOSF_THREADS / 32) + (threadIdx.x >> 5);
+    const long long begin = warp_id * rays_per_warp;
+    const long long end = min(begin + rays_per_warp, (long long)p.n);
+    if (begin >= end) return;
+    const double gx0 = (double)p.bin_x0, gy0 = (double)p.bin_y0;
+    const double gx1 = (double)(p.bin_x0 + p.bin_w), gy1 = (double)(p.bin_y0 + p.bin_h);
+
+    // The warp's rays are fetched 32 at a time, one per lane (a coalesced 1 KB load issued when the previous
+    // 32 are used up, so it is in flight while the lanes walk); a refill hands them out by shuffle.
+    long long pf_base = begin;            // ray number held by lane 0's prefetch registers
+    int pf_used = 0;                      // how many of the 32 have been handed out
+    double4 pf = make_double4(0, 0, 0, 0);
+    if (pf_base + lane < end) pf = p.rays[pf_base + lane];
+
+    bool active = false;
+    int state = LOSF_ST_NONE;
+    long long idx = 0;
+    double x1 = 0, y1 = 0, dx = 0, dy = 0, tX = 0, tY = 0;
+    int nx = 0, ny = 0, cell = 0, ex = 0, ey = 0;
+    int dcx = 0, dcy = 0;                 // cell index increments of an x / y step
+    unsigned xmask = 0, ymask = 0, cur = 0, seen = 0;
+
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        const bool more = pf_base + pf_used < end;
+        if (idle == 0xffffffffu || (__popc(idle) >= 12 && more)) {
+            // ---- finalize the rays of the stopped lanes (together)
+            int result = -1;  // 0 blocked, 1 visible, 2 undecided
+            if (!active && state != LOSF_ST_NONE) {
+                if (state == LOSF_ST_END) {
+                    result = (seen & LOSF_CAND) ? 2 : 1;
+                } else if (state == LOSF_ST_OUT) {
+                    result = 2;
+                } else {
+                    // prove that the crossing lies inside the covered unit edge, margin 2^-20 from its ends
+                    const bool xs = state == LOSF_ST_EDGE_X;
+                    const int cx = ex - (dcx > 0 ? nx : -nx), cy = ey - (dcy > 0 ? ny : -ny);
+                    const int fwd = xs ? (dcx > 0) : (dcy > 0);
+                    const double c = (double)((xs ? cx + p.bin_x0 : cy + p.bin_y0) + fwd);  // the lattice line crossed
+                    const double k = (double)(xs ? cy + p.bin_y0 : cx + p.bin_x0);          // the edge spans [k, k+1] on it
+                    const double a0 = xs ? x1 : y1, b0 = xs ? y1 : x1;
+                    const double da = xs ? dx : dy, db = xs ? dy : dx;
+                    const double ada = fabs(da);
+                    const double P = fabs(c - a0) * db;
+                    const double lo = ((k + LOSF_MARGIN) - b0) * ada, hi = ((k + (1.0 - LOSF_MARGIN)) - b0) * ada;
+                    result = (lo < P && P < hi && ada >= 1e-90) ? 0 : 2;
+                }
+                if (result < 2) p.out_flag[idx] = (uint8_t)result;
+                state = LOSF_ST_NONE;
+            }
+            const unsigned und = __ballot_sync(0xffffffffu, result == 2);
+            if (und) {
+                const int leader = __ffs(und) - 1;
+                unsigned base = 0;
+                if (lane == leader) base = atomicAdd(p.list_count, (unsigned)__popc(und));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (result == 2) p.list[base + __popc(und & below)] = (uint32_t)idx;
+            }
+            // ---- hand out the next rays
+            const int avail = (int)min((long long)(32 - pf_used), end - pf_base - pf_used);
+            const int rank = __popc(idle & below);
+            const int src = (pf_used + rank) & 31;
+            double4 ray;
+            ray.x = __shfl_sync(0xffffffffu, pf.x, src); ray.y = __shfl_sync(0xffffffffu, pf.y, src);
+            ray.z = __shfl_sync(0xffffffffu, pf.z, src); ray.w = __shfl_sync(0xffffffffu, pf.w, src);
+            const bool take = !active && rank < avail;
+            if (take) idx = pf_base + pf_used + rank;
+            pf_used += min(__popc(idle), avail);
+            if (pf_used == 32) {
+                pf_base += 32; pf_used = 0;
+                if (pf_base + lane < end) pf = p.rays[pf_base + lane];
+            }
+            if (take) {
+                const bool inside = ray.x >= gx0 && ray.x < gx1 && ray.z >= gx0 && ray.z < gx1 && ray.y >= gy0 &&
+                                    ray.y < gy1 && ray.w >= gy0 && ray.w < gy1;
+                if (!inside) {
+                    state = LOSF_ST_OUT;
+                } else {
+                    x1 = ray.x; y1 = ray.y;
+                    const double fx = floor(x1), fy = floor(y1);
+                    const int cx = (int)fx - p.bin_x0, cy = (int)fy - p.bin_y0;
+                    ex = (int)floor(ray.z) - p.bin_x0; ey = (int)floor(ray.w) - p.bin_y0;
+                    dx = ray.z - x1; dy = ray.w - y1;
+                    const bool right = dx > 0, up = dy > 0;
+                    nx = abs(ex - cx); ny = abs(ey - cy);
+                    dcx = right ? 1 : -1; dcy = up ? p.bin_w : -p.bin_w;
+                    xmask = right ? LOSF_E : LOSF_W; ymask = up ? LOSF_N : LOSF_S;
+                    // distances to the first vertical / horizontal cell border, cross-multiplied (no division)
+                    tX = (right ? (fx + 1.0 - x1) : (x1 - fx)) * fabs(dy);
+                    tY = (up ? (fy + 1.0 - y1) : (y1 - fy)) * fabs(dx);
+                    cell = cy * p.bin_w + cx;
+                    cur = code_at(cell);
+                    seen = cur;
+                    if (nx + ny == 0) state = LOSF_ST_END; else active = true;
+                }
+            }
+            if (idle == 0xffffffffu && __ballot_sync(0xffffffffu, active || state != LOSF_ST_NONE) == 0u) break;
+            continue;
+        }
+        // ---- four cells of every walking lane
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            if (active) {
+                const bool xs = (tX < tY && nx > 0) || ny == 0;
+                if (cur & (xs ? xmask : ymask)) {
+                    active = false;
+                    state = xs ? LOSF_ST_EDGE_X : LOSF_ST_EDGE_Y;
+                } else {
+                    if (xs) { tX += fabs(dy); nx--; cell += dcx; }
+                    else    { tY += fabs(dx); ny--; cell += dcy; }
+                    cur = code_at(cell);
+                    seen |= cur;
+                    if (nx + ny == 0) { active = false; state = LOSF_ST_END; }
+                }
             }
         }
     }
@@ -704,8 +899,56 @@ static int run_batch(pm3d_ctx *ctx, bool is_move, const double *rays, int64_t n,
     p.out_pos = (double2 *)d_pos;
     const int64_t blocks = (n + 255) / 256;
     if (blocks > 0x7fffffffll) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "batch too large");
+    p.cell_code = nullptr; p.list = nullptr; p.list_count = nullptr;
+    int fast = ctx->cell_code != nullptr;
+    if (const char *e = getenv("PM3D_LOS_FAST")) fast = fast && atoi(e) != 0;  // tuning / test override
     if (is_move) {
         k_move<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p);
+    } else if (fast) {
+        // two passes: k_los_fast decides what the cell codes alone can prove, k_los takes the rest from the list
+        if (!ctx->los_count) PM3D_CUDA(ctx, cudaMalloc((void **)&ctx->los_count, 64));
+        const int64_t chunk_max = 1ll << 30;  // the list holds 32-bit ray numbers
+        {
+            void *lp = ctx->los_list;
+            int rc = ensure_io(ctx, &lp, &ctx->los_list_bytes, (size_t)std::min<int64_t>(n, chunk_max) * 4);
+            ctx->los_list = (uint32_t *)lp;
+            if (rc) return rc;
+        }
+        const size_t code_bytes = (((size_t)ctx->bin_w * ctx->bin_h + 15) / 16) * 16;
+        const bool smem = code_bytes <= 100 * 1024;
+        if (smem && !ctx->los_smem_optin) {
+            PM3D_CUDA(ctx, cudaFuncSetAttribute(k_los_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            ctx->los_smem_optin = true;
+        }
+        int per_sm_a = 1, per_sm_b = 2;
+        if (smem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, k_los_fast<true>, LOSF_THREADS, code_bytes);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, k_los_fast<false>, LOSF_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_los, LOS_THREADS, 0);
+        if (per_sm_a < 1) per_sm_a = 1;
+        if (per_sm_b < 1) per_sm_b = 1;
+        for (int64_t off = 0; off < n; off += chunk_max) {
+            LosParams q = p;
+            q.n = std::min<int64_t>(n - off, chunk_max);
+            q.rays = p.rays + off;
+            q.out_flag = p.out_flag + off;
+            q.cell_code = ctx->cell_code;
+            q.list = ctx->los_list;
+            q.list_count = ctx->los_count;
+            PM3D_CUDA(ctx, cudaMemsetAsync(ctx->los_count, 0, 4, ctx->stream));
+            long long warps = (long long)ctx->sm_count * per_sm_a * (LOSF_THREADS / 32);
+            long long per_warp = (q.n + warps - 1) / warps;
+            if (per_warp < 32) per_warp = 32;
+            warps = (q.n + per_warp - 1) / per_warp;
+            const unsigned blocks_a = (unsigned)((warps + LOSF_THREADS / 32 - 1) / (LOSF_THREADS / 32));
+            if (smem) k_los_fast<true><<<blocks_a, LOSF_THREADS, code_bytes, ctx->stream>>>(q, per_warp);
+            else k_los_fast<false><<<blocks_a, LOSF_THREADS, 0, ctx->stream>>>(q, per_warp);
+            // the second pass sizes its ranges from the device-side count; a grid of one wave is enough for any count
+            long long warps_b = std::min<long long>((long long)ctx->sm_count * per_sm_b * (LOS_THREADS / 32), (q.n + 31) / 32);
+            const unsigned blocks_b = (unsigned)((warps_b + LOS_THREADS / 32 - 1) / (LOS_THREADS / 32));
+            k_los<<<blocks_b, LOS_THREADS, 0, ctx->stream>>>(q, 0);
+            ctx->launches += 2;
+        }
+        ctx->launches--;  // (the common epilogue below counts one)
     } else {
         // persistent: 8 CTAs per SM, every warp owns a contiguous range of rays (at least 32)
         int per_sm = 2;

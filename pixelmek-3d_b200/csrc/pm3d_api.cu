@@ -162,7 +162,7 @@ void pm3d_destroy(pm3d_ctx *ctx) {
     pm3d_comm_destroy(ctx);
     void *ptrs[] = {ctx->grid, ctx->dist, ctx->wall_lut, ctx->atlas, ctx->floor_tiles, ctx->sheet_pixels, ctx->sheet_info,
                     ctx->views, ctx->sprites, ctx->sprite_offset, ctx->frame, ctx->checksums, ctx->segs, ctx->seg_irect,
-                    ctx->cell_start, ctx->cell_items, ctx->cell_rec, ctx->colliders, ctx->cb_start, ctx->cb_items, ctx->cb_loose, ctx->present_map, ctx->present_buf, ctx->sparse_cells, ctx->sparse_count, ctx->clutter_class, ctx->clutter_tab, ctx->io_a, ctx->io_b, ctx->io_c, ctx->flush_buf};
+                    ctx->cell_start, ctx->cell_items, ctx->cell_rec, ctx->cell_code, ctx->los_list, ctx->los_count, ctx->colliders, ctx->cb_start, ctx->cb_items, ctx->cb_loose, ctx->present_map, ctx->present_buf, ctx->sparse_cells, ctx->sparse_count, ctx->clutter_class, ctx->clutter_tab, ctx->io_a, ctx->io_b, ctx->io_c, ctx->flush_buf};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &fs : ctx->sets) {
@@ -904,6 +904,38 @@ int pm3d_upload_segments(pm3d_ctx *ctx, const double *xyxy, int n) {
     }
     if ((rc = dev_realloc(ctx, &ctx->cell_rec, recs.size()))) return rc;
     PM3D_CUDA(ctx, cudaMemcpy(ctx->cell_rec, recs.data(), recs.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    // code byte per bin cell for the first LOS pass (los_kernel.cu k_los_fast): bit 0 = the cell has candidates;
+    // bits 1..4 = its W / E / S / N unit edge is covered by an axis-parallel segment lying exactly on that lattice line
+    {
+        std::vector<uint8_t> code((((size_t)bw * bh + 15) / 16) * 16, 0);
+        for (size_t c = 0; c < (size_t)bw * bh; c++)
+            if (count[c + 1] > count[c]) code[c] |= 1u;
+        for (int i = 0; i < n; i++) {
+            const double *s = xyxy + (size_t)i * 4;
+            const bool vertical = s[0] == s[2], horizontal = s[1] == s[3];
+            if (vertical == horizontal) continue;  // oblique, or a point
+            const double line = vertical ? s[0] : s[1];
+            if (line != floor(line)) continue;     // not on the lattice (the border rectangles inset by clipDistance)
+            const double lo = vertical ? std::min(s[1], s[3]) : std::min(s[0], s[2]);
+            const double hi = vertical ? std::max(s[1], s[3]) : std::max(s[0], s[2]);
+            const int c = (int)line;
+            for (int k = (int)ceil(lo); (double)(k + 1) <= hi; k++) {  // unit edges [k, k+1] inside [lo, hi]
+                if (vertical) {
+                    const int cy = k - y0, cxe = c - 1 - x0, cxw = c - x0;
+                    if (cy < 0 || cy >= bh) continue;
+                    if (cxe >= 0 && cxe < bw) code[(size_t)cy * bw + cxe] |= 4u;   // E edge of the cell on the left
+                    if (cxw >= 0 && cxw < bw) code[(size_t)cy * bw + cxw] |= 2u;   // W edge of the cell on the right
+                } else {
+                    const int cx = k - x0, cyn = c - 1 - y0, cys = c - y0;
+                    if (cx < 0 || cx >= bw) continue;
+                    if (cyn >= 0 && cyn < bh) code[(size_t)cyn * bw + cx] |= 16u;  // N edge of the cell below
+                    if (cys >= 0 && cys < bh) code[(size_t)cys * bw + cx] |= 8u;   // S edge of the cell above
+                }
+            }
+        }
+        if ((rc = dev_realloc(ctx, &ctx->cell_code, code.size()))) return rc;
+        PM3D_CUDA(ctx, cudaMemcpy(ctx->cell_code, code.data(), code.size(), cudaMemcpyHostToDevice));
+    }
     if (n) {
         PM3D_CUDA(ctx, cudaMemcpy(ctx->segs, xyxy, (size_t)n * 32, cudaMemcpyHostToDevice));
         PM3D_CUDA(ctx, cudaMemcpy(ctx->seg_irect, irect.data(), (size_t)n * sizeof(int4), cudaMemcpyHostToDevice));

@@ -205,6 +205,13 @@ struct pm3d_ctx {
     int32_t *cell_items = nullptr;
     int4 *cell_rec = nullptr;        // count + first three candidate ids (or offset) per bin cell
     int bin_x0 = 0, bin_y0 = 0, bin_w = 0, bin_h = 0;
+    // two-pass LOS (los_kernel.cu k_los_fast): one code byte per bin cell (candidates present + which of its four
+    // unit edges an axis-parallel segment covers), the list of rays the first pass leaves to k_los, its length
+    uint8_t *cell_code = nullptr;
+    uint32_t *los_list = nullptr;
+    size_t los_list_bytes = 0;
+    unsigned *los_count = nullptr;
+    bool los_smem_optin = false;
     // presentation step (present_kernel.cu)
     int32_t *present_map = nullptr;  // [present_w + present_h] output -> source column / row, -1 = outside
     int present_w = 0, present_h = 0, present_src_w = 0, present_src_h = 0;

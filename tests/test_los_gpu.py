@@ -178,3 +178,86 @@ def test_division_free_predicate_matches_reference_arithmetic(gpu_ctx):
     bad = np.nonzero(got != want)[0]
     assert len(bad) == 0, f"{len(bad)} mismatches, first: {rays[bad[:5]].tolist()} gpu {got[bad[:5]].tolist()} oracle {want[bad[:5]].tolist()}"
     assert 0 < int(want.sum()) < len(want)
+
+
+# ---- two-pass line of sight (k_los_fast + k_los): the first pass decides rays from per-cell code bytes alone —
+#      "blocked" when the ray provably crosses the interior of a unit edge a segment covers, "visible" when no
+#      visited cell has a candidate — and must give the brute-force booleans like the exact pass it replaces.
+def _both_modes(ctx, rays, monkeypatch):
+    monkeypatch.setenv("PM3D_LOS_FAST", "1")
+    fast = ctx.los_batch(rays)
+    monkeypatch.setenv("PM3D_LOS_FAST", "0")
+    exact = ctx.los_batch(rays)
+    monkeypatch.delenv("PM3D_LOS_FAST")
+    return fast, exact
+
+
+@pytest.mark.parametrize("size,density,seed", [(256, 0.10, 42), (96, 0.30, 5), (200, 0.01, 9), (300, 0.002, 10), (64, 0.0, 3)])
+def test_two_pass_los_matches_brute_force(gpu_ctx, monkeypatch, size, density, seed):
+    """Dense maps (most rays blocked within a few cells), sparse maps (most rays visible, long walks through
+    candidate-free cells) and an empty map (only the border rectangles)."""
+    grid, segs, rays = c5_small(30000, seed=seed, size=size, density=density)
+    gpu_ctx.upload_segments(segs)
+    fast, exact = _both_modes(gpu_ctx, rays, monkeypatch)
+    want = O.los_batch(segs, rays, threads=8)
+    assert np.array_equal(exact, want)
+    assert np.array_equal(fast, want)
+    if density <= 0.01:
+        assert want.mean() > 0.3  # the visible path is exercised
+
+
+def test_two_pass_los_corner_grazes(gpu_ctx, monkeypatch):
+    """Rays aimed at wall-cell corners and at points of wall faces within 2^-18 .. 2^-24 of a corner (either side of
+    the first pass's 2^-20 margin), rays through lattice corners exactly, rays starting or ending ON a face, rays
+    running along faces: the first pass must hand every one it cannot prove to the exact predicate."""
+    grid = W.synthetic_levels(40, 40, 1, 0.2, 21)
+    lvl = grid[0]
+    segs = pm3d.generate_wall_collision_lines(lvl, True, W.CLIP_DISTANCE)
+    walls = np.argwhere(lvl[1:-1, 1:-1] != 0) + 1
+    free = np.argwhere(lvl == 0)
+    rng = W.SplitMix64(77)
+    rays = []
+    offs = [0.0] + [s * 2.0 ** -e for e in (18, 19, 20, 21, 22, 24, 30, 40, 52) for s in (1.0, -1.0)]
+    for wx, wy in walls[:160]:
+        for cx, cy in ((wx, wy), (wx + 1, wy), (wx, wy + 1), (wx + 1, wy + 1)):
+            src = free[(rng.uniform(3) * len(free)).astype(np.int64)] + 0.5
+            for sx, sy in src:
+                for o in offs:
+                    # through / short of / beyond the point (corner + o along either axis)
+                    for tx, ty in ((cx + o, cy), (cx, cy + o)):
+                        rays.append([sx, sy, tx, ty])
+                        rays.append([sx, sy, 2 * tx - sx, 2 * ty - sy])
+                        rays.append([tx, ty, sx, sy])
+    rays = np.array(rays, dtype=np.float64)
+    rays = rays[(rays.min(axis=1) > 0.5) & (rays.max(axis=1) < 39.5)]
+    gpu_ctx.upload_segments(segs)
+    fast, exact = _both_modes(gpu_ctx, rays, monkeypatch)
+    with np.errstate(all="ignore"):
+        want = O.los_batch(segs, rays, threads=8)
+    bad = np.nonzero(fast != want)[0]
+    assert len(bad) == 0, f"{len(bad)} mismatches, first: {rays[bad[:5]].tolist()}"
+    assert np.array_equal(exact, want)
+    assert 0 < int(want.sum()) < len(want)
+
+
+def test_two_pass_los_arbitrary_segments(gpu_ctx, monkeypatch):
+    """pm3d_upload_segments accepts any segment list (the Go side hands over g.collisionMap): oblique segments,
+    axis-parallel ones off the lattice or with fractional ends, duplicates and points must never be used for a
+    first-pass proof they do not support."""
+    rng = W.SplitMix64(5150)
+    u = rng.uniform(4 * 300).reshape(-1, 4) * 30 + 1
+    segs = [u[:60]]                                           # oblique
+    a = np.round(u[60:140]);  a[:, 2] = a[:, 0]              # vertical on the lattice, integer ends
+    b = np.round(u[140:200]); b[:, 3] = b[:, 1]              # horizontal on the lattice
+    c = u[200:240].copy(); c[:, 2] = c[:, 0]                  # vertical off the lattice
+    d = np.round(u[240:280]); d[:, 2] = d[:, 0]; d[:, 1] += 0.25; d[:, 3] -= 0.5  # lattice line, fractional ends
+    e = np.round(u[280:300]); e[:, 2:] = e[:, :2]             # points
+    segs = np.concatenate([segs[0], a, b, c, d, e, a[:10]])
+    rays = rng.uniform(4 * 60000).reshape(-1, 4) * 31 + 0.5
+    rays[::7] = np.round(rays[::7] * 2) / 2                   # half-lattice endpoints: exact touches
+    gpu_ctx.upload_segments(segs)
+    fast, exact = _both_modes(gpu_ctx, rays, monkeypatch)
+    want = O.los_batch(segs, rays, threads=8)
+    assert np.array_equal(exact, want)
+    assert np.array_equal(fast, want)
+    assert 0 < int(want.sum()) < len(want)

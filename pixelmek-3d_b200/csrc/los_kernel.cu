@@ -367,14 +367,16 @@ __global__ void __launch_bounds__(LOS_THREADS, LOS_MIN_BLOCKS) k_los(LosParams p
 #define LOSF_S 8u
 #define LOSF_N 16u
 
-// Lane states between two refills: a lane that stops walking only RECORDS why (LOSF_ST_*); the margin test, the
-// answer byte and the append to the undecided list run later for all stopped lanes of the warp together, in the
-// same convergent block that hands them their next rays (a lane finishing alone ran that tail at 1.7 of 32 lanes).
-#define LOSF_ST_NONE 0     // nothing to finalize
-#define LOSF_ST_EDGE_X 1   // stopped in front of a covered W/E edge: margin test pending
-#define LOSF_ST_EDGE_Y 2   // ... S/N edge
-#define LOSF_ST_END 3      // reached the target cell
-#define LOSF_ST_OUT 4      // outside the binned area: undecided
+// A lane that stops walking only clears `active`; the margin test, the answer byte and the append to the undecided
+// list run later for all stopped lanes of the warp together, in the same convergent block that hands them their
+// next rays (a lane finishing alone ran that tail at 1.7 of 32 lanes).  Why it stopped is read off its registers:
+// no steps left (n2 == 0) = it reached the target cell, otherwise it stands in front of a covered edge.
+#ifndef LOSF_STEPS
+#define LOSF_STEPS 4     // cells per lane between two looks at the warp's idle lanes
+#endif
+#ifndef LOSF_REFILL
+#define LOSF_REFILL 12   // idle lanes that trigger a refill
+#endif
 
 template <bool SMEM>
 __global__ void __launch_bounds__(LOSF_THREADS, 2) k_los_fast(LosParams p, long long rays_per_warp) {
@@ -396,8 +398,6 @@ __global__ void __launch_bounds__(LOSF_THREADS, 2) k_los_fast(LosParams p, long 
     const long long begin = warp_id * rays_per_warp;
     const long long end = min(begin + rays_per_warp, (long long)p.n);
     if (begin >= end) return;
-    const double gx0 = (double)p.bin_x0, gy0 = (double)p.bin_y0;
-    const double gx1 = (double)(p.bin_x0 + p.bin_w), gy1 = (double)(p.bin_y0 + p.bin_h);
 
     // The warp's rays are fetched 32 at a time, one per lane (a coalesced 1 KB load issued when the previous
     // 32 are used up, so it is in flight while the lanes walk); a refill hands them out by shuffle.
@@ -407,28 +407,27 @@ __global__ void __launch_bounds__(LOSF_THREADS, 2) k_los_fast(LosParams p, long 
     if (pf_base + lane < end) pf = p.rays[pf_base + lane];
 
     bool active = false;
-    int state = LOSF_ST_NONE;
-    long long idx = 0;
+    long long idx = -1;                   // < 0: the lane holds no ray to finalize
     double x1 = 0, y1 = 0, dx = 0, dy = 0, tX = 0, tY = 0;
-    int nx = 0, ny = 0, cell = 0, ex = 0, ey = 0;
+    unsigned n2 = 0;                      // steps left: x steps in the low half, y steps in the high half
+    int cell = 0, exy = 0;                // target cell (x | y << 16)
     int dcx = 0, dcy = 0;                 // cell index increments of an x / y step
     unsigned xmask = 0, ymask = 0, cur = 0, seen = 0;
 
     for (;;) {
         const unsigned idle = __ballot_sync(0xffffffffu, !active);
         const bool more = pf_base + pf_used < end;
-        if (idle == 0xffffffffu || (__popc(idle) >= 12 && more)) {
+        if (idle == 0xffffffffu || (__popc(idle) >= LOSF_REFILL && more)) {
             // ---- finalize the rays of the stopped lanes (together)
             int result = -1;  // 0 blocked, 1 visible, 2 undecided
-            if (!active && state != LOSF_ST_NONE) {
-                if (state == LOSF_ST_END) {
-                    result = (seen & LOSF_CAND) ? 2 : 1;
-                } else if (state == LOSF_ST_OUT) {
-                    result = 2;
+            if (!active && idx >= 0) {
+                if (n2 == 0u) {
+                    result = (seen & LOSF_CAND) ? 2 : 1;  // target reached (or the ray left the bins: seen = CAND)
                 } else {
                     // prove that the crossing lies inside the covered unit edge, margin 2^-20 from its ends
-                    const bool xs = state == LOSF_ST_EDGE_X;
-                    const int cx = ex - (dcx > 0 ? nx : -nx), cy = ey - (dcy > 0 ? ny : -ny);
+                    const int nx = (int)(n2 & 0xffffu), ny = (int)(n2 >> 16);
+                    const bool xs = (tX < tY) ? (nx > 0) : (ny == 0);
+                    const int cx = (exy & 0xffff) - (dcx > 0 ? nx : -nx), cy = (exy >> 16) - (dcy > 0 ? ny : -ny);
                     const int fwd = xs ? (dcx > 0) : (dcy > 0);
                     const double c = (double)((xs ? cx + p.bin_x0 : cy + p.bin_y0) + fwd);  // the lattice line crossed
                     const double k = (double)(xs ? cy + p.bin_y0 : cx + p.bin_x0);          // the edge spans [k, k+1] on it
@@ -440,7 +439,6 @@ __global__ void __launch_bounds__(LOSF_THREADS, 2) k_los_fast(LosParams p, long 
                     result = (lo < P && P < hi && ada >= 1e-90) ? 0 : 2;
                 }
                 if (result < 2) p.out_flag[idx] = (uint8_t)result;
-                state = LOSF_ST_NONE;
             }
             const unsigned und = __ballot_sync(0xffffffffu, result == 2);
             if (und) {
@@ -450,6 +448,7 @@ __global__ void __launch_bounds__(LOSF_THREADS, 2) k_los_fast(LosParams p, long 
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (result == 2) p.list[base + __popc(und & below)] = (uint32_t)idx;
             }
+            if (!active) idx = -1;
             // ---- hand out the next rays
             const int avail = (int)min((long long)(32 - pf_used), end - pf_base - pf_used);
             const int rank = __popc(idle & below);
@@ -465,18 +464,20 @@ __global__ void __launch_bounds__(LOSF_THREADS, 2) k_los_fast(LosParams p, long 
                 if (pf_base + lane < end) pf = p.rays[pf_base + lane];
             }
             if (take) {
-                const bool inside = ray.x >= gx0 && ray.x < gx1 && ray.z >= gx0 && ray.z < gx1 && ray.y >= gy0 &&
-                                    ray.y < gy1 && ray.w >= gy0 && ray.w < gy1;
-                if (!inside) {
-                    state = LOSF_ST_OUT;
+                // finite and small enough for the int conversions; then inside the bins as cell numbers
+                const bool sane = fabs(ray.x) + fabs(ray.y) + fabs(ray.z) + fabs(ray.w) < 1e9;
+                x1 = ray.x; y1 = ray.y;
+                const double fx = floor(x1), fy = floor(y1);
+                const int cx = sane ? (int)fx - p.bin_x0 : -1, cy = (int)fy - p.bin_y0;
+                const int ex = (int)floor(ray.z) - p.bin_x0, ey = (int)floor(ray.w) - p.bin_y0;
+                if (!((unsigned)cx < (unsigned)p.bin_w && (unsigned)ex < (unsigned)p.bin_w &&
+                      (unsigned)cy < (unsigned)p.bin_h && (unsigned)ey < (unsigned)p.bin_h)) {
+                    n2 = 0u; seen = LOSF_CAND;  // not finite, or outside the binned area: undecided
                 } else {
-                    x1 = ray.x; y1 = ray.y;
-                    const double fx = floor(x1), fy = floor(y1);
-                    const int cx = (int)fx - p.bin_x0, cy = (int)fy - p.bin_y0;
-                    ex = (int)floor(ray.z) - p.bin_x0; ey = (int)floor(ray.w) - p.bin_y0;
                     dx = ray.z - x1; dy = ray.w - y1;
                     const bool right = dx > 0, up = dy > 0;
-                    nx = abs(ex - cx); ny = abs(ey - cy);
+                    n2 = (unsigned)abs(ex - cx) | ((unsigned)abs(ey - cy) << 16);
+                    exy = ex | (ey << 16);
                     dcx = right ? 1 : -1; dcy = up ? p.bin_w : -p.bin_w;
                     xmask = right ? LOSF_E : LOSF_W; ymask = up ? LOSF_N : LOSF_S;
                     // distances to the first vertical / horizontal cell border, cross-multiplied (no division)
@@ -485,26 +486,26 @@ __global__ void __launch_bounds__(LOSF_THREADS, 2) k_los_fast(LosParams p, long 
                     cell = cy * p.bin_w + cx;
                     cur = code_at(cell);
                     seen = cur;
-                    if (nx + ny == 0) state = LOSF_ST_END; else active = true;
+                    active = n2 != 0u;
                 }
             }
-            if (idle == 0xffffffffu && __ballot_sync(0xffffffffu, active || state != LOSF_ST_NONE) == 0u) break;
+            if (idle == 0xffffffffu && __ballot_sync(0xffffffffu, idx >= 0) == 0u) break;
             continue;
         }
-        // ---- four cells of every walking lane
+        // ---- a few cells of every walking lane
 #pragma unroll
-        for (int it = 0; it < 4; it++) {
+        for (int it = 0; it < LOSF_STEPS; it++) {
             if (active) {
-                const bool xs = (tX < tY && nx > 0) || ny == 0;
+                const bool xs = (tX < tY) ? ((n2 & 0xffffu) != 0u) : (n2 < 0x10000u);
                 if (cur & (xs ? xmask : ymask)) {
                     active = false;
-                    state = xs ? LOSF_ST_EDGE_X : LOSF_ST_EDGE_Y;
                 } else {
-                    if (xs) { tX += fabs(dy); nx--; cell += dcx; }
-                    else    { tY += fabs(dx); ny--; cell += dcy; }
+                    if (xs) tX += fabs(dy); else tY += fabs(dx);
+                    n2 -= xs ? 1u : 0x10000u;
+                    cell += xs ? dcx : dcy;
                     cur = code_at(cell);
                     seen |= cur;
-                    if (nx + ny == 0) { active = false; state = LOSF_ST_END; }
+                    active = n2 != 0u;
                 }
             }
         }

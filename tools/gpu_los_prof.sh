@@ -2,7 +2,5 @@
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
 mkdir -p gpurun_out
 python tools/prof_los.py || exit 1
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/los_launches.csv python tools/prof_los.py > /dev/null 2>&1
-LOS_DENSITY=0.005 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/los_launches_sparse.csv python tools/prof_los.py > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_los -s 4 -c 2 -o gpurun_out/los_full -f python tools/prof_los.py > gpurun_out/los_full.log 2>&1
 tail -3 gpurun_out/los_full.log

@@ -167,7 +167,11 @@ int pm3d_set_view(pm3d_ctx *ctx, int width, int height, int max_views, int max_s
  * different lanes are unordered among themselves, so two in-flight calls must not write the same output buffer.
  * Results of "the last render" (pm3d_download_results, pm3d_frame_checksums, pm3d_present with d_src NULL) wait for
  * that call's lane; pm3d_timer_* bracket all lanes.  pm3d_render (host buffers) always uses lane 0. */
-enum { PM3D_OPT_KEEP_COLUMNS = 1, PM3D_OPT_FORCE_PAINTER = 2, PM3D_OPT_PIPELINE = 3, PM3D_OPT_OVERLAP = 4, PM3D_OPT_LANES = 5 };
+/* PM3D_OPT_DDA_JUMP (default 1): the wall cast advances between two probes of the map in closed form (a certified
+ * state of the reference's DDA after N steps) instead of stepping; 0 runs the sequential loop only (A/B check:
+ * output must not change). */
+enum { PM3D_OPT_KEEP_COLUMNS = 1, PM3D_OPT_FORCE_PAINTER = 2, PM3D_OPT_PIPELINE = 3, PM3D_OPT_OVERLAP = 4, PM3D_OPT_LANES = 5,
+       PM3D_OPT_DDA_JUMP = 6 };
 int pm3d_set_option(pm3d_ctx *ctx, int option, int value);
 
 /* ------------------------------------------------------------------ frame path
@@ -454,6 +458,14 @@ int pm3d_selfcheck_division(pm3d_ctx *ctx, uint64_t seed, int blocks, int iters,
  * path accepted (the rest fall back to the reference sequence in the kernel); out_mismatches must read 0. */
 int pm3d_selfcheck_floor(pm3d_ctx *ctx, uint64_t seed, int blocks, int iters, uint64_t *out_mismatches,
                          uint64_t *out_tested, uint64_t *out_accepted);
+
+/* Device self-check of the wall cast's closed-form DDA jump (pm3d_internal.cuh dda_jump): blocks*256 rays (random
+ * poses and directions, exact diagonals, rational slopes, cell-centre / lattice positions) are walked `steps` steps
+ * by the reference's sequential loop; at random step counts the certified closed-form state (x steps, y steps, side
+ * of the last step) must equal the loop's.  out_certified counts the checks the certificate accepted (the rest
+ * take the sequential loop in the kernel); out_mismatches must read 0. */
+int pm3d_selfcheck_dda(pm3d_ctx *ctx, uint64_t seed, int blocks, int steps, uint64_t *out_mismatches,
+                       uint64_t *out_tested, uint64_t *out_certified);
 
 #ifdef __cplusplus
 }

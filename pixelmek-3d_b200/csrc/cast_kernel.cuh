@@ -17,6 +17,9 @@
 // L2 loads per ray into 3-4.
 #pragma once
 #include "pm3d_internal.cuh"
+#ifdef PM3D_FRONT_STATS
+__device__ unsigned long long g_front_stats[8];  // (experiments only) 0 jump fallbacks, 1 jump rays, 2 slowest cast thread, 3 slowest view CTA
+#endif
 
 struct CastParams {
     const pm3d_view *views;
@@ -24,6 +27,8 @@ struct CastParams {
     const double *sparse_cells;   // [stored_levels][PM3D_SPARSE_MAX][2]
     const int32_t *sparse_count;  // [stored_levels], -1 = dense
     const uint8_t *dist;  // per stored level: Chebyshev distance to the nearest wall cell or map edge (0 = wall)
+    const uint16_t *qdist;  // per stored level and step quadrant: DDA steps to the nearest wall cell / map exit (0 = wall)
+    int jump;             // 1: closed-form jumps between probes (dda_jump), 0: the sequential loop only
     const int16_t *wall_lut;
     int2 *col_span;
     uint2 *col_tt;
@@ -115,6 +120,46 @@ __device__ __forceinline__ void cast_ray(const CastParams &p, const int view, co
     if (hit == 0 && (unsigned)mx < (unsigned)p.map_w && (unsigned)my < (unsigned)p.map_h) {
         D = __ldg(dist + mx * p.map_h + my);
         if (D == 0) D = 1;
+    }
+    // ---- jump mode.  Between two probes the steps cannot hit anything, so only the NUMBER of x and y steps among
+    // them matters: dda_jump gives the state after N steps in closed form with a certificate that the reference's
+    // sequence of rounded additions and comparisons reaches exactly that state.  The probe distance comes from the
+    // quadrant field (steps to the nearest wall cell or map exit for a ray walking in this ray's quadrant), so an
+    // open map costs a handful of jumps instead of ~700 dependent add/compare steps.  Any failed certificate
+    // (near ties, non-finite operands) restarts the ray in the sequential loop below.
+    if (p.jump && hit == 0 && (unsigned)mx < (unsigned)p.map_w && (unsigned)my < (unsigned)p.map_h) {
+        const uint16_t *__restrict__ qd =
+            p.qdist + ((size_t)sl * 4 + ((stepX > 0 ? 1 : 0) | (stepY > 0 ? 2 : 0))) * p.map_w * p.map_h;
+        int Dq = __ldg(qd + mx * p.map_h + my);
+        // axis-parallel rays: a side distance that is inf or NaN never wins (or always loses) a comparison
+        const bool x_dead = !(sideDistX < INFINITY) || sideDistY != sideDistY;   // only y steps
+        const bool y_dead = !x_dead && sideDistY == INFINITY && deltaDistX < 1e290;  // only x steps
+        const double c0 = sideDistY - sideDistX, inv = 1.0 / (deltaDistX + deltaDistY);
+        int N = 0, jx = mx, jy = my, jside = -1, jhit = 0;
+        bool ok = Dq > 0;  // (a camera inside a wall cell: the sequential loop)
+        while (ok) {
+            N += Dq;
+            int i, j;
+            if (x_dead) { i = 0; j = N; jside = 1; }
+            else if (y_dead) { i = N; j = 0; jside = 0; }
+            else ok = dda_jump(sideDistX, sideDistY, deltaDistX, deltaDistY, c0, inv, N, i, j, jside);
+            if (!ok) break;
+            jx = mx + i * stepX; jy = my + j * stepY;
+            if ((unsigned)jx < (unsigned)p.map_w && (unsigned)jy < (unsigned)p.map_h) {
+                Dq = __ldg(qd + jx * p.map_h + jy);
+                if (Dq == 0) { jhit = 1; break; }
+            } else {
+                jhit = 2;
+                jx = jx < 0 ? 0 : (jx > p.map_w - 1 ? p.map_w - 1 : jx);
+                jy = jy < 0 ? 0 : (jy > p.map_h - 1 ? p.map_h - 1 : jy);
+                break;
+            }
+        }
+        if (ok) { mx = jx; my = jy; side = jside; hit = jhit; }
+#ifdef PM3D_FRONT_STATS
+        atomicAdd(&g_front_stats[1], 1ull);
+        if (!ok) atomicAdd(&g_front_stats[0], 1ull);
+#endif
     }
     while (hit == 0) {
         for (int k = D - 1; k > 0; --k) {  // blind steps: cannot hit, cannot leave

@@ -5,11 +5,24 @@
 #include "cast_kernel.cuh"
 #include "view_kernel.cuh"
 
+#ifdef PM3D_FRONT_STATS
+// (experiments only: tools/exp_front_stats.py builds the library with -DPM3D_FRONT_STATS)
+extern "C" int pm3d_debug_front_stats(pm3d_ctx *ctx, unsigned long long *out, int reset) {
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_front_stats, sizeof(g_front_stats));
+    if (reset) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(g_front_stats, z, sizeof(z)); }
+    return 0;
+}
+#endif
 #ifndef FRONT_MIN_BLOCKS
 #define FRONT_MIN_BLOCKS 4
 #endif
 template <bool DEBUG>
 __global__ void __launch_bounds__(VIEW_THREADS, FRONT_MIN_BLOCKS) k_front(CastParams cp, ViewParams vp, int n_cast_blocks, long long n_pairs) {
+#ifdef PM3D_FRONT_STATS
+    const long long t0 = clock64();
+#endif
     if ((int)blockIdx.x < n_cast_blocks) {
         // a pair of warps = the 64 columns of one (view, level, group)
         const long long pair = (long long)blockIdx.x * (VIEW_THREADS / 64) + (threadIdx.x >> 6);
@@ -17,8 +30,14 @@ __global__ void __launch_bounds__(VIEW_THREADS, FRONT_MIN_BLOCKS) k_front(CastPa
         const int group = (int)(pair % cp.n_groups);
         const long long vl = pair / cp.n_groups;
         cast_ray<DEBUG>(cp, (int)(vl / cp.num_levels), (int)(vl % cp.num_levels), group, group * GROUP_COLS + (threadIdx.x & 63));
+#ifdef PM3D_FRONT_STATS
+        atomicMax(&g_front_stats[2], (unsigned long long)(clock64() - t0));
+#endif
     } else {
         view_setup(vp, (int)blockIdx.x - n_cast_blocks);
+#ifdef PM3D_FRONT_STATS
+        atomicMax(&g_front_stats[3], (unsigned long long)(clock64() - t0));
+#endif
     }
 }
 
@@ -27,6 +46,8 @@ int pm3d_launch_front(pm3d_ctx *ctx, int n_views, cudaStream_t stream) {
     p.views = ctx->cur_views;
     p.grid = ctx->grid;
     p.dist = ctx->dist;
+    p.qdist = ctx->qdist;
+    p.jump = ctx->dda_jump;
     p.sparse_cells = ctx->sparse_cells; p.sparse_count = ctx->sparse_count;
     p.wall_lut = ctx->wall_lut;
     p.col_span = ctx->col_span; p.col_tt = ctx->col_tt; p.col_ps = ctx->col_ps;

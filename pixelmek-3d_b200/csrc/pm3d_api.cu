@@ -160,7 +160,7 @@ void pm3d_destroy(pm3d_ctx *ctx) {
     sync_frame_streams(ctx);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     pm3d_comm_destroy(ctx);
-    void *ptrs[] = {ctx->grid, ctx->dist, ctx->wall_lut, ctx->atlas, ctx->floor_tiles, ctx->sheet_pixels, ctx->sheet_info,
+    void *ptrs[] = {ctx->grid, ctx->dist, ctx->qdist, ctx->wall_lut, ctx->atlas, ctx->floor_tiles, ctx->sheet_pixels, ctx->sheet_info,
                     ctx->views, ctx->sprites, ctx->sprite_offset, ctx->frame, ctx->checksums, ctx->segs, ctx->seg_irect,
                     ctx->cell_start, ctx->cell_items, ctx->cell_rec, ctx->cell_code, ctx->los_list, ctx->los_count, ctx->colliders, ctx->cb_start, ctx->cb_items, ctx->cb_loose, ctx->present_map, ctx->present_buf, ctx->sparse_cells, ctx->sparse_count, ctx->clutter_class, ctx->clutter_tab, ctx->io_a, ctx->io_b, ctx->io_c, ctx->flush_buf};
     for (void *p : ptrs)
@@ -260,6 +260,33 @@ int pm3d_upload_grid(pm3d_ctx *ctx, const uint16_t *grid, int stored_levels, int
         rc = dev_realloc(ctx, &ctx->dist, count);
         if (rc) return rc;
         PM3D_CUDA(ctx, cudaMemcpy(ctx->dist, dist.data(), count, cudaMemcpyHostToDevice));
+    }
+    // jump field (cast_kernel.cuh): per step quadrant q = (stepX > 0) | (stepY > 0) << 1, the number of DDA steps
+    // a ray walking in that quadrant needs at least to reach a wall cell or leave the map: F = 0 on walls and
+    // outside, else 1 + min(F(x + stepX, y), F(x, y + stepY)) — the L1 distance to the nearest wall cell inside the
+    // quadrant's cone (every step moves one cell along one axis, never against the quadrant)
+    {
+        const int W = map_w, H = map_h;
+        std::vector<uint16_t> q((size_t)stored_levels * 4 * W * H);
+        for (int l = 0; l < stored_levels; l++) {
+            const uint16_t *g = grid + (size_t)l * W * H;
+            for (int quad = 0; quad < 4; quad++) {
+                uint16_t *f = q.data() + ((size_t)l * 4 + quad) * W * H;
+                const int sx = (quad & 1) ? 1 : -1, sy = (quad & 2) ? 1 : -1;
+                auto at = [&](int x, int y) -> int { return (x < 0 || y < 0 || x >= W || y >= H) ? 0 : f[(size_t)x * H + y]; };
+                for (int xi = 0; xi < W; xi++) {
+                    const int x = sx > 0 ? W - 1 - xi : xi;
+                    for (int yi = 0; yi < H; yi++) {
+                        const int y = sy > 0 ? H - 1 - yi : yi;
+                        int v = 0;
+                        if (g[(size_t)x * H + y] == 0) v = std::min(1 + std::min(at(x + sx, y), at(x, y + sy)), 65535);
+                        f[(size_t)x * H + y] = (uint16_t)v;
+                    }
+                }
+            }
+        }
+        if ((rc = dev_realloc(ctx, &ctx->qdist, q.size()))) return rc;
+        PM3D_CUDA(ctx, cudaMemcpy(ctx->qdist, q.data(), q.size() * 2, cudaMemcpyHostToDevice));
     }
     // sparse levels (cast_kernel.cuh): levels with at most PM3D_SPARSE_MAX wall cells list their cell centres, so
     // an upper-level ray that provably passes none of them skips the walk across the empty level
@@ -386,6 +413,9 @@ int pm3d_set_option(pm3d_ctx *ctx, int option, int value) {
         return PM3D_OK;
     case PM3D_OPT_FORCE_PAINTER:
         ctx->force_painter = value ? 1 : 0;
+        return PM3D_OK;
+    case PM3D_OPT_DDA_JUMP:
+        ctx->dda_jump = value ? 1 : 0;
         return PM3D_OK;
     case PM3D_OPT_OVERLAP:
         PM3D_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -75,6 +75,7 @@ struct pm3d_ctx {
     // mission data
     uint16_t *grid = nullptr;
     uint8_t *dist = nullptr;  // [stored_levels][map_w][map_h] free-run distance field of the grid
+    uint16_t *qdist = nullptr;  // [stored_levels][4][map_w][map_h] per step quadrant: steps to the nearest wall cell / map exit
     double *sparse_cells = nullptr;   // [stored_levels][PM3D_SPARSE_MAX][2] wall-cell centres of sparse levels
     int32_t *sparse_count = nullptr;  // [stored_levels] number of wall cells, -1 = more than PM3D_SPARSE_MAX
     int stored_levels = 0, map_w = 0, map_h = 0, num_levels = 0;
@@ -91,7 +92,7 @@ struct pm3d_ctx {
 
     // view configuration
     int w = 0, h = 0, max_views = 0, max_sprites = 0, n_groups = 0;
-    int keep_columns = 0, force_painter = 0;
+    int keep_columns = 0, force_painter = 0, dda_jump = 1;
     int last_views = 0;
 
     // per-call device buffers
@@ -345,6 +346,41 @@ __device__ __forceinline__ bool floor_fast_index(double w, double D, double P, u
     const uint32_t lo = (uint32_t)__double2loint(m), hi = (uint32_t)__double2hiint(m);
     idx = __funnelshift_r(lo, hi, 20);
     return (lo & 0xfffffu) != 0u && idx < bound;
+}
+
+// ---- DDA jump --------------------------------------------------------------------------------
+// The reference's wall cast (oracle/pm3d_oracle.c:117-127) is a MERGE of two non-decreasing binary64 sequences
+//     A_0 = sideDistX, A_{k+1} = RN(A_k + deltaDistX)        B_0 = sideDistY, B_{k+1} = RN(B_k + deltaDistY):
+// every step takes an x step when A_i < B_j and a y step otherwise.  Only the cells it visits matter (the wall
+// distance comes from the integer hit cell), and the state (i, j) after N steps is the unique split i + j = N with
+//     (i == 0 or A_{i-1} < B_j)  and  (j == 0 or B_{j-1} <= A_i)                                  (merge path)
+// whatever happened in between; the N-th step was an x step iff A_{i-1} >= B_{j-1} (a tie takes y first).
+// dda_jump evaluates that split for a given N in closed form: i = ceil((B_0 - A_0 + (N-1) dY) / (dX + dY)) is the
+// split of the real-number progressions, and the inequalities are then CERTIFIED on the true sequences through
+//     |A_k - fma(k, dX, A_0)| <= (k + 1) 2^-53 A_k (1 + 2^-30)        (k rounded additions + one fma rounding)
+// by requiring gaps larger than T = (N + 8) 2^-50 max(A_i, B_j) — four times the worst case.  A failed
+// certificate (a near tie: rays on exact diagonals, or non-finite operands, whose comparisons all read false)
+// returns false and the caller runs the reference loop instead.  Requires A_0, B_0 >= 0.
+// pm3d_selfcheck_dda compares it with the sequential loop on random and tie-prone rays (selfcheck.cu).
+__device__ __forceinline__ bool dda_jump(double sX0, double sY0, double dX, double dY, double c0, double inv, int N,
+                                         int &i_out, int &j_out, int &side_out) {
+    double r = ceil(__fma_rn((double)(N - 1), dY, c0) * inv);
+    r = fmin(fmax(r, 0.0), (double)N);  // (NaN -> 0)
+    const int i = (int)r, j = N - i;
+    const double a0 = __fma_rn((double)i, dX, sX0), b0 = __fma_rn((double)j, dY, sY0);  // A_i, B_j
+    const double a1 = i > 0 ? __fma_rn((double)(i - 1), dX, sX0) : -INFINITY;           // A_{i-1}
+    const double b1 = j > 0 ? __fma_rn((double)(j - 1), dY, sY0) : -INFINITY;           // B_{j-1}
+    const double T = (double)(N + 8) * 8.8817841970012523e-16 * fmax(a0, b0);           // 2^-50
+    i_out = i; j_out = j;
+    if (a1 - b1 > T) {          // the last step was an x step; B_{j-1} < A_{i-1} <= A_i holds, certify A_{i-1} < B_j
+        side_out = 0;
+        return b0 - a1 > T;
+    }
+    if (b1 - a1 > T) {          // the last step was a y step; A_{i-1} < B_{j-1} <= B_j holds, certify B_{j-1} <= A_i
+        side_out = 1;
+        return a0 - b1 > T;
+    }
+    return false;
 }
 
 // lighting: byte(ClampInt(int(base + sqrt(dist)*falloff + illumination (+ extra)), min, max)) per channel

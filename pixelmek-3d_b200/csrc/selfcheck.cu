@@ -111,6 +111,75 @@ __global__ void k_selfcheck_floor(uint64_t seed, int iters, unsigned long long *
     atomicAdd(counters + 2, accepted);
 }
 
+// pm3d_selfcheck_dda: dda_jump against the sequential merge it replaces.
+__global__ void k_selfcheck_dda(uint64_t seed, int steps, unsigned long long *counters) {
+    uint64_t s = seed ^ ((uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * 0xD1342543DE82EF95ull);
+    const double U = 1.0 / 9007199254740992.0;
+    const uint64_t r0 = sm64(s), r1 = sm64(s), r2 = sm64(s), r3 = sm64(s), r4 = sm64(s);
+    const int mode = (int)(r4 & 7);
+    // position inside a cell, direction: as the cast builds them (oracle/pm3d_oracle.c:102-115)
+    double fracX = (double)(r0 >> 11) * U, fracY = (double)(r1 >> 11) * U;
+    double dirX = 2.0 * (double)(r2 >> 11) * U - 1.0, dirY = 2.0 * (double)(r3 >> 11) * U - 1.0;
+    if (mode == 1) { dirY = dirX; }                                             // exact diagonal: ties everywhere
+    else if (mode == 2) { dirY = dirX * (double)(1 + (r4 >> 8) % 7) / (double)(1 + (r4 >> 16) % 7); }  // rational slopes
+    else if (mode == 3) { fracX = 0.5; fracY = 0.5; }                            // cell centre (the bundled poses)
+    else if (mode == 4) { fracX = 0.0; fracY = (r4 & 0x100) ? 0.0 : 0.25; dirY = dirX * ((r4 & 0x200) ? 1.0 : 2.0); }
+    else if (mode == 5) { dirX *= 1e-9; }                                        // almost axis-parallel
+    else if (mode == 6) { dirX = (r4 & 0x100) ? 0.0 : dirX; dirY = (r4 & 0x200) ? 0.0 : dirY; }  // axis-parallel: inf / NaN
+    const double pos = (double)((r4 >> 24) % 500);
+    const double posX = pos + fracX, posY = (double)((r4 >> 40) % 500) + fracY;
+    const long long mapX = (long long)posX, mapY = (long long)posY;
+    const double dX = fabs(1.0 / dirX), dY = fabs(1.0 / dirY);
+    const double sX0 = dirX < 0 ? (posX - (double)mapX) * dX : ((double)mapX + 1.0 - posX) * dX;
+    const double sY0 = dirY < 0 ? (posY - (double)mapY) * dY : ((double)mapY + 1.0 - posY) * dY;
+    const bool x_dead = !(sX0 < INFINITY) || sY0 != sY0;
+    const bool y_dead = !x_dead && sY0 == INFINITY && dX < 1e290;
+    const double c0 = sY0 - sX0, inv = 1.0 / (dX + dY);
+    double a = sX0, b = sY0;
+    int i = 0, j = 0, side = -1;
+    unsigned long long bad = 0, n = 0, cert = 0;
+    int next_check = 1 + (int)(sm64(s) % 4);
+    for (int step = 1; step <= steps; step++) {
+        if (a < b) { a += dX; i++; side = 0; } else { b += dY; j++; side = 1; }
+        if (step == next_check) {
+            next_check += 1 + (int)(sm64(s) % 37);
+            int gi = 0, gj = step, gs = 1;
+            bool ok = true;
+            if (x_dead) { gi = 0; gj = step; gs = 1; }
+            else if (y_dead) { gi = step; gj = 0; gs = 0; }
+            else ok = dda_jump(sX0, sY0, dX, dY, c0, inv, step, gi, gj, gs);
+            n++;
+            if (ok) {
+                cert++;
+                if (gi != i || gj != j || gs != side) bad++;
+            }
+        }
+    }
+    atomicAdd(counters, bad);
+    atomicAdd(counters + 1, n);
+    atomicAdd(counters + 2, cert);
+}
+
+extern "C" int pm3d_selfcheck_dda(pm3d_ctx *ctx, uint64_t seed, int blocks, int steps, uint64_t *out_mismatches,
+                                  uint64_t *out_tested, uint64_t *out_certified) {
+    if (!ctx || blocks < 1 || steps < 1 || !out_mismatches || !out_tested || !out_certified) return PM3D_ERR_ARG;
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned long long *d = nullptr;
+    PM3D_CUDA(ctx, cudaMalloc((void **)&d, 24));
+    PM3D_CUDA(ctx, cudaMemsetAsync(d, 0, 24, ctx->stream));
+    k_selfcheck_dda<<<blocks, 256, 0, ctx->stream>>>(seed, steps, d);
+    ctx->launches++;
+    PM3D_CUDA(ctx, cudaGetLastError());
+    unsigned long long h[3] = {0, 0, 0};
+    PM3D_CUDA(ctx, cudaMemcpyAsync(h, d, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PM3D_CUDA(ctx, cudaFree(d));
+    *out_mismatches = h[0];
+    *out_tested = h[1];
+    *out_certified = h[2];
+    return PM3D_OK;
+}
+
 extern "C" int pm3d_selfcheck_floor(pm3d_ctx *ctx, uint64_t seed, int blocks, int iters, uint64_t *out_mismatches,
                                     uint64_t *out_tested, uint64_t *out_accepted) {
     if (!ctx || blocks < 1 || iters < 1 || !out_mismatches || !out_tested || !out_accepted) return PM3D_ERR_ARG;

@@ -325,6 +325,13 @@ class Context:
                                                   C.byref(acc)), "pm3d_selfcheck_floor")
         return int(bad.value), int(n.value), int(acc.value)
 
+    def selfcheck_dda(self, seed: int, blocks: int, steps: int) -> tuple[int, int, int]:
+        """(mismatches, states tested, states the certificate accepted) of the closed-form DDA jump on the device."""
+        bad, n, acc = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.pm3d_selfcheck_dda(self.h, int(seed), int(blocks), int(steps), C.byref(bad), C.byref(n),
+                                                C.byref(acc)), "pm3d_selfcheck_dda")
+        return int(bad.value), int(n.value), int(acc.value)
+
     def selfcheck_division(self, seed: int, blocks: int, iters: int) -> tuple[int, int]:
         """(mismatches, pairs tested) of the division-free floor-cast quotient against `/` on the device."""
         bad, n = C.c_uint64(), C.c_uint64()

@@ -640,3 +640,56 @@ def test_sparse_upper_levels_skip_the_walk_without_changing_a_pixel(gpu_ctx):
         assert_frame_equal(got["rgba"][i], ref["rgba"], f"pose {i}")
         n_upper_walls += int((ref["columns"]["tile"][1:] >= 0).sum())
     assert n_upper_walls > 200     # the upper-level walls are really on screen in some of these frames
+
+
+# ---- closed-form DDA jumps (pm3d_internal.cuh dda_jump, cast_kernel.cuh jump mode)
+def test_dda_jump_is_certified_exact(gpu_ctx):
+    """The wall cast advances N steps of the reference's DDA in closed form whenever a certificate on the two
+    rounded side-distance sequences holds.  37888 rays (random, exact diagonals, rational slopes, cell centres,
+    lattice positions, (almost) axis-parallel incl. inf / NaN side distances) x ~100 random step counts up to
+    2000 against the sequential loop: every certified state must be the loop's."""
+    bad, n, cert = gpu_ctx.selfcheck_dda(20261020, 148, 2000)
+    assert n > 3_000_000
+    assert bad == 0, f"{bad} of {cert} certified jump states differ from the sequential DDA ({n} tested)"
+    assert cert > 0.6 * n, f"only {cert} of {n} states certified: the jump would rarely be used"
+
+
+def _columns_and_frames(ctx, c, offsets):
+    got = ctx.render(c["views"], c["sprites"], offsets)
+    cols = [ctx.download_columns(i) for i in range(len(c["views"]))]
+    return got, cols
+
+
+@pytest.mark.parametrize("which", ["c2", "c3", "edge"])
+def test_jump_and_sequential_cast_agree(gpu_ctx, which):
+    """PM3D_OPT_DDA_JUMP = 0 walks every ray with the sequential loop; the default jump mode must give the same
+    column records (hit cell, side, distances bit for bit), z-buffer and pixels."""
+    if which == "c2":
+        c = W.config_c2(w=640, h=360, n_poses=6)
+    elif which == "c3":
+        c = W.config_c3(levels=8, w=480, h=270, pitch=0.2, map_size=128)
+    else:
+        scene = edge_scene()
+        c = dict(scene=scene, w=200, h=120, sprites=np.zeros(0, O.SPRITE_DTYPE),
+                 views=W.make_views(scene, 200, 120, EDGE_POSES + [(5.5, 5.5, 0.5, math.pi / 4, 0.0), (5.0, 5.0, 0.5, math.pi / 4, 0.0)],
+                                    fov_deg=70.0, render_distance=-1.0))
+    n = len(c["views"])
+    offsets = c.get("offsets")
+    if offsets is None:
+        offsets = (np.arange(n + 1) * len(c["sprites"])).astype(np.int32)
+        c["sprites"] = np.concatenate([c["sprites"]] * n) if len(c["sprites"]) else c["sprites"]
+    gpu_ctx.upload_scene(c["scene"])
+    gpu_ctx.set_option(pm3d._lib.OPT_KEEP_COLUMNS, 1)
+    gpu_ctx.set_view(c["w"], c["h"], n, max(len(c["sprites"]), 1))
+    try:
+        gpu_ctx.set_option(pm3d._lib.OPT_DDA_JUMP, 0)
+        seq, seq_cols = _columns_and_frames(gpu_ctx, c, offsets)
+        gpu_ctx.set_option(pm3d._lib.OPT_DDA_JUMP, 1)
+        jmp, jmp_cols = _columns_and_frames(gpu_ctx, c, offsets)
+    finally:
+        gpu_ctx.set_option(pm3d._lib.OPT_DDA_JUMP, 1)
+    for (ca, za), (cb, zb) in zip(seq_cols, jmp_cols):
+        for f in [f for f in ca.dtype.names if not f.startswith("_")]:  # (field by field: the records carry padding bytes)
+            assert ca[f].tobytes() == cb[f].tobytes(), f
+        assert za.tobytes() == zb.tobytes()
+    assert np.array_equal(seq["rgba"], jmp["rgba"])

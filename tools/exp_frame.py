@@ -28,6 +28,9 @@ def run(ctx, cfg, w, h, label, sprites=True, reps=200, ring=8):
 
 if __name__ == "__main__":
     ctx = pm3d.Context(0)
+    ctx.set_option(pm3d._lib.OPT_DDA_JUMP, int(os.environ.get("DDA_JUMP", "1")))
+    ctx.set_option(pm3d._lib.OPT_OVERLAP, int(os.environ.get("OVERLAP", "1")))
+    print("DDA_JUMP =", os.environ.get("DDA_JUMP", "1"), "OVERLAP =", os.environ.get("OVERLAP", "1"))
     c2 = W.config_c2(n_poses=8)
     run(ctx, c2, 1920, 1080, "c2 1080p 200 sprites")
     run(ctx, c2, 1920, 1080, "c2 1080p no sprites", sprites=False)

@@ -10,6 +10,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 cfg = W.config_c4(n_views=n)
 ctx = pm3d.Context(0)
+ctx.set_option(pm3d._lib.OPT_OVERLAP, int(os.environ.get('OVERLAP', '1')))
+ctx.set_option(pm3d._lib.OPT_DDA_JUMP, int(os.environ.get('DDA_JUMP', '1')))
 ctx.upload_scene(cfg["scene"]); ctx.set_view(320, 200, n, len(cfg["sprites"]))
 v, s, o = cfg["views"], cfg["sprites"], cfg["offsets"]
 dv, ds, do = ctx.device_alloc(v.nbytes), ctx.device_alloc(s.nbytes), ctx.device_alloc(o.nbytes)

@@ -5,5 +5,6 @@ import numpy as np, pm3d
 from pm3d import workloads as W
 from exp_frame import run
 ctx = pm3d.Context(0)
-c2 = W.config_c2(n_poses=1)
-run(ctx, c2, 1920, 1080, "c2 pose0 1080p 200 sprites", reps=10)
+ctx.set_option(pm3d._lib.OPT_OVERLAP, int(os.environ.get("OVERLAP", "1")))
+c2 = W.config_c2(n_poses=8)
+run(ctx, c2, 1920, 1080, "c2 1080p 200 sprites", reps=16)

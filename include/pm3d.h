@@ -459,6 +459,19 @@ int pm3d_selfcheck_division(pm3d_ctx *ctx, uint64_t seed, int blocks, int iters,
 int pm3d_selfcheck_floor(pm3d_ctx *ctx, uint64_t seed, int blocks, int iters, uint64_t *out_mismatches,
                          uint64_t *out_tested, uint64_t *out_accepted);
 
+/* ---- Pathing.FindPath (game/model/pathing.go:123-186; call site game/ai_movement.go:64), batched: one query per AI
+ * unit.  queries[n][4] = start x, y, finish x, y (float64 map positions; the tiles are int(x), int(y) as in the
+ * reference).  The search runs over level 0 of the grid given to pm3d_upload_grid (initPathing, pathing.go:94-112: a
+ * tile is a blocker iff its cell is non-zero) and reproduces astar.Path of github.com/harbdog/go-astar — including the
+ * container/heap order that picks one of the many equally short paths — then the reference's reversal into cell
+ * centres and its Bezier smoothing in segments of seven steps (game/common/bezier).
+ * out_points[n][max_points][2]: the points FindPath returns, start -> finish.  out_count[n]: how many there are
+ * (more than max_points: only the first max_points were written), -1 = "unable to find path" (the reference's error;
+ * also a start or finish outside the map).  flags: PM3D_IN_DEVICE / PM3D_OUT_DEVICE / PM3D_NO_SYNC (device buffers
+ * only).  Scratch: 16 bytes per map cell and search in flight, at most 4 GiB, owned by the ctx. */
+int pm3d_find_path_batch(pm3d_ctx *ctx, const double *queries, int64_t n, int max_points, double *out_points,
+                         int32_t *out_count, uint32_t flags);
+
 /* Device self-check of the wall cast's closed-form DDA jump (pm3d_internal.cuh dda_jump): blocks*256 rays (random
  * poses and directions, exact diagonals, rational slopes, cell-centre / lattice positions) are walked `steps` steps
  * by the reference's sequential loop; at random step counts the certified closed-form state (x steps, y steps, side

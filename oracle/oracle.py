@@ -356,3 +356,22 @@ def raycast_sprites(world: np.ndarray, cam_x: float, cam_y: float, render_distan
           C.c_int32(target), _ptr(clutter), C.c_int32(len(clutter)), _ptr(extras), C.c_int32(len(extras)), _ptr(out), _ptr(idx),
           C.c_int32(cap))
     return out[:n], idx[:n]
+
+
+def find_path_batch(level0: np.ndarray, queries: np.ndarray, cap: int = 4096, threads: int = 8):
+    """Pathing.FindPath for a batch of (start x, y, finish x, y) queries: (points [n][cap][2], count [n] (-1 = no
+    path), astar path cells [n], nodes popped [n])."""
+    L = lib()
+    level0 = np.ascontiguousarray(level0, dtype=np.uint16)
+    q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, 4)
+    n = len(q)
+    pts = np.zeros((n, cap, 2), dtype=np.float64)
+    cnt = np.zeros(n, dtype=np.int32)
+    cells = np.zeros(n, dtype=np.int32)
+    exp = np.zeros(n, dtype=np.int64)
+    L.orc_find_path_batch.restype = None
+    L.orc_find_path_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+    L.orc_find_path_batch(_ptr(level0), level0.shape[0], level0.shape[1], _ptr(q), n, _ptr(pts), cap, _ptr(cnt), _ptr(cells),
+                          _ptr(exp), threads)
+    return pts, cnt, cells, exp

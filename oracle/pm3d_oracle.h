@@ -246,6 +246,15 @@ int32_t orc_raycast_sprites(const orc_sprite *world, int32_t n_world, double cam
 /* Go int(float64) on amd64. */
 int64_t orc_go_int(double v);
 
+/* Pathing.FindPath (game/model/pathing.go:123-186) [V] over astar.Path of go-astar [R] and container/heap [R]
+ * (pm3d_oracle_path.c): the smoothed path from start to finish over the level-0 grid [map_w][map_h]; returns the
+ * number of curve points (writes <= cap into out_xy), -1 when there is no path. */
+int64_t orc_find_path(const uint16_t *level0, int32_t map_w, int32_t map_h, double sx, double sy, double fx, double fy,
+                      double *out_xy, int64_t cap, int64_t *n_cells, int64_t *expanded);
+void orc_find_path_batch(const uint16_t *level0, int32_t map_w, int32_t map_h, const double *queries, int64_t n,
+                         double *out_xy, int64_t cap, int32_t *out_count, int32_t *out_cells, int64_t *out_expanded,
+                         int32_t threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -162,7 +162,7 @@ void pm3d_destroy(pm3d_ctx *ctx) {
     pm3d_comm_destroy(ctx);
     void *ptrs[] = {ctx->grid, ctx->dist, ctx->qdist, ctx->wall_lut, ctx->atlas, ctx->floor_tiles, ctx->sheet_pixels, ctx->sheet_info,
                     ctx->views, ctx->sprites, ctx->sprite_offset, ctx->frame, ctx->checksums, ctx->segs, ctx->seg_irect,
-                    ctx->cell_start, ctx->cell_items, ctx->cell_rec, ctx->cell_code, ctx->los_list, ctx->los_count, ctx->colliders, ctx->cb_start, ctx->cb_items, ctx->cb_loose, ctx->present_map, ctx->present_buf, ctx->sparse_cells, ctx->sparse_count, ctx->clutter_class, ctx->clutter_tab, ctx->io_a, ctx->io_b, ctx->io_c, ctx->flush_buf};
+                    ctx->cell_start, ctx->cell_items, ctx->cell_rec, ctx->cell_code, ctx->los_list, ctx->los_count, ctx->path_scratch, ctx->colliders, ctx->cb_start, ctx->cb_items, ctx->cb_loose, ctx->present_map, ctx->present_buf, ctx->sparse_cells, ctx->sparse_count, ctx->clutter_class, ctx->clutter_tab, ctx->io_a, ctx->io_b, ctx->io_c, ctx->flush_buf};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &fs : ctx->sets) {

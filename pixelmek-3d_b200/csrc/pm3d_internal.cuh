@@ -213,6 +213,9 @@ struct pm3d_ctx {
     size_t los_list_bytes = 0;
     unsigned *los_count = nullptr;
     bool los_smem_optin = false;
+    // batched Pathing.FindPath (path_kernel.cu): node states and queues of the searches in flight
+    void *path_scratch = nullptr;
+    size_t path_scratch_bytes = 0;
     // presentation step (present_kernel.cu)
     int32_t *present_map = nullptr;  // [present_w + present_h] output -> source column / row, -1 = outside
     int present_w = 0, present_h = 0, present_src_w = 0, present_src_h = 0;

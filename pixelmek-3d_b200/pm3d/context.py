@@ -207,6 +207,16 @@ class Context:
         self._check(self.lib.pm3d_los_batch(self.h, ptr(rays), len(rays), ptr(out), 0), "pm3d_los_batch")
         return out
 
+    def find_path_batch(self, queries: np.ndarray, max_points: int = 4096):
+        """Pathing.FindPath for a batch of (start x, y, finish x, y) queries over level 0 of the uploaded grid:
+        (points [n][max_points][2], count [n]; -1 = no path)."""
+        q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, 4)
+        n = len(q)
+        pts = np.zeros((n, max_points, 2), dtype=np.float64)
+        cnt = np.zeros(n, dtype=np.int32)
+        self._check(self.lib.pm3d_find_path_batch(self.h, ptr(q), n, int(max_points), ptr(pts), ptr(cnt), 0), "pm3d_find_path_batch")
+        return pts, cnt
+
     def move_batch(self, moves: np.ndarray, clip: float):
         moves = np.ascontiguousarray(moves, dtype=np.float64).reshape(-1, 4)
         n = len(moves)

@@ -390,6 +390,28 @@ def los_rays(level0: np.ndarray, n: int, seed: int) -> np.ndarray:
     return rays
 
 
+def path_queries(level0: np.ndarray, n: int, seed: int, max_manhattan: int | None = None) -> np.ndarray:
+    """(start x, y, finish x, y) between free cells, fractional positions inside the cells; optionally no farther
+    apart than max_manhattan cells (AI units path towards targets in their neighbourhood)."""
+    rng = SplitMix64(seed)
+    free = np.argwhere(level0 == 0)
+    a = free[(rng.uniform(n) * len(free)).astype(np.int64)]
+    b = free[(rng.uniform(n) * len(free)).astype(np.int64)]
+    if max_manhattan is not None:
+        for _ in range(64):
+            far = np.abs(a - b).sum(axis=1) > max_manhattan
+            if not far.any():
+                break
+            b[far] = free[(rng.uniform(int(far.sum())) * len(free)).astype(np.int64)]
+        far = np.abs(a - b).sum(axis=1) > max_manhattan
+        b[far] = a[far]
+    j = rng.uniform(4 * n).reshape(n, 4)
+    q = np.empty((n, 4), dtype=np.float64)
+    q[:, :2] = a + 0.05 + 0.9 * j[:, :2]
+    q[:, 2:] = b + 0.05 + 0.9 * j[:, 2:]
+    return q
+
+
 def move_workload(level0: np.ndarray, n_movers: int, n_colliders: int, seed: int, max_len: float = 0.5):
     """A tick of the projectile / unit fan-out (game/combat.go:206-239): colliders scattered over free cells,
     movers (a third of them next to a collider) each asking for one short move.  Returns (colliders, movers)."""

@@ -352,7 +352,8 @@ __device__ __forceinline__ bool floor_fast_index(double w, double D, double P, u
 }
 
 // ---- DDA jump --------------------------------------------------------------------------------
-// The reference's wall cast (oracle/pm3d_oracle.c:117-127) is a MERGE of two non-decreasing binary64 sequences
+// The reference's wall cast (raycaster-go Camera.castLevel: `if sideDistX < sideDistY { sideDistX += deltaDistX; mapX += stepX }
+// else { sideDistY += deltaDistY; mapY += stepY }`) is a MERGE of two non-decreasing binary64 sequences
 //     A_0 = sideDistX, A_{k+1} = RN(A_k + deltaDistX)        B_0 = sideDistY, B_{k+1} = RN(B_k + deltaDistY):
 // every step takes an x step when A_i < B_j and a y step otherwise.  Only the cells it visits matter (the wall
 // distance comes from the integer hit cell), and the state (i, j) after N steps is the unique split i + j = N with

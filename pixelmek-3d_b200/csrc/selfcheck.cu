@@ -117,7 +117,7 @@ __global__ void k_selfcheck_dda(uint64_t seed, int steps, unsigned long long *co
     const double U = 1.0 / 9007199254740992.0;
     const uint64_t r0 = sm64(s), r1 = sm64(s), r2 = sm64(s), r3 = sm64(s), r4 = sm64(s);
     const int mode = (int)(r4 & 7);
-    // position inside a cell, direction: as the cast builds them (oracle/pm3d_oracle.c:102-115)
+    // position inside a cell, direction: as the cast builds them (cast_kernel.cuh)
     double fracX = (double)(r0 >> 11) * U, fracY = (double)(r1 >> 11) * U;
     double dirX = 2.0 * (double)(r2 >> 11) * U - 1.0, dirY = 2.0 * (double)(r3 >> 11) * U - 1.0;
     if (mode == 1) { dirY = dirX; }                                             // exact diagonal: ties everywhere

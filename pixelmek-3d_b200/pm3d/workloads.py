@@ -191,12 +191,53 @@ def load_golden(name: str) -> dict:
         return {k: z[k] for k in z.files}
 
 
-def proving_grounds_scene():
+_REAL = None
+
+
+def real_pixels() -> dict:
+    """The reference's own wall / floor / sky images and sprite sheets of proving_grounds + trial_day
+    (tests/golden/proving_grounds_pixels.npz, decoded from the PNGs by tests/golden/make_pixels.py), premultiplied the
+    way the game's loaders hold them."""
+    global _REAL
+    if _REAL is None:
+        z = load_golden("proving_grounds_pixels")
+        names = [str(n) for n in z["tile_names"]]
+        sheet_names = [str(n) for n in z["sheet_names"]]
+        _REAL = dict(tile_names=names, tiles=premultiply(z["tiles"]), sheet_names=sheet_names,
+                     sheets=[premultiply(z[f"sheet_{i}"]) for i in range(len(sheet_names))])
+    return _REAL
+
+
+def proving_grounds_scene(pixels: str = "real"):
+    """The bundled map.  pixels = "real": the reference's textures and sprite sheets, resolved through the map's own
+    texture table the way TextureHandler.TextureAt / MapTexture.GetImage do (game/texture/texture.go:69-97,
+    game/model/map.go:106-115: side 0 -> SideY when set, side 1 -> SideX when set, else Image); sheets 0..3 are
+    tree_0, tree_1, the adder 6x1 strip and rock_0 — the sizes the procedural sheets imitate.  pixels = "synthetic":
+    the procedural tiles and silhouettes (alpha-hole boundary tile, 1-px translucent rims)."""
     g = load_golden("proving_grounds")
     lighting = (float(g["light_falloff"]), float(g["light_illumination"]), tuple(int(v) for v in g["min_light"]),
                 tuple(int(v) for v in g["max_light"]))
-    scene = scene_from_grid(g["levels"], int(g["num_raycast_levels"]), g["floor_grid"], lighting=lighting,
-                            has_boundary=bool(g["has_boundary_wall"]))
+    if pixels == "synthetic":
+        scene = scene_from_grid(g["levels"], int(g["num_raycast_levels"]), g["floor_grid"], lighting=lighting,
+                                has_boundary=bool(g["has_boundary_wall"]))
+        return scene, g
+    rp = real_pixels()
+    tile_of = {nm: i for i, nm in enumerate(rp["tile_names"])}
+    image = [str(v) for v in g["tex_image"]]
+    side_x = [str(v) for v in g["tex_side_x"]]
+    side_y = [str(v) for v in g["tex_side_y"]]
+    side0 = np.array([tile_of.get(side_y[i] or image[i], -1) for i in range(len(image))], dtype=np.int32)
+    side1 = np.array([tile_of.get(side_x[i] or image[i], -1) for i in range(len(image))], dtype=np.int32)
+    keep = g["tex_index"] > 0
+    floor_images = [str(v) for v in g["floor_images"]]
+    ft = np.array([tile_of[nm] for nm in floor_images], dtype=np.int16)[np.asarray(g["floor_grid"], dtype=np.int64)]
+    scene = SceneData(
+        grid=g["levels"], num_levels=int(g["num_raycast_levels"]), wall_tex_index=g["tex_index"][keep].astype(np.int32),
+        wall_tile_side0=side0[keep], wall_tile_side1=side1[keep], floor_tiles=ft, atlas=rp["tiles"],
+        sky_tile=tile_of[str(g["sky_box"])], floorbox_tile=tile_of[str(g["floor_box"])], sheets=list(rp["sheets"]),
+        light_falloff=lighting[0], global_illumination=lighting[1], min_light=lighting[2], max_light=lighting[3],
+        has_boundary_wall=bool(g["has_boundary_wall"]),
+    )
     return scene, g
 
 
@@ -319,17 +360,17 @@ def nearest_sprites(all_sprites: np.ndarray, poses, k: int):
 # --------------------------------------------------------------------------- the five configs
 
 
-def config_c1():
+def config_c1(pixels: str = "real"):
     """Bundled proving_grounds, trial_day drop zone, 640x360, static sprites + mission units."""
-    scene, g = proving_grounds_scene()
+    scene, g = proving_grounds_scene(pixels)
     pose = (float(g["drop_zone"][0]), float(g["drop_zone"][1]), 0.5, cardinal_to_angle(float(g["drop_heading_deg"])), 0.0)
     views = make_views(scene, 640, 360, [pose])
     return dict(scene=scene, w=640, h=360, views=views, sprites=golden_sprites(scene, g), poses=[pose], golden=g)
 
 
-def config_c2(w: int = 1920, h: int = 1080, n_sprites: int = 200, n_poses: int = 1, seed: int = 12345):
+def config_c2(w: int = 1920, h: int = 1080, n_sprites: int = 200, n_poses: int = 1, seed: int = 12345, pixels: str = "real"):
     """Same map at 1080p with 200 frustum sprites; n_poses > 1 gives a ring of distinct views."""
-    scene, g = proving_grounds_scene()
+    scene, g = proving_grounds_scene(pixels)
     base = (float(g["drop_zone"][0]), float(g["drop_zone"][1]), 0.5, cardinal_to_angle(float(g["drop_heading_deg"])), 0.0)
     poses = [base]
     if n_poses > 1:
@@ -358,8 +399,8 @@ def config_c3(levels: int = 3, w: int = 3840, h: int = 2160, pitch: float = 0.0,
     return dict(scene=scene, w=w, h=h, views=views, sprites=np.zeros(0, SPRITE_DTYPE), poses=[pose])
 
 
-def config_c4(n_views: int = 4096, w: int = 320, h: int = 200, k_sprites: int = 50, seed: int = 4096):
-    scene, g = proving_grounds_scene()
+def config_c4(n_views: int = 4096, w: int = 320, h: int = 200, k_sprites: int = 50, seed: int = 4096, pixels: str = "real"):
+    scene, g = proving_grounds_scene(pixels)
     poses = free_cell_poses(scene, n_views, seed)
     views = make_views(scene, w, h, poses)
     sprites, off = nearest_sprites(golden_sprites(scene, g), poses, k_sprites)

@@ -60,15 +60,20 @@ def check_all(ctx, got, want, offsets, n_sprites):
 # --------------------------------------------------------------------------- the five configs (reduced where the oracle would be slow)
 
 
-def test_c1_bundled_map_640x360(gpu_ctx):
-    c = W.config_c1()
+@pytest.mark.parametrize("pixels", ["real", "synthetic"])
+def test_c1_bundled_map_640x360(gpu_ctx, pixels):
+    """pixels = "real": the reference's own wall / floor / sky PNGs and tree / mech sheets (tests/golden/
+    proving_grounds_pixels.npz; the trees are mostly translucent texels, the boundary wall half holes);
+    "synthetic": the procedural tiles (alpha-hole boundary tile, 1-px translucent rims)."""
+    c = W.config_c1(pixels)
     off = np.array([0, len(c["sprites"])], dtype=np.int32)
     got, want = render_both(gpu_ctx, c["scene"], 640, 360, c["views"], c["sprites"], off)
     check_all(gpu_ctx, got, want, off, len(c["sprites"]))
 
 
-def test_c2_1080p_200_sprites(gpu_ctx):
-    c = W.config_c2(n_poses=3)
+@pytest.mark.parametrize("pixels", ["real", "synthetic"])
+def test_c2_1080p_200_sprites(gpu_ctx, pixels):
+    c = W.config_c2(n_poses=3, pixels=pixels)
     got, want = render_both(gpu_ctx, c["scene"], 1920, 1080, c["views"], c["sprites"], c["offsets"])
     check_all(gpu_ctx, got, want, c["offsets"], len(c["sprites"]))
 
@@ -82,8 +87,9 @@ def test_c3_multilevel_infinite_distance(gpu_ctx, levels, pitch):
     check_all(gpu_ctx, got, want, off, 0)
 
 
-def test_c4_batched_views_320x200(gpu_ctx):
-    c = W.config_c4(n_views=48)
+@pytest.mark.parametrize("pixels", ["real", "synthetic"])
+def test_c4_batched_views_320x200(gpu_ctx, pixels):
+    c = W.config_c4(n_views=48, pixels=pixels)
     got, want = render_both(gpu_ctx, c["scene"], 320, 200, c["views"], c["sprites"], c["offsets"])
     check_all(gpu_ctx, got, want, c["offsets"], len(c["sprites"]))
 

@@ -3,7 +3,7 @@
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/a_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/a_pytest.log
-tail -15 gpurun_out/a_pytest.log
+grep -E "^E|passed|failed|rc=" gpurun_out/a_pytest.log | tail -15
 timeout 600 python bench.py --steps 200 --warmup 20 > gpurun_out/a_bench.json 2> gpurun_out/a_bench.err; echo "bench rc=$?"
 tail -c 1500 gpurun_out/a_bench.err
 python - <<'PY'

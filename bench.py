@@ -343,10 +343,66 @@ def sweep_c5(ctx, rank, world, dist, torch, dev):
     peak, _ = hbm_peak()
     return {
         "workload": f"c5: 16777216 LOS rays, 256x256 map 10% walls, {len(segs)} collision segments, contiguous shards; per rep "
-                    "k_los + all-gather of the 16 MiB of answers to every rank (pm3d_comm_los_batch), gather timed",
+                    "k_los_fast + k_los + all-gather of the 16 MiB of answers to every rank (pm3d_comm_los_batch), gather timed",
         "mrays_per_s": n_rays / (ms_max * 1e-3) / 1e6, "ms_per_batch": ms_max, "rays_per_gpu": n,
         "hbm_frac": (33.0 * n / (ms * 1e-3)) / 1e9 / peak, "visible_rays": int(visible.item()),
     }
+
+
+def sweep_astar(ctx, rank, world, dist, torch, dev, with_cpu):
+    """Batched Pathing.FindPath (game/model/pathing.go:123-186): 4096 AI units of proving_grounds each asking for a
+    path to a target within 60 cells, contiguous shards, results resident; returns dict for 'extra'."""
+    import ctypes as C
+
+    from pm3d import shard, workloads as Wk
+
+    n_all, cap = 4096, 1024
+    g = Wk.load_golden("proving_grounds")
+    lvl = g["levels"][0]
+    scene, _ = Wk.proving_grounds_scene()
+    ctx.upload_scene(scene)
+    q_all = Wk.path_queries(lvl, n_all, 5, max_manhattan=60)
+    lo, hi = shard.ray_shard(n_all, rank, world)
+    q = np.ascontiguousarray(q_all[lo:hi])
+    n = len(q)
+    d_q, d_p, d_c = ctx.device_alloc(max(q.nbytes, 32)), ctx.device_alloc(max(n, 1) * cap * 16), ctx.device_alloc(max(n, 1) * 4)
+    ctx.h2d(d_q, q)
+    call = lambda: ctx._check(ctx.lib.pm3d_find_path_batch(ctx.h, C.c_void_p(d_q), n, cap, C.c_void_p(d_p), C.c_void_p(d_c), 7), "pm3d_find_path_batch")
+    call()
+    ctx.sync()
+    if world > 1:
+        dist.barrier()
+    reps = 3
+    ctx.timer_start(5)
+    for _ in range(reps):
+        call()
+    ctx.timer_stop(5)
+    ms = ctx.timer_ms(5) / reps
+    cnt = np.zeros(n, dtype=np.int32)
+    ctx.d2h(cnt, d_c)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    tot = torch.tensor([int((cnt > 0).sum()), int(cnt[cnt > 0].sum())], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot)
+    for p_ in (d_q, d_p, d_c):
+        ctx.device_free(p_)
+    ms_max = float(t.item())
+    out = {
+        "workload": f"astar: {n_all} FindPath queries on proving_grounds (500x500, targets within 60 cells), contiguous shards; "
+                    "go-astar's exact queue order + Bezier smoothing, one search per thread",
+        "paths_per_s": n_all / (ms_max * 1e-3), "ms_per_batch": ms_max, "queries_per_gpu": n,
+        "paths_found": int(tot[0].item()), "curve_points": int(tot[1].item()),
+    }
+    if with_cpu:
+        from oracle import oracle as O
+
+        threads = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        O.find_path_batch(lvl, q_all[:512], cap=cap, threads=threads)
+        out["cpu_port_paths_per_s"] = 512 / (time.perf_counter() - t0)
+        out["cpu_port_threads"] = threads
+    return out
 
 
 def sweep_moves(ctx, rank, world, dist, torch, dev):
@@ -737,6 +793,7 @@ def run_ours(args, rank, world, local_rank):
             extra["moves"] = sweep_moves(ctx, rank, world, dist, torch, dev)
             extra["clutter"] = sweep_clutter(ctx, rank, world, dist, torch, dev, rank == 0 and world == 1 and not args.no_cpu)
             extra["tick"] = sweep_tick(ctx, rank, world, dist, torch, dev)
+            extra["astar"] = sweep_astar(ctx, rank, world, dist, torch, dev, rank == 0 and world == 1 and not args.no_cpu)
             extra["present"] = sweep_present(ctx, torch)
         except Exception as e:
             # a failed sweep is a failed run: the headline line is still printed (with the error), then every rank

@@ -400,7 +400,9 @@ int pm3d_comm_all_gather(pm3d_ctx *ctx, const void *d_send, void *d_recv, int64_
 /* pm3d_render_resident for THIS rank's n_local views of a batch of n_views_global (its views in shard order:
  * global view rank + k * n_ranks is local view k), then the gather: on return (enqueue only, pm3d_sync to wait)
  * d_all_conv[n_views_global] and d_all_checksums[n_views_global] (device memory, either may be NULL) hold the
- * convergence record and the frame checksum of EVERY view of the batch, in global view order, on every rank. */
+ * convergence record and the frame checksum of EVERY view of the batch, in global view order, on every rank.
+ * The checksum / gather tail runs on the ctx stream behind the batch; a FOLLOWING frame batch does not wait for it
+ * (nothing the tail writes is a frame input), so its cast / setup launch overlaps this batch's compose and gather. */
 int pm3d_comm_render_views(pm3d_ctx *ctx, const pm3d_view *d_views, int n_local, const pm3d_sprite *d_sprites,
                            const int32_t *d_sprite_offset, int n_sprites_total, uint8_t *d_out_rgba, int n_views_global,
                            pm3d_convergence *d_all_conv, uint64_t *d_all_checksums);

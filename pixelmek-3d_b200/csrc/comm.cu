@@ -148,7 +148,9 @@ int views_post(pm3d_ctx *ctx, int n_views_global, pm3d_convergence *d_all_conv, 
     k_unshard_views<<<(n_views_global + 127) / 128, 128, 0, ctx->stream>>>((const ViewResult *)ctx->comm_recv, d_all_conv, d_all_sums, n_views_global, ctx->comm_size, per);
     ctx->launches++;
     PM3D_CUDA(ctx, cudaGetLastError());
-    pm3d_main_touch(ctx);
+    // (no pm3d_main_touch: checksum, pack, gather and unshard only CONSUME a frame batch — nothing they write is an
+    //  input of a frame, so the front launch of the next batch need not wait for them and runs beside this batch's
+    //  compose launch and gather; the set-reuse events still keep the conv / checksum buffers intact until read)
     return PM3D_OK;
 }
 

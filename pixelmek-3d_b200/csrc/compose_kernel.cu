@@ -232,6 +232,10 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
     constexpr int WARP_WORDS = MAX_WARP_SPRITES / 32;
     __shared__ WarpList<MAX_WARP_SPRITES, LATENCY> s_list[COMPOSE_WARPS];
     __shared__ uint32_t s_xm[COMPOSE_WARPS][WARP_WORDS][32];  // per-lane sprite masks (kept out of registers and out of unrolled code)
+    // latency mode: per pixel, the listed sprites whose texel was TRANSLUCENT in the front-to-back walk (bit = list
+    // index).  The repaint of such a pixel blends exactly these over its opaque base instead of testing every sprite
+    // of the lane again (the bundled trees are mostly fully transparent texels around a few translucent ones)
+    __shared__ uint32_t s_hit[LATENCY ? COMPOSE_WARPS : 1][4][LATENCY ? WARP_WORDS : 1][32];
 
     const int group = blockIdx.x, view = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -463,6 +467,10 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
         const bool sprite_f2b = n_list > 0 && !p.force_painter;
         unsigned s_far = 0u;    // pixels whose opaque texel was found among the far entries (not in the list)
         if (sprite_f2b && LATENCY) {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int wq = 0; wq < WARP_WORDS; wq++) s_hit[warp][j][wq][lane] = 0u;
             // Latency mode (few rows per warp, single frames).  SPRITE_BATCH sprites per step: a lane's walk is a chain of
             // dependent loads (record -> texel), so the records and texels of the next few candidates are fetched
             // together and then resolved nearest first.
@@ -508,7 +516,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                         if ((s_got >> j) & 1u) continue;
                         const uint32_t a = tx[b][j] >> 24;
                         if (a == 255u) { s_top[j] = blend_over(0u, tx[b][j], tint); s_got |= 1u << j; s_stop |= (uint32_t)ids[b] << (8 * j); }
-                        else if (a != 0u) s_trans |= 1u << j;
+                        else if (a != 0u) { s_trans |= 1u << j; s_hit[warp][j][ids[b] >> 5][lane] |= 1u << (ids[b] & 31); }
                     }
                 }
             }
@@ -696,6 +704,31 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                     }
                 }
             }
+            if (LATENCY && !p.force_painter) {
+                // the translucent texels the walk met, far -> near (ascending list index), over the opaque base
+#pragma unroll 1
+                for (int wd = 0; wd < n_words; wd++) {
+                    uint32_t hm[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) hm[j] = ((repaint >> j) & 1u) ? s_hit[warp][j][wd][lane] : 0u;
+                    uint32_t m = hm[0] | hm[1] | hm[2] | hm[3];
+                    while (m) {
+                        const int bit = __ffs(m) - 1;
+                        m &= m - 1u;
+                        const DrawRec &d = list_rec(wd * 32 + bit);
+                        uint32_t t[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {  // the four texels are fetched together
+                            const uint64_t a = ((hm[j] >> bit) & 1u) ? sprite_index(d, x0 + j, y, zb[j]) : NO_TEXEL;
+                            t[j] = a != NO_TEXEL ? __ldg(p.sheet_pixels + a) : 0u;
+                        }
+                        const uint32_t tint = d.tint;
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            if ((hm[j] >> bit) & 1u) px[j] = blend_over(px[j], t[j], tint);
+                    }
+                }
+            } else
 #pragma unroll 1
             for (int wd = 0; wd < n_words; wd++) {
                 uint32_t m = s_xm[warp][wd][lane];

@@ -1,9 +1,10 @@
 // front_kernel.cu — the frame path's first launch: the per-column wall cast (cast_kernel.cuh) and the
 // per-view setup (view_kernel.cuh) are independent of each other, so they run as CTAs of ONE grid:
-// CTAs [0, n_cast) cast four (view, level, 64-column group) units of 64 rays each,
-// CTAs [n_cast, n_cast + n_views) set up one view each.  The compose kernel consumes both.
+// CTAs [0, n_views) set up the sprites of one view each (issued first: the longest CTAs of a single frame),
+// the next n_cast CTAs cast four (view, level, 64-column group) units of 64 rays each,
+// the rest build the per-row tables (VIEW_THREADS rows of a view per CTA).  The compose kernel consumes all three.
 #include "cast_kernel.cuh"
-#include "view_kernel.cuh"
+#include "view_kernel.cuh"  // (after cast_kernel.cuh: PM3D_FRONT_STATS counters)
 
 #ifdef PM3D_FRONT_STATS
 // (experiments only: tools/exp_front_stats.py builds the library with -DPM3D_FRONT_STATS)
@@ -19,13 +20,20 @@ extern "C" int pm3d_debug_front_stats(pm3d_ctx *ctx, unsigned long long *out, in
 #define FRONT_MIN_BLOCKS 4
 #endif
 template <bool DEBUG>
-__global__ void __launch_bounds__(VIEW_THREADS, FRONT_MIN_BLOCKS) k_front(CastParams cp, ViewParams vp, int n_cast_blocks, long long n_pairs) {
+__global__ void __launch_bounds__(VIEW_THREADS, FRONT_MIN_BLOCKS) k_front(CastParams cp, ViewParams vp, int n_cast_blocks, long long n_pairs, int n_views) {
 #ifdef PM3D_FRONT_STATS
     const long long t0 = clock64();
 #endif
-    if ((int)blockIdx.x < n_cast_blocks) {
+    // the view setups come first in the grid: one CTA each, the longest-running ones of a single frame
+    const int b = (int)blockIdx.x;
+    if (b < n_views) {
+        view_setup(vp, b);
+#ifdef PM3D_FRONT_STATS
+        atomicMax(&g_front_stats[3], (unsigned long long)(clock64() - t0));
+#endif
+    } else if (b < n_views + n_cast_blocks) {
         // a pair of warps = the 64 columns of one (view, level, group)
-        const long long pair = (long long)blockIdx.x * (VIEW_THREADS / 64) + (threadIdx.x >> 6);
+        const long long pair = (long long)(b - n_views) * (VIEW_THREADS / 64) + (threadIdx.x >> 6);
         if (pair >= n_pairs) return;
         const int group = (int)(pair % cp.n_groups);
         const long long vl = pair / cp.n_groups;
@@ -34,10 +42,9 @@ __global__ void __launch_bounds__(VIEW_THREADS, FRONT_MIN_BLOCKS) k_front(CastPa
         atomicMax(&g_front_stats[2], (unsigned long long)(clock64() - t0));
 #endif
     } else {
-        view_setup(vp, (int)blockIdx.x - n_cast_blocks);
-#ifdef PM3D_FRONT_STATS
-        atomicMax(&g_front_stats[3], (unsigned long long)(clock64() - t0));
-#endif
+        // row tables: VIEW_THREADS rows of one view per CTA
+        const int r = b - n_views - n_cast_blocks, row_blocks = (vp.h + VIEW_THREADS - 1) / VIEW_THREADS;
+        view_rows(vp, r / row_blocks, (r % row_blocks) * VIEW_THREADS);
     }
 }
 
@@ -77,11 +84,12 @@ int pm3d_launch_front(pm3d_ctx *ctx, int n_views, cudaStream_t stream) {
 
     const long long n_pairs = (long long)n_views * ctx->num_levels * ctx->n_groups;
     const long long n_cast = (n_pairs + VIEW_THREADS / 64 - 1) / (VIEW_THREADS / 64);
-    if (n_cast + n_views > 0x7fffffffll) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "too many rays for one launch");
-    const unsigned grid = (unsigned)(n_cast + n_views);
+    const long long row_blocks = (long long)n_views * ((ctx->h + VIEW_THREADS - 1) / VIEW_THREADS);
+    if (n_cast + n_views + row_blocks > 0x7fffffffll) return pm3d_fail(ctx, PM3D_ERR_CAPACITY, "too many rays for one launch");
+    const unsigned grid = (unsigned)(n_cast + n_views + row_blocks);
     pm3d_kt_mark(ctx, 0, 0, stream);
-    if (p.dbg) k_front<true><<<grid, VIEW_THREADS, 0, stream>>>(p, v, (int)n_cast, n_pairs);
-    else k_front<false><<<grid, VIEW_THREADS, 0, stream>>>(p, v, (int)n_cast, n_pairs);
+    if (p.dbg) k_front<true><<<grid, VIEW_THREADS, 0, stream>>>(p, v, (int)n_cast, n_pairs, n_views);
+    else k_front<false><<<grid, VIEW_THREADS, 0, stream>>>(p, v, (int)n_cast, n_pairs, n_views);
     pm3d_kt_mark(ctx, 0, 1, stream);
     ctx->launches++;
     PM3D_CUDA(ctx, cudaGetLastError());

@@ -57,17 +57,17 @@ __device__ __forceinline__ bool key_before(const SortKey &a, const SortKey &b) {
     return a.idx < b.idx;
 }
 
-__device__ __forceinline__ void view_setup(const ViewParams &p, const int view) {
-    const int tid = threadIdx.x;
+// (a) row table of one view: rows [row0, row0 + VIEW_THREADS) — its own CTAs of the front launch, beside the cast and
+// the sprite setup (it is a third of the sprite setup's serial time otherwise)
+__device__ __forceinline__ void view_rows(const ViewParams &p, const int view, const int row0) {
     const pm3d_view c = p.views[view];
-    const int64_t h = p.h, w = p.w;
-
-    // ---------------- (a) rows
+    const int64_t h = p.h;
     const int64_t horizon = go_int((double)h * 0.5) + c.pitch_px;
     // the two box spans are row-invariant: one 64-bit division each, not one per row
     const uint64_t sky_step = horizon > 0 ? span_step(p.tex_size, horizon) : 0ull;
     const uint64_t box_step = h > horizon ? span_step(p.tex_size, h - horizon) : 0ull;
-    for (int y = tid; y < p.h; y += VIEW_THREADS) {
+    const int y = row0 + (int)threadIdx.x;
+    if (y < p.h) {
         RowRec r;
         r.cd = ((double)h + 2.0 * c.cam_z_px) / (2.0 * (double)(y - c.pitch_px) - (double)h);
         r.tint = light_tint(c, r.cd, 255, 0.0, false);
@@ -81,7 +81,87 @@ __device__ __forceinline__ void view_setup(const ViewParams &p, const int view) 
         r.info = (valid ? 0x80000000u : 0u) | (y < horizon ? 0x40000000u : 0u) | ((exp_mid(r.cd) && r.cd > 0.0) ? 0x20000000u : 0u) | v;
         p.row_rec[(size_t)view * p.h + y] = r;
     }
+}
 
+// One sprite of a view: screen rectangle (SetScreenRect) and, when it can touch the screen, its draw record.
+// Returns whether it is on screen.  (raycaster.Camera sprite cast in Go integer semantics.)
+__device__ __forceinline__ bool project_sprite(const ViewParams &p, const pm3d_view &c, const pm3d_sprite &sp, const double dist,
+                                               const int src, pm3d_rect &rc, DrawRec &d) {
+    const int64_t h = p.h, w = p.w;
+    const double spriteX = sp.x - c.pos_x, spriteY = sp.y - c.pos_y;
+    const double invDet = 1.0 / (c.plane_x * c.dir_y - c.dir_x * c.plane_y);
+    const double transformX = invDet * (c.dir_y * spriteX - c.dir_x * spriteY);
+    const double transformY = invDet * (-c.plane_y * spriteX + c.plane_x * spriteY);
+    const int64_t tex_w = (int64_t)sp.rx1 - sp.rx0, tex_h = (int64_t)sp.ry1 - sp.ry0;
+    const int64_t spriteScreenX = go_int((double)w / 2.0 * (1.0 + transformX / transformY));
+    const double ratioWH = (double)tex_w / (double)tex_h;
+    const double uDiv = 1.0 / (sp.scale * ratioWH);
+    const double vDiv = 1.0 / sp.scale;
+    const double vMove = -sp.z * (double)h + anchor_offset(sp.anchor, sp.scale, h);
+    const int64_t vMoveScreen = wadd(wadd(go_int(vMove / transformY), c.pitch_px), go_int(c.cam_z_px / transformY));
+    const int64_t spriteHeight = go_int(fabs((double)h / transformY) / vDiv);
+    const int64_t dsy = wadd(wadd(wneg(spriteHeight) / 2, h / 2), vMoveScreen);
+    const int64_t dey = wadd(wadd(spriteHeight / 2, h / 2), vMoveScreen);
+    const int64_t spriteWidth = go_int(fabs((double)h / transformY) / uDiv);
+    const int64_t dsx = wadd(wneg(spriteWidth) / 2, spriteScreenX);
+    const int64_t dex = wadd(spriteWidth / 2, spriteScreenX);
+
+    bool ok = transformY > 0 && spriteWidth > 0 && spriteHeight > 0 && dex > dsx && dey > dsy && tex_w > 0 &&
+              tex_h > 0 && sp.sheet >= 0 && sp.sheet < p.n_sheets;
+    if (c.render_distance >= 0 && !(dist <= c.render_distance)) ok = false;
+    if (ok && (spriteWidth > (1ll << 20) || spriteHeight > (1ll << 20) || tex_w > 4096 || tex_h > 4096)) ok = false;
+
+    if (ok) {
+        rc.x0 = (int32_t)clamp_i64(dsx, -(1 << 30), 1 << 30);
+        rc.y0 = (int32_t)clamp_i64(dsy, -(1 << 30), 1 << 30);
+        rc.x1 = (int32_t)clamp_i64(dex, -(1 << 30), 1 << 30);
+        rc.y1 = (int32_t)clamp_i64(dey, -(1 << 30), 1 << 30);
+    } else {
+        rc.x0 = 0; rc.y0 = 0; rc.x1 = -1; rc.y1 = -1;
+    }
+    // only sprites that can touch a drawable stripe (0 < stripe < w) and row are kept
+    const bool on_screen = ok && dex > 1 && dsx < w && dey > 0 && dsy < h;
+    if (on_screen) {
+        d.dsx = (int32_t)clamp_i64(dsx, -(1 << 30), 1 << 30);
+        d.dex = (int32_t)clamp_i64(dex, -(1 << 30), 1 << 30);
+        d.dsy = (int32_t)clamp_i64(dsy, -(1 << 30), 1 << 30);
+        d.dey = (int32_t)clamp_i64(dey, -(1 << 30), 1 << 30);
+        d.transformY = transformY;
+        const uint64_t ystep = span_step(tex_h, dey - dsy);
+        d.ystep2 = ystep * 2ull;
+        d.ypos0 = (1ull - 2ull * (uint64_t)dsy) * ystep;
+        // m = floor(2^64 / sw) + 1 for sw >= 2 (exact floor(n/sw) for n < 2^32); sw == 1 has no stripes
+        d.xmagic = spriteWidth >= 2 ? (0xFFFFFFFFFFFFFFFFull / (uint64_t)spriteWidth) + 1ull : 0ull;
+        const SheetInfo si = p.sheets[sp.sheet];
+        d.sheet_px = (uint64_t)si.px_offset + (uint64_t)((int64_t)sp.ry0 * si.w + sp.rx0);
+        d.tex_w = (uint32_t)tex_w;
+        d.tex_h = (uint32_t)tex_h;
+        d.sheet_w = (uint32_t)si.w;
+        d.tint = light_tint(c, transformY, 255, sp.illumination, true);
+        // texel ranges inside the sheet: rx0 + tx in [0, si.w), ry0 + ty in [0, si.h)
+        int64_t txl = sp.rx0 < 0 ? -(int64_t)sp.rx0 : 0, txh = (int64_t)si.w - sp.rx0;
+        int64_t tyl = sp.ry0 < 0 ? -(int64_t)sp.ry0 : 0, tyh = (int64_t)si.h - sp.ry0;
+        if (txh > tex_w) txh = tex_w;
+        if (tyh > tex_h) tyh = tex_h;
+        if (txh < txl) txh = txl;
+        if (tyh < tyl) tyh = tyl;
+        d.tx_lo = (uint16_t)txl; d.tx_hi = (uint16_t)txh; d.ty_lo = (uint16_t)tyl; d.ty_hi = (uint16_t)tyh;
+        d.dist = dist;
+        d.src = src;
+        d.flags = sp.focusable ? 1u : 0u;
+        d._pad0 = 0; d._pad1 = 0;
+    }
+    return on_screen;
+}
+
+__device__ __forceinline__ void view_setup(const ViewParams &p, const int view) {
+    const int tid = threadIdx.x;
+    const pm3d_view c = p.views[view];
+
+#ifdef PM3D_FRONT_STATS
+    const long long vt0 = clock64();
+    auto vstamp = [&](int k) { __syncthreads(); if (tid == 0) g_front_stats[k] = (unsigned long long)(clock64() - vt0); };
+#endif
     // ---------------- (b) sprites
     // pm3d_render validates the offsets on the host; pm3d_render_resident cannot (they live in HBM, written by
     // pm3d_raycast_sprites_batch or by the caller), so they are checked here: a view whose entries are negative, not
@@ -103,8 +183,49 @@ __device__ __forceinline__ void view_setup(const ViewParams &p, const int view) 
     __shared__ uint16_t key_i[MAX_VIEW_SPRITES];   // ... and its index in the view's sprite list (0xffff = pad)
     __shared__ int2 xspan[MAX_VIEW_SPRITES];     // dsx, dex of the compacted draw list
     __shared__ int warp_tot[VIEW_THREADS / 32];
-    __shared__ int s_ndraw;
+    __shared__ int s_ndraw, s_nan;
+    int4 *srect = reinterpret_cast<int4 *>(xspan);  // fast path: dsx, dex, dsy, dey of the compacted draw list (<= VIEW_THREADS)
+    const int lane = tid & 31, wid = tid >> 5;
 
+    // ---- fast path, at most one sprite per thread (the game's per-frame lists: a few hundred sprites).  Nothing is
+    // sorted: every thread projects ITS sprite first (the long part: a dozen binary64 divisions, independent of the
+    // order), then finds its place in the paint order by counting the on-screen sprites that paint before it
+    // (farther, or as far with a lower list index) — one pass over the distances in shared memory instead of the
+    // 36 barrier-separated passes of a 256-key bitonic sort.  A NaN distance (not a total order) takes the sort below.
+    bool fast = n <= VIEW_THREADS;
+    if (fast) {
+        if (tid == 0) s_nan = 0;
+        __syncthreads();
+        DrawRec d;
+        bool on = false;
+        double dist = 0.0;
+        if (tid < n) {
+            const pm3d_sprite sp = sprites[tid];
+            dist = sprite_distance(c, sp);
+            pm3d_rect rc;
+            on = project_sprite(p, c, sp, dist, tid, rc, d);
+            p.rects[s0 + tid] = rc;
+            if (dist != dist) s_nan = 1;
+            key_d[tid] = on ? dist : -INFINITY;  // (off-screen sprites paint before nobody)
+        }
+        __syncthreads();
+        fast = s_nan == 0;
+        if (fast) {
+            int pos = 0, tot = 0;
+            for (int j = 0; j < n; j++) {
+                const double dj = key_d[j];
+                tot += dj != -INFINITY;
+                pos += (dj > dist) || (dj == dist && j < tid);
+            }
+            if (on) {
+                draw[pos] = d;
+                srect[pos] = make_int4(d.dsx, d.dex, d.dsy, d.dey);
+            }
+            if (tid == 0) { s_ndraw = tot; p.n_draw[view] = tot; }
+        }
+        __syncthreads();
+    }
+    if (!fast) {
     int npad = 1;
     while (npad < n) npad <<= 1;
 
@@ -131,7 +252,6 @@ __device__ __forceinline__ void view_setup(const ViewParams &p, const int view) 
     }
 
     // ordered compaction of the on-screen sprites: chunk of VIEW_THREADS paint-order entries at a time
-    const int lane = tid & 31, wid = tid >> 5;
     int base_count = 0;
     for (int base = 0; base < n; base += VIEW_THREADS) {
         const int i = base + tid;
@@ -139,74 +259,9 @@ __device__ __forceinline__ void view_setup(const ViewParams &p, const int view) 
         bool on_screen = false;
         if (i < n) {
             const int src = key_i[i];
-            const pm3d_sprite sp = sprites[src];
-            const double spriteX = sp.x - c.pos_x, spriteY = sp.y - c.pos_y;
-            const double invDet = 1.0 / (c.plane_x * c.dir_y - c.dir_x * c.plane_y);
-            const double transformX = invDet * (c.dir_y * spriteX - c.dir_x * spriteY);
-            const double transformY = invDet * (-c.plane_y * spriteX + c.plane_x * spriteY);
-            const int64_t tex_w = (int64_t)sp.rx1 - sp.rx0, tex_h = (int64_t)sp.ry1 - sp.ry0;
-            const int64_t spriteScreenX = go_int((double)w / 2.0 * (1.0 + transformX / transformY));
-            const double ratioWH = (double)tex_w / (double)tex_h;
-            const double uDiv = 1.0 / (sp.scale * ratioWH);
-            const double vDiv = 1.0 / sp.scale;
-            const double vMove = -sp.z * (double)h + anchor_offset(sp.anchor, sp.scale, h);
-            const int64_t vMoveScreen = wadd(wadd(go_int(vMove / transformY), c.pitch_px), go_int(c.cam_z_px / transformY));
-            const int64_t spriteHeight = go_int(fabs((double)h / transformY) / vDiv);
-            const int64_t dsy = wadd(wadd(wneg(spriteHeight) / 2, h / 2), vMoveScreen);
-            const int64_t dey = wadd(wadd(spriteHeight / 2, h / 2), vMoveScreen);
-            const int64_t spriteWidth = go_int(fabs((double)h / transformY) / uDiv);
-            const int64_t dsx = wadd(wneg(spriteWidth) / 2, spriteScreenX);
-            const int64_t dex = wadd(spriteWidth / 2, spriteScreenX);
-            const double dist = key_d[i];
-
-            bool ok = transformY > 0 && spriteWidth > 0 && spriteHeight > 0 && dex > dsx && dey > dsy && tex_w > 0 &&
-                      tex_h > 0 && sp.sheet >= 0 && sp.sheet < p.n_sheets;
-            if (c.render_distance >= 0 && !(dist <= c.render_distance)) ok = false;
-            if (ok && (spriteWidth > (1ll << 20) || spriteHeight > (1ll << 20) || tex_w > 4096 || tex_h > 4096)) ok = false;
-
             pm3d_rect rc;
-            if (ok) {
-                rc.x0 = (int32_t)clamp_i64(dsx, -(1 << 30), 1 << 30);
-                rc.y0 = (int32_t)clamp_i64(dsy, -(1 << 30), 1 << 30);
-                rc.x1 = (int32_t)clamp_i64(dex, -(1 << 30), 1 << 30);
-                rc.y1 = (int32_t)clamp_i64(dey, -(1 << 30), 1 << 30);
-            } else {
-                rc.x0 = 0; rc.y0 = 0; rc.x1 = -1; rc.y1 = -1;
-            }
+            on_screen = project_sprite(p, c, sprites[src], key_d[i], src, rc, d);
             p.rects[s0 + src] = rc;
-
-            // only sprites that can touch a drawable stripe (0 < stripe < w) and row are kept
-            on_screen = ok && dex > 1 && dsx < w && dey > 0 && dsy < h;
-            if (on_screen) {
-                d.dsx = (int32_t)clamp_i64(dsx, -(1 << 30), 1 << 30);
-                d.dex = (int32_t)clamp_i64(dex, -(1 << 30), 1 << 30);
-                d.dsy = (int32_t)clamp_i64(dsy, -(1 << 30), 1 << 30);
-                d.dey = (int32_t)clamp_i64(dey, -(1 << 30), 1 << 30);
-                d.transformY = transformY;
-                const uint64_t ystep = span_step(tex_h, dey - dsy);
-                d.ystep2 = ystep * 2ull;
-                d.ypos0 = (1ull - 2ull * (uint64_t)dsy) * ystep;
-                // m = floor(2^64 / sw) + 1 for sw >= 2 (exact floor(n/sw) for n < 2^32); sw == 1 has no stripes
-                d.xmagic = spriteWidth >= 2 ? (0xFFFFFFFFFFFFFFFFull / (uint64_t)spriteWidth) + 1ull : 0ull;
-                const SheetInfo si = p.sheets[sp.sheet];
-                d.sheet_px = (uint64_t)si.px_offset + (uint64_t)((int64_t)sp.ry0 * si.w + sp.rx0);
-                d.tex_w = (uint32_t)tex_w;
-                d.tex_h = (uint32_t)tex_h;
-                d.sheet_w = (uint32_t)si.w;
-                d.tint = light_tint(c, transformY, 255, sp.illumination, true);
-                // texel ranges inside the sheet: rx0 + tx in [0, si.w), ry0 + ty in [0, si.h)
-                int64_t txl = sp.rx0 < 0 ? -(int64_t)sp.rx0 : 0, txh = (int64_t)si.w - sp.rx0;
-                int64_t tyl = sp.ry0 < 0 ? -(int64_t)sp.ry0 : 0, tyh = (int64_t)si.h - sp.ry0;
-                if (txh > tex_w) txh = tex_w;
-                if (tyh > tex_h) tyh = tex_h;
-                if (txh < txl) txh = txl;
-                if (tyh < tyl) tyh = tyl;
-                d.tx_lo = (uint16_t)txl; d.tx_hi = (uint16_t)txh; d.ty_lo = (uint16_t)tyl; d.ty_hi = (uint16_t)tyh;
-                d.dist = dist;
-                d.src = src;
-                d.flags = sp.focusable ? 1u : 0u;
-                d._pad0 = 0; d._pad1 = 0;
-            }
         }
         // block-wide ordered position of this entry among the on-screen ones
         const unsigned bal = __ballot_sync(0xffffffffu, on_screen);
@@ -227,6 +282,10 @@ __device__ __forceinline__ void view_setup(const ViewParams &p, const int view) 
     if (tid == 0) { s_ndraw = base_count; p.n_draw[view] = base_count; }
 
     __syncthreads();
+    }
+#ifdef PM3D_FRONT_STATS
+    vstamp(6);  // projection + ordering done
+#endif
 
     // ---------------- (c) column-group lists, paint order preserved: one warp per group
     const int m = s_ndraw;
@@ -239,11 +298,15 @@ __device__ __forceinline__ void view_setup(const ViewParams &p, const int view) 
         for (int base = 0; base < m; base += 32) {
             const int i = base + lane;
             bool keep = false;
-            if (i < m) { const int2 xs = xspan[i]; keep = xs.y > gx0 && xs.x < gx1; }
+            int4 rc = make_int4(0, 0, 0, 0);
+            if (i < m) {
+                if (fast) { rc = srect[i]; keep = rc.y > gx0 && rc.x < gx1; }
+                else { const int2 xs = xspan[i]; keep = xs.y > gx0 && xs.x < gx1; }
+            }
             const unsigned bal = __ballot_sync(0xffffffffu, keep);
             if (keep) {
                 const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
-                const int4 rc = *reinterpret_cast<const int4 *>(&draw[i]);  // dsx, dex, dsy, dey
+                if (!fast) rc = *reinterpret_cast<const int4 *>(&draw[i]);  // dsx, dex, dsy, dey
                 list[pos] = (uint16_t)i;
                 rects[pos] = rc;
                 ymin = min(ymin, rc.z);

@@ -27,7 +27,7 @@ def run(cfg, w, h, label, sprites=True):
         ctx.sync(); stats(1)
         ctx.render_resident(dv + r * 104, 1, ds + int(off[r]) * 64, do, ns, dout)
         ctx.sync(); st = stats(1)
-        print(f"{label} pose {r}: jump rays {st[1]}, fallbacks {st[0]}, slowest cast CTA-thread {st[2]} cycles, view CTA {st[3]} cycles")
+        print(f"{label} pose {r}: jump rays {st[1]}, fallbacks {st[0]}, slowest cast CTA-thread {st[2]} cycles, view CTA {st[3]} cycles (after its row table: sort done {st[5]}, projection done {st[6]})")
     for p in (dv, ds, do, dout): ctx.device_free(p)
 c2 = W.config_c2(n_poses=8)
 run(c2, 1920, 1080, "c2")

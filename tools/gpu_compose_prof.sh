@@ -1,8 +1,6 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
 mkdir -p gpurun_out
-OVERLAP=0 python tools/prof_batch.py 4096 3 || exit 1
-OVERLAP=0 ncu --set full --clock-control none --import-source on -k regex:k_compose -s 2 -c 1 -o gpurun_out/compose_c4 -f python tools/prof_batch.py 4096 3 > gpurun_out/compose_c4.log 2>&1
-tail -2 gpurun_out/compose_c4.log
-OVERLAP=0 ncu --set full --clock-control none --import-source on -k regex:k_compose -s 20 -c 2 -o gpurun_out/compose_c2 -f python tools/prof_c2.py > gpurun_out/compose_c2.log 2>&1
+OVERLAP=0 python tools/prof_c2.py || exit 1
+OVERLAP=0 ncu --set full --clock-control none --import-source on -k regex:k_compose -s 20 -c 8 -o gpurun_out/compose_c2 -f python tools/prof_c2.py > gpurun_out/compose_c2.log 2>&1
 tail -2 gpurun_out/compose_c2.log

@@ -666,7 +666,7 @@ def _columns_and_frames(ctx, c, offsets):
     return got, cols
 
 
-@pytest.mark.parametrize("which", ["c2", "c3", "edge"])
+@pytest.mark.parametrize("which", ["c2", "c3", "edge", "graze"])
 def test_jump_and_sequential_cast_agree(gpu_ctx, which):
     """PM3D_OPT_DDA_JUMP = 0 walks every ray with the sequential loop; the default jump mode must give the same
     column records (hit cell, side, distances bit for bit), z-buffer and pixels."""
@@ -674,6 +674,24 @@ def test_jump_and_sequential_cast_agree(gpu_ctx, which):
         c = W.config_c2(w=640, h=360, n_poses=6)
     elif which == "c3":
         c = W.config_c3(levels=8, w=480, h=270, pitch=0.2, map_size=128)
+    elif which == "graze":
+        # rays running along walls for hundreds of cells (the long jumps over wall-free bounding boxes): the boundary
+        # ring, a long interior wall, a diagonal staircase, corridors one cell wide
+        grid = np.zeros((2, 300, 260), dtype=np.uint16)
+        grid[0, 0, :] = grid[0, -1, :] = W.BOUNDARY_TEX
+        grid[0, :, 0] = grid[0, :, -1] = W.BOUNDARY_TEX
+        grid[0, 40:260, 100] = 1
+        grid[:, 20:280, 180] = 2
+        grid[0, 20:280, 182] = 3
+        for k in range(60):
+            grid[0, 100 + k, 20 + k] = 4
+        scene = W.scene_from_grid(grid, 3)
+        poses = [(1.5, 1.5, 0.5, 0.001, 0.0), (1.2, 258.7, 0.5, -0.002, 0.0), (298.5, 1.5, 0.5, math.pi / 2 + 0.003, 0.0),
+                 (30.5, 100.9, 0.5, 0.0005, 0.0), (41.0, 99.5, 0.5, 0.01, 0.0), (21.5, 181.5, 0.5, 0.0, 0.0),
+                 (279.5, 181.5, 0.5, math.pi, 0.0), (98.5, 17.5, 0.5, math.pi / 4, 0.0), (99.5, 21.5, 0.5, math.pi / 4 + 0.004, 0.0),
+                 (150.0, 130.0, 0.5, 2.0, 0.0)]
+        c = dict(scene=scene, w=320, h=120, sprites=np.zeros(0, O.SPRITE_DTYPE),
+                 views=W.make_views(scene, 320, 120, poses, fov_deg=70.0, render_distance=-1.0))
     else:
         scene = edge_scene()
         c = dict(scene=scene, w=200, h=120, sprites=np.zeros(0, O.SPRITE_DTYPE),

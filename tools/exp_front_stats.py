@@ -10,7 +10,7 @@ ctx.set_option(pm3d._lib.OPT_OVERLAP, 0)
 lib = C.CDLL(os.path.join(ROOT, "pixelmek-3d_b200", "libpm3d.so"))
 lib.pm3d_debug_front_stats.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]
 def stats(reset=1):
-    out = (C.c_ulonglong * 8)()
+    out = (C.c_ulonglong * 12)()
     lib.pm3d_debug_front_stats(ctx.h, out, reset)
     return list(out)
 def run(cfg, w, h, label, sprites=True):
@@ -27,7 +27,7 @@ def run(cfg, w, h, label, sprites=True):
         ctx.sync(); stats(1)
         ctx.render_resident(dv + r * 104, 1, ds + int(off[r]) * 64, do, ns, dout)
         ctx.sync(); st = stats(1)
-        print(f"{label} pose {r}: jump rays {st[1]}, fallbacks {st[0]}, slowest cast CTA-thread {st[2]} cycles, view CTA {st[3]} cycles (after its row table: sort done {st[5]}, projection done {st[6]})")
+        print(f"{label} pose {r}: jump rays {st[1]}, fallbacks {st[0]}, slowest cast CTA-thread {st[2]} cycles, view CTA {st[3]} cycles; jump iterations max {st[4]} mean {st[7]/max(st[1],1):.1f}, long-jump tries {st[5]/max(st[1],1):.1f} per ray; slowest loop {st[6]} cycles; per iteration: jump {st[9]/max(st[7],1):.0f} probe {st[10]/max(st[7],1):.0f} cycles")
     for p in (dv, ds, do, dout): ctx.device_free(p)
 c2 = W.config_c2(n_poses=8)
 run(c2, 1920, 1080, "c2")

@@ -89,3 +89,75 @@ def test_cpp_mirror_frame_matches_oracle(gpu_ctx, tmp_path):
     assert f"convergence sprite {want}" in r.stdout
     rc = ref["rects"][0]
     assert f"[{rc[0]} {rc[1]} {rc[2]} {rc[3]}]" in r.stdout
+
+
+# ---- the C++ mirror of Game.lineOfSight / Game.getValidMove(checkAlternate=true) (host/game_collision.hpp)
+COL_DEMO = os.path.join(HOST, "collision_demo")
+
+
+def build_collision_demo():
+    src = [os.path.join(HOST, "collision_demo.cpp"), os.path.join(HOST, "game_collision.hpp")]
+    if not os.path.exists(COL_DEMO) or any(os.path.getmtime(s) > os.path.getmtime(COL_DEMO) for s in src):
+        subprocess.check_call([
+            "g++", "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"), "-o", COL_DEMO, src[0],
+            "-L" + os.path.join(ROOT, "pixelmek-3d_b200"), "-lpm3d", "-Wl,-rpath,$ORIGIN/.."])
+    return COL_DEMO
+
+
+def test_cpp_collision_mirror_builds(ensure_built):
+    demo = build_collision_demo()
+    if pm3d.load().pm3d_device_count() > 0:
+        pytest.skip("a GPU is present")
+    r = subprocess.run([demo, "missing.bin", "out.bin"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_get_valid_move_with_check_alternate_matches_oracle(gpu_ctx, tmp_path):
+    """pm3d::Game::getValidMove(entity, x, y, z, true) — the checkAlternate recursion of game/collision.go:204-306 in
+    C++ over pm3d_valid_move_batch — against the oracle's recursion, and lineOfSight through the same class."""
+    from pm3d import workloads as Wk
+    from test_move_gpu import random_colliders, random_movers
+
+    demo = build_collision_demo()
+    g = Wk.load_golden("debug_land")
+    lvl = np.ascontiguousarray(g["levels"][:1])
+    scene = Wk.scene_from_grid(lvl, 1)
+    segs = np.ascontiguousarray(g["segments"], dtype=np.float64)
+    rng = np.random.default_rng(17)
+    c = random_colliders(rng, lvl[0], 90).astype(pm3d._lib.COLLIDER_DTYPE)
+    m = random_movers(rng, lvl[0], c, 1200, 2.5).astype(pm3d._lib.MOVER_DTYPE)
+    m["radius"] = np.maximum(m["radius"], 0.05)
+    m["height"] = np.maximum(m["height"], 0.05)
+    m["self"] = -1; m["parent"] = -1; m["destroyed"] = 0
+    hv = np.stack([rng.random(len(m)) * 2 * math.pi - math.pi, rng.random(len(m)) * 0.2], axis=1)
+    scen = str(tmp_path / "scenario.bin")
+    with open(scen, "wb") as f:
+        np.array([lvl.shape[1], lvl.shape[2], len(segs), len(c), len(m)], dtype=np.int32).tofile(f)
+        np.ascontiguousarray(lvl[0], dtype=np.uint16).tofile(f)
+        segs.tofile(f)
+        c.tofile(f)
+        for k in range(len(m)):
+            m[k:k + 1].tofile(f)
+            hv[k].tofile(f)
+    out = str(tmp_path / "results.bin")
+    r = subprocess.run([demo, scen, out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rec_dt = np.dtype([("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("collided", "<i4"), ("n", "<i4"), ("first", "<i4"), ("_pad", "<i4"),
+                       ("fx", "<f8"), ("fy", "<f8"), ("fz", "<f8")])
+    raw = np.fromfile(out, dtype=np.uint8)
+    got = raw[:len(m) * rec_dt.itemsize].view(rec_dt)
+    los = raw[len(m) * rec_dt.itemsize:]
+    osc = O.Scene(scene)
+    n_alt = 0
+    for k in range(len(m)):
+        want = O.valid_move_alternate(osc, segs, c.astype(O.COLLIDER_DTYPE), 0, Wk.CLIP_DISTANCE, m[k:k + 1].astype(O.MOVER_DTYPE),
+                                      float(hv[k, 0]), float(hv[k, 1]), True)
+        assert (got[k]["x"], got[k]["y"], got[k]["z"], got[k]["collided"]) == (want["x"], want["y"], want["z"], int(want["collided"])), k
+        assert got[k]["n"] == (1 if want["n_collisions"] > 0 else 0)
+        if got[k]["n"]:
+            assert (got[k]["first"], got[k]["fx"], got[k]["fy"], got[k]["fz"]) == (want["first_entity"], want["first_x"], want["first_y"], want["first_z"])
+        n_alt += int(want["n_points"] > 0)
+    assert n_alt > 20
+    rays = np.stack([m["pos_x"], m["pos_y"], c["x"][np.arange(len(m)) % len(c)], c["y"][np.arange(len(m)) % len(c)]], axis=1)
+    assert np.array_equal(los, O.los_batch(segs, rays, threads=4))

@@ -243,3 +243,31 @@ def test_move_walls_known_answers():
     assert pos.tolist() == [[3.5, 3.5], [2.5, 3.5], [2.5, 3.5]]
     assert col.tolist() == [0, 1, 0]
     assert hits[1] >= 1
+
+
+def test_go_golden_c1():
+    """The oracle against the REAL Go raycaster at C1 — hit cells and wall sides of every column and level, sprite
+    rectangles and the convergence record as dumped by baseline/go_harness (TextureAt / SetScreenRect recorders around
+    raycaster-go's Camera.Update).  Skipped until tests/golden/go_c1.npz exists: no Go toolchain in this image."""
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "go_c1.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/go_c1.npz absent (baseline/go_harness needs a Go toolchain): parity stays unpinned")
+    z = np.load(path)
+    c1 = W.config_c1()
+    sc = O.Scene(c1["scene"])
+    cam = orc_camera(c1["views"][0], int(z["w"]), int(z["h"]))
+    n_static = len(z["sprite_rects"])
+    res = O.render(sc, cam, c1["sprites"][:n_static].astype(O.SPRITE_DTYPE), threads=4)
+    cols = res["columns"]
+    tex = z["texture_at"]
+    for lv in range(int(z["levels"])):
+        calls = tex[tex[:, 2] == lv]
+        hit = cols["tile"][lv] >= 0   # the library asks for a texture where a wall was hit inside the map
+        assert len(calls) >= int(hit.sum())
+        got = np.stack([cols["map_x"][lv][hit], cols["map_y"][lv][hit], cols["side"][lv][hit]], axis=1)
+        assert np.array_equal(calls[:len(got), [0, 1, 3]], got), f"level {lv}: hit cells / sides differ from the Go run"
+    assert np.array_equal(res["rects"], z["sprite_rects"])
+    assert res["convergence"]["distance"] == float(z["convergence"][0])
+    assert res["convergence"]["sprite"] == int(z["convergence_sprite"])

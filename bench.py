@@ -661,29 +661,48 @@ def run_ours(args, rank, world, local_rank):
     #      frame i+1 beside compose of frame i), then PM3D_OPT_LANES = LANES, where the library deals the independent
     #      frames of the ring round-robin to LANES lanes (own streams + intermediate buffers) so that several frames
     #      are in flight; `value` is the latter, the former is reported as `single_lane`.
-    def timed_resident(lanes):
+    def timed_resident(lanes, use_graph=False):
+        """K frames of the ring.  use_graph: the RING frames are recorded once (pm3d_frames_capture_*: one CUDA graph
+        over all lanes and streams) and replayed, one launch per RING frames, the K % RING frames left over are plain
+        calls; else every frame is enqueued with its own calls (the headline: the driver's short runs have K < RING)."""
         ctx.set_option(pm3d._lib.OPT_LANES, lanes)
-        for i in range(max(args.warmup, 3)):
-            frame(i)
+        graph = None
+        if use_graph:
+            ctx.frames_capture_begin()
+            for i in range(RING):
+                frame(i)
+            graph = ctx.frames_capture_end()
+
+        def run(n):
+            full, rest = (n // RING, n % RING) if graph is not None else (0, n)
+            for _ in range(full):
+                ctx.frames_replay(graph)
+            for i in range(rest):
+                frame(i)
+
+        run(max(args.warmup, 3, RING))
         ctx.sync()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         l0 = ctx.launches
         ctx.timer_start(0)
-        for i in range(args.steps):
-            frame(i)
+        run(args.steps)
         ctx.timer_stop(0)
         ms = ctx.timer_ms(0)
         ctx.sync()
         torch.cuda.synchronize()
-        return ms, ctx.launches - l0
+        launches = ctx.launches - l0
+        if graph is not None:
+            ctx.frames_graph_destroy(graph)
+        return ms, launches
 
     single_ms, _ = timed_resident(1)
     sampler = ClockSampler(local_rank)
     sampler.start()
     elapsed_ms, launches = timed_resident(LANES)
     sampler.stop()
+    graph_ms = timed_resident(LANES, use_graph=True)[0] if args.steps >= RING else None
     ctx.set_option(pm3d._lib.OPT_LANES, 1)
     # per-kernel durations: the same frames again with an event pair around each kernel (the event
     # records cost ~1 us each, so they are kept out of the region `value` is computed from)
@@ -756,6 +775,14 @@ def run_ours(args, rank, world, local_rank):
 
     line = base_line(args, world, value, elapsed_ms / args.steps)
     line["lanes"] = LANES
+    if graph_ms is not None:
+        tg = torch.tensor([graph_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        line["graph_replay"] = {"value": world * args.steps / (float(tg.item()) * 1e-3), "unit": "frames/s",
+                                "note": f"same frames, the ring recorded once into one CUDA graph (pm3d_frames_capture_begin/_end) and replayed: one launch per {RING} "
+                                        "frames instead of ~8 runtime calls per frame; a replay is one item of the ctx stream, so the ring's last frames "
+                                        "drain before the next replay starts (a bubble per ring) - it pays when the HOST is the limit (many ranks per box), not on one GPU"}
     line["parallelism"] = (f"{world} independent ring(s) of {RING} camera poses, one per GPU; no data-path collective; frames are "
                                      f"enqueued back to back and dealt round-robin to {LANES} lanes of one ctx (PM3D_OPT_LANES: own streams "
                                      "and intermediate buffers per lane, so the cast/setup and compose launches of several frames overlap)")

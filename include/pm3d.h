@@ -198,6 +198,19 @@ int pm3d_render(pm3d_ctx *ctx, const pm3d_view *views, int n_views, const pm3d_s
  * and the next pm3d_sync / pm3d_download_results returns PM3D_ERR_CAPACITY naming the view. */
 int pm3d_render_resident(pm3d_ctx *ctx, const pm3d_view *d_views, int n_views, const pm3d_sprite *d_sprites,
                          const int32_t *d_sprite_offset, int n_sprites_total, uint8_t *d_out_rgba);
+/* ---- recorded frame sequences.  A headless server that renders the SAME sequence of resident frames again and again
+ * (a ring of unit cameras whose poses it rewrites in place in device memory, a replay) pays ~8 runtime calls per
+ * frame to enqueue it.  Between pm3d_frames_capture_begin and pm3d_frames_capture_end the pm3d_render_resident calls
+ * (and nothing else) are not executed but captured — from every stream and lane the frames would run on — into one
+ * CUDA graph; pm3d_frames_replay enqueues all of them again with ONE launch on the ctx stream: same device pointers,
+ * whatever they hold at that time, same kernels, same dependencies.  Ordering: a replay follows everything enqueued
+ * on the ctx before it and precedes everything after it, like any other call.  PM3D_OPT_LANES / PM3D_OPT_OVERLAP /
+ * pm3d_set_view must not change between capture and replay (the graph holds the buffers of that configuration). */
+int pm3d_frames_capture_begin(pm3d_ctx *ctx);
+int pm3d_frames_capture_end(pm3d_ctx *ctx, int *out_graph);
+int pm3d_frames_replay(pm3d_ctx *ctx, int graph);
+int pm3d_frames_graph_destroy(pm3d_ctx *ctx, int graph);
+
 /* rects (n_sprites of the last render) and convergence (n_views) of the last render; either may be NULL */
 int pm3d_download_results(pm3d_ctx *ctx, pm3d_rect *out_rects, pm3d_convergence *out_conv);
 /* wall-cast records + z-buffer of one view of the last pm3d_render (parity/debug).

@@ -23,8 +23,22 @@ int pm3d_fail(pm3d_ctx *ctx, int code, const char *fmt, ...) {
     return code;
 }
 
+// a recorded frame sequence holds the device pointers of the configuration it was captured under: any reallocation
+// of mission data or frame buffers retires the recordings (pm3d_frames_replay then fails with PM3D_ERR_ARG)
+static int retire_frame_graphs(pm3d_ctx *ctx) {
+    if (ctx->capturing) return pm3d_fail(ctx, PM3D_ERR_ARG, "uploads and reconfiguration are not allowed inside a frame capture");
+    bool any = false;
+    for (auto &fg : ctx->graphs) any = any || fg.exec;
+    if (!any) return PM3D_OK;
+    PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &fg : ctx->graphs)
+        if (fg.exec) { cudaGraphExecDestroy(fg.exec); fg.exec = nullptr; }
+    return PM3D_OK;
+}
+
 template <typename T>
 static int dev_realloc(pm3d_ctx *ctx, T **ptr, size_t count) {
+    { int rc_ = retire_frame_graphs(ctx); if (rc_) return rc_; }
     if (*ptr) { PM3D_CUDA(ctx, cudaFree(*ptr)); *ptr = nullptr; }
     if (count == 0) count = 1;
     PM3D_CUDA(ctx, cudaMalloc((void **)ptr, count * sizeof(T)));
@@ -72,6 +86,7 @@ int pm3d_wait_last_frame(pm3d_ctx *ctx) { return pm3d_main_enter(ctx); }  // a s
 
 // frame -> main: non-frame work enqueued on the main stream follows every frame dealt to another lane
 int pm3d_main_enter(pm3d_ctx *ctx) {
+    if (ctx->capturing) return pm3d_fail(ctx, PM3D_ERR_ARG, "only pm3d_render_resident may be called between pm3d_frames_capture_begin and pm3d_frames_capture_end");
     if (!ctx->lanes_dirty) return PM3D_OK;
     for (int l = 1; l < PM3D_MAX_LANES; l++) {
         if (!ctx->lane_cstream[l]) continue;
@@ -160,6 +175,11 @@ void pm3d_destroy(pm3d_ctx *ctx) {
     sync_frame_streams(ctx);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     pm3d_comm_destroy(ctx);
+    for (auto &fg : ctx->graphs)
+        if (fg.exec) cudaGraphExecDestroy(fg.exec);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (cudaEvent_t e : ctx->ev_join)
+        if (e) cudaEventDestroy(e);
     void *ptrs[] = {ctx->grid, ctx->dist, ctx->qdist, ctx->wall_lut, ctx->atlas, ctx->floor_tiles, ctx->sheet_pixels, ctx->sheet_info,
                     ctx->views, ctx->sprites, ctx->sprite_offset, ctx->frame, ctx->checksums, ctx->segs, ctx->seg_irect,
                     ctx->cell_start, ctx->cell_items, ctx->cell_rec, ctx->cell_code, ctx->los_list, ctx->los_count, ctx->path_scratch, ctx->colliders, ctx->cb_start, ctx->cb_items, ctx->cb_loose, ctx->present_map, ctx->present_buf, ctx->sparse_cells, ctx->sparse_count, ctx->clutter_class, ctx->clutter_tab, ctx->io_a, ctx->io_b, ctx->io_c, ctx->flush_buf};
@@ -204,6 +224,7 @@ void pm3d_destroy(pm3d_ctx *ctx) {
 
 int pm3d_sync(pm3d_ctx *ctx) {
     if (!ctx) return PM3D_ERR_ARG;
+    if (ctx->capturing) return pm3d_fail(ctx, PM3D_ERR_ARG, "pm3d_sync inside a frame capture");
     PM3D_CUDA(ctx, sync_frame_streams(ctx));
     if (ctx->copy_stream) PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     small_flush_all(ctx);
@@ -571,6 +592,7 @@ static int render_core(pm3d_ctx *ctx, int n_views, int n_sprites, uint8_t *targe
     }
     if ((rc = pm3d_launch_compose(ctx, n_views, target))) return rc;
     if (overlap) PM3D_CUDA(ctx, cudaEventRecord(fs.ev_compose, cstream));
+    if (ctx->capturing) ctx->set_in_capture[ctx->cur_set] = true;
     ctx->last_cstream = cstream;
     if (ctx->kt_on && ctx->kt_n < ctx->kt_cap) ctx->kt_n++;
     ctx->last_frame = target;
@@ -597,7 +619,8 @@ static int pm3d_begin_frame(pm3d_ctx *ctx, int n_views, cudaStream_t *fstream, i
             ctx->cur_fstream = ctx->lane_fstream[lane];
             ctx->cur_cstream = ctx->lane_cstream[lane];
         }
-        PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->cur_fstream, ctx->sets[ctx->cur_set].ev_compose, 0));
+        if (!ctx->capturing || ctx->set_in_capture[ctx->cur_set])
+            PM3D_CUDA(ctx, cudaStreamWaitEvent(ctx->cur_fstream, ctx->sets[ctx->cur_set].ev_compose, 0));
         uint64_t *seen = lane ? &ctx->seen_lane[lane] : (ctx->cur_fstream == ctx->front_stream ? &ctx->seen_front : &ctx->seen_front_lo);
         int rc = order_after_main(ctx, ctx->cur_fstream, seen);
         if (rc) return rc;
@@ -642,6 +665,111 @@ int pm3d_render_resident(pm3d_ctx *ctx, const pm3d_view *d_views, int n_views, c
     if ((rc = pm3d_begin_frame(ctx, n_views, &fstream, lane))) return rc;
     ctx->cur_views = d_views; ctx->cur_sprites = d_sprites; ctx->cur_offset = d_sprite_offset;
     return render_core(ctx, n_views, n_sprites_total, d_out_rgba);
+}
+
+// ---- recorded frame sequences
+static void capture_streams(pm3d_ctx *ctx, std::vector<cudaStream_t> &aux) {
+    if (ctx->n_sets <= 1) return;  // PM3D_OPT_OVERLAP = 0: everything runs on the ctx stream
+    aux.push_back(ctx->front_stream);
+    aux.push_back(ctx->front_stream_lo);
+    for (int l = 1; l < ctx->n_lanes; l++) { aux.push_back(ctx->lane_fstream[l]); aux.push_back(ctx->lane_cstream[l]); }
+}
+
+int pm3d_frames_capture_begin(pm3d_ctx *ctx) {
+    if (!ctx) return PM3D_ERR_ARG;
+    if (ctx->capturing) return pm3d_fail(ctx, PM3D_ERR_ARG, "a frame capture is already open");
+    if (!ctx->own_stream) return pm3d_fail(ctx, PM3D_ERR_ARG, "a ctx on a caller stream cannot record frame sequences");
+    if (ctx->w < 1) return pm3d_fail(ctx, PM3D_ERR_ARG, "pm3d_set_view must be called first");
+    if (ctx->kt_on) return pm3d_fail(ctx, PM3D_ERR_ARG, "per-kernel timing (pm3d_ktimer_begin) is on");
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    PM3D_CUDA(ctx, sync_frame_streams(ctx));  // nothing of the capture may depend on work enqueued before it
+    int rc = pm3d_check_status(ctx);
+    if (rc) return rc;
+    if (!ctx->ev_fork) {
+        PM3D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        for (cudaEvent_t &e : ctx->ev_join) PM3D_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    ctx->lanes_dirty = false;
+    ctx->seen_front = ctx->seen_front_lo = ctx->main_seq;
+    for (uint64_t &s : ctx->seen_lane) s = ctx->main_seq;
+    for (bool &b : ctx->set_in_capture) b = false;
+    PM3D_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    // fork: every stream a frame may run on joins the capture
+    std::vector<cudaStream_t> aux;
+    capture_streams(ctx, aux);
+    cudaError_t e = cudaEventRecord(ctx->ev_fork, ctx->stream);
+    for (cudaStream_t s : aux)
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, ctx->ev_fork, 0);
+    if (e != cudaSuccess) {
+        cudaGraph_t g = nullptr;
+        cudaStreamEndCapture(ctx->stream, &g);
+        if (g) cudaGraphDestroy(g);
+        return pm3d_fail(ctx, PM3D_ERR_CUDA, "frame capture: %s", cudaGetErrorString(e));
+    }
+    ctx->capturing = true;
+    ctx->capture_launches0 = ctx->launches;
+    return PM3D_OK;
+}
+
+int pm3d_frames_capture_end(pm3d_ctx *ctx, int *out_graph) {
+    if (!ctx || !out_graph) return PM3D_ERR_ARG;
+    if (!ctx->capturing) return pm3d_fail(ctx, PM3D_ERR_ARG, "no frame capture is open");
+    ctx->capturing = false;
+    std::vector<cudaStream_t> aux;
+    capture_streams(ctx, aux);
+    cudaError_t e = cudaSuccess;
+    for (size_t k = 0; k < aux.size() && e == cudaSuccess; k++) {  // join: the graph ends when every stream's work has
+        e = cudaEventRecord(ctx->ev_join[k], aux[k]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0);
+    }
+    cudaGraph_t graph = nullptr;
+    cudaError_t e2 = cudaStreamEndCapture(ctx->stream, &graph);
+    if (e == cudaSuccess) e = e2;
+    pm3d_ctx::FrameGraph fg;
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&fg.exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    ctx->lanes_dirty = false;
+    pm3d_main_touch(ctx);
+    // an event last recorded inside a capture cannot be waited for outside of it: give the frame sets' events a real
+    // (immediately complete) record again
+    for (int k = 0; k < 2 * PM3D_MAX_LANES; k++)
+        if (ctx->set_in_capture[k] && ctx->sets[k].ev_compose) {
+            cudaEventRecord(ctx->sets[k].ev_compose, ctx->stream);
+            cudaEventRecord(ctx->sets[k].ev_front, ctx->stream);
+            ctx->set_in_capture[k] = false;
+        }
+    if (e != cudaSuccess) return pm3d_fail(ctx, PM3D_ERR_CUDA, "frame capture: %s", cudaGetErrorString(e));
+    fg.launches = ctx->launches - ctx->capture_launches0;
+    fg.last_frame = ctx->last_frame; fg.last_views = ctx->last_views; fg.last_sprites = ctx->last_sprites;
+    ctx->launches = ctx->capture_launches0;  // nothing ran yet
+    ctx->graphs.push_back(fg);
+    *out_graph = (int)ctx->graphs.size() - 1;
+    return PM3D_OK;
+}
+
+int pm3d_frames_replay(pm3d_ctx *ctx, int graph) {
+    if (!ctx) return PM3D_ERR_ARG;
+    if (graph < 0 || graph >= (int)ctx->graphs.size() || !ctx->graphs[graph].exec) return pm3d_fail(ctx, PM3D_ERR_ARG, "no such recorded frame sequence");
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = pm3d_main_enter(ctx);  // after the frames dealt to the lanes so far
+    if (rc) return rc;
+    const pm3d_ctx::FrameGraph &fg = ctx->graphs[graph];
+    PM3D_CUDA(ctx, cudaGraphLaunch(fg.exec, ctx->stream));
+    ctx->launches += fg.launches;
+    ctx->last_cstream = ctx->stream;
+    ctx->last_frame = fg.last_frame; ctx->last_views = fg.last_views; ctx->last_sprites = fg.last_sprites;
+    pm3d_main_touch(ctx);  // the next frame call waits for the ctx stream, i.e. for the replayed frames
+    return PM3D_OK;
+}
+
+int pm3d_frames_graph_destroy(pm3d_ctx *ctx, int graph) {
+    if (!ctx) return PM3D_ERR_ARG;
+    if (graph < 0 || graph >= (int)ctx->graphs.size()) return pm3d_fail(ctx, PM3D_ERR_ARG, "no such recorded frame sequence");
+    PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    PM3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->graphs[graph].exec) PM3D_CUDA(ctx, cudaGraphExecDestroy(ctx->graphs[graph].exec));
+    ctx->graphs[graph].exec = nullptr;
+    return PM3D_OK;
 }
 
 int pm3d_download_results(pm3d_ctx *ctx, pm3d_rect *out_rects, pm3d_convergence *out_conv) {

@@ -181,6 +181,16 @@ struct pm3d_ctx {
     uint64_t main_seq = 1;
     uint64_t seen_front = 0, seen_front_lo = 0, seen_lane[PM3D_MAX_LANES] = {};
     bool lanes_dirty = false;
+    // ---- recorded frame sequences (pm3d_frames_capture_begin / _end / pm3d_frames_replay): the enqueue-only frame
+    // calls between begin and end are captured from all the frame streams into ONE CUDA graph; a replay is a single
+    // launch on the ctx stream instead of ~8 runtime calls per frame.  While capturing, a frame set only waits for
+    // its previous user when that user is part of the capture (an event recorded before it is not capturable).
+    bool capturing = false;
+    bool set_in_capture[2 * PM3D_MAX_LANES] = {};
+    int64_t capture_launches0 = 0;
+    cudaEvent_t ev_fork = nullptr, ev_join[2 + 2 * PM3D_MAX_LANES] = {};
+    struct FrameGraph { cudaGraphExec_t exec = nullptr; int64_t launches = 0; uint8_t *last_frame = nullptr; int last_views = 0, last_sprites = 0; };
+    std::vector<FrameGraph> graphs;
     // device -> host error words in mapped pinned memory (kernels store, pm3d_sync reads after the streams drained):
     //   [0] 1 + index of a view whose sprite_offset entries are out of range (resident path: offsets live in HBM)
     //   [1] 1 when pm3d_raycast_sprites_batch listed more than max_total sprites (PM3D_NO_SYNC path)

@@ -177,6 +177,10 @@ SYMBOLS = {
     "pm3d_group_sync": (C.c_int, [_P]),
     "pm3d_group_render_views": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P]),
     "pm3d_group_los_batch": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "pm3d_frames_capture_begin": (C.c_int, [_P]),
+    "pm3d_frames_capture_end": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "pm3d_frames_replay": (C.c_int, [_P, C.c_int]),
+    "pm3d_frames_graph_destroy": (C.c_int, [_P, C.c_int]),
     "pm3d_find_path_batch": (C.c_int, [_P, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32]),
     "pm3d_selfcheck_dda": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pm3d_selfcheck_floor": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

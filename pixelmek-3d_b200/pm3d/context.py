@@ -207,6 +207,21 @@ class Context:
         self._check(self.lib.pm3d_los_batch(self.h, ptr(rays), len(rays), ptr(out), 0), "pm3d_los_batch")
         return out
 
+    # ------------------------------------------------------------------ recorded frame sequences (one CUDA graph)
+    def frames_capture_begin(self):
+        self._check(self.lib.pm3d_frames_capture_begin(self.h), "pm3d_frames_capture_begin")
+
+    def frames_capture_end(self) -> int:
+        g = C.c_int(-1)
+        self._check(self.lib.pm3d_frames_capture_end(self.h, C.byref(g)), "pm3d_frames_capture_end")
+        return int(g.value)
+
+    def frames_replay(self, graph: int):
+        self._check(self.lib.pm3d_frames_replay(self.h, int(graph)), "pm3d_frames_replay")
+
+    def frames_graph_destroy(self, graph: int):
+        self._check(self.lib.pm3d_frames_graph_destroy(self.h, int(graph)), "pm3d_frames_graph_destroy")
+
     def find_path_batch(self, queries: np.ndarray, max_points: int = 4096):
         """Pathing.FindPath for a batch of (start x, y, finish x, y) queries over level 0 of the uploaded grid:
         (points [n][max_points][2], count [n]; -1 = no path)."""

@@ -253,3 +253,66 @@ def test_unsynced_list_overflow_is_reported(gpu_ctx):
     finally:
         for p in (d_w, d_q, d_s, d_o):
             ctx.device_free(p)
+
+
+# ---- recorded frame sequences (pm3d_frames_capture_begin / _end / pm3d_frames_replay)
+@pytest.mark.parametrize("lanes,overlap", [(1, 1), (4, 1), (1, 0)])
+def test_recorded_frame_sequence_replays_the_same_frames(gpu_ctx, lanes, overlap):
+    """A ring of resident frames captured into one CUDA graph: every replay writes the frames the plain calls write
+    (checksums per output slot), also after the poses were rewritten in place between two replays; other entry points
+    are refused inside the capture; a reconfiguration retires the recording."""
+    import ctypes as C
+
+    cfg = W.config_c2(320, 180, 40, n_poses=6)
+    w, h, ring = 320, 180, 6
+    ctx = gpu_ctx
+    ctx.upload_scene(cfg["scene"])
+    ctx.set_option(pm3d._lib.OPT_OVERLAP, overlap)
+    ctx.set_option(pm3d._lib.OPT_LANES, lanes)
+    ctx.set_view(w, h, 1, 40)
+    views, spr, off = cfg["views"], cfg["sprites"], cfg["offsets"]
+    fb = w * h * 4
+    dv, ds, do, dout = ctx.device_alloc(views.nbytes), ctx.device_alloc(spr.nbytes), ctx.device_alloc(8), ctx.device_alloc(ring * fb)
+    ctx.h2d(dv, views); ctx.h2d(ds, spr); ctx.h2d(do, np.array([0, 40], np.int32))
+
+    def frame(r):
+        ctx.render_resident(dv + r * views.itemsize, 1, ds + int(off[r]) * spr.itemsize, do, 40, dout + r * fb)
+
+    def ring_bytes():
+        ctx.sync()
+        out = np.zeros(ring * fb, dtype=np.uint8)
+        ctx.d2h(out, dout)
+        return out
+
+    try:
+        for r in range(ring):
+            frame(r)
+        plain = ring_bytes()
+        ctx.h2d(dout, np.zeros(ring * fb, dtype=np.uint8))
+        ctx.frames_capture_begin()
+        for r in range(ring):
+            frame(r)
+        with pytest.raises(pm3d.Pm3dError):
+            ctx.sync()                                   # refused inside a capture
+        g = ctx.frames_capture_end()
+        assert not ring_bytes().any()                    # capturing executed nothing
+        for _ in range(3):
+            ctx.frames_replay(g)
+        assert np.array_equal(ring_bytes(), plain)
+        # poses rewritten in place: the recording follows the data, not the values it saw
+        ctx.h2d(dv, views[::-1].copy())
+        ctx.frames_replay(g)
+        swapped = ring_bytes().reshape(ring, fb)
+        ctx.h2d(dv, views)
+        assert not np.array_equal(swapped, plain.reshape(ring, fb))   # other cameras now
+        ctx.frames_replay(g)
+        frame(0)                                         # plain calls after a replay stay ordered behind it
+        assert np.array_equal(ring_bytes(), plain)
+        ctx.set_view(w, h, 2, 40)                        # reconfiguration retires the recording
+        with pytest.raises(pm3d.Pm3dError):
+            ctx.frames_replay(g)
+    finally:
+        ctx.set_option(pm3d._lib.OPT_LANES, 1)
+        ctx.set_option(pm3d._lib.OPT_OVERLAP, 1)
+        for p_ in (dv, ds, do, dout):
+            ctx.device_free(p_)

@@ -400,6 +400,37 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
         }
     }
 
+    // ---- per-lane mask of the warp's sprites that overlap this lane's four columns (lanes then walk different
+    //      sprites concurrently instead of every lane scanning the whole list).  Built transposed: lane i turns sprite
+    //      i's column range into a 16-bit mask of the column quads it touches, and sixteen ballots hand every lane its
+    //      word — ~50 instructions per 32 sprites instead of a 32-step loop per lane (which was a third of a two-row
+    //      warp's instructions).  Before the early return of off-screen lanes: the ballots want the whole warp.
+    const int n_words = (n_list + 31) >> 5;
+    {
+        const int lx_ = lane & 15;
+#pragma unroll 1
+        for (int wd = 0; wd < n_words; wd++) {
+            const int i = wd * 32 + lane;
+            uint32_t q = 0u;
+            if (i < n_list) {
+                const Rect16 rc = wl.rect[i];
+                // quad k covers columns [gx0 + 4k, gx0 + 4k + 3]; it overlaps [rc.x0, rc.x1) iff
+                // 4k >= rc.x0 - gx0 - 3 and 4k <= rc.x1 - gx0 - 1
+                const int a = (int)rc.x0 - gx0 - 3, b = (int)rc.x1 - gx0 - 1;
+                const int lo = a <= 0 ? 0 : (a + 3) >> 2;
+                const int hi = b < 0 ? -1 : min(15, b >> 2);
+                if (lo <= hi) q = ((2u << hi) - 1u) & ~((1u << lo) - 1u);
+            }
+            uint32_t m = 0u;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const unsigned bal = __ballot_sync(0xffffffffu, (q >> k) & 1u);
+                if (lx_ == k) m = bal;
+            }
+            s_xm[warp][wd][lane] = m;
+        }
+    }
+
     // ---- this lane's four columns
     const int lx = lane & 15, ly = lane >> 4;
     const int x0 = gx0 + lx * 4;
@@ -419,20 +450,6 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
     const uint32_t boundx = (uint32_t)min((uint64_t)p.map_w << p.tex_shift, (uint64_t)0x80000000u);
     const uint32_t boundy = (uint32_t)min((uint64_t)p.map_h << p.tex_shift, (uint64_t)0x80000000u);
     double lane_cd_max = -2.0;  // -2: not computed yet (only warps that reach a floor row need it)
-
-    // per-lane mask of the warp's sprites that overlap this lane's four columns (lanes then walk
-    // different sprites concurrently instead of every lane scanning the whole list)
-    const int n_words = (n_list + 31) >> 5;
-#pragma unroll 1
-    for (int wd = 0; wd < n_words; wd++) {
-        uint32_t m = 0u;
-        const int lim = min(32, n_list - wd * 32);
-        for (int b = 0; b < lim; b++) {
-            const Rect16 rc = wl.rect[wd * 32 + b];
-            if (!(x0 + 3 < rc.x0 || x0 >= rc.x1)) m |= 1u << b;
-        }
-        s_xm[warp][wd][lane] = m;
-    }
 
     // box texel column of each of this lane's pixels: once per warp when it walks many rows, else by the rows that
     // show the box (a two-row warp below the horizon never needs it)

@@ -483,7 +483,8 @@ int pm3d_selfcheck_floor(pm3d_ctx *ctx, uint64_t seed, int blocks, int iters, ui
  * out_points[n][max_points][2]: the points FindPath returns, start -> finish.  out_count[n]: how many there are
  * (more than max_points: only the first max_points were written), -1 = "unable to find path" (the reference's error;
  * also a start or finish outside the map).  flags: PM3D_IN_DEVICE / PM3D_OUT_DEVICE / PM3D_NO_SYNC (device buffers
- * only).  Scratch: 16 bytes per map cell and search in flight, at most 4 GiB, owned by the ctx. */
+ * only).  Scratch: 16 bytes per map cell and search in flight (as many searches at once as a third of the free
+ * device memory holds, at most 48 GiB; more queries run in waves), owned by the ctx until pm3d_destroy. */
 int pm3d_find_path_batch(pm3d_ctx *ctx, const double *queries, int64_t n, int max_points, double *out_points,
                          int32_t *out_count, uint32_t flags);
 

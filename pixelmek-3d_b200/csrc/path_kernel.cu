@@ -235,9 +235,14 @@ extern "C" int pm3d_find_path_batch(pm3d_ctx *ctx, const double *queries, int64_
     PM3D_CUDA(ctx, cudaSetDevice(ctx->device));
     { int rc_ = pm3d_main_enter(ctx); if (rc_) return rc_; }
     pm3d_main_touch(ctx);
-    // searches in flight: 16 bytes of scratch per cell and search, at most 4 GiB of it, whole warps
-    int64_t wave = std::min<int64_t>(n, std::max<int64_t>(32, ((int64_t)4 << 30) / (int64_t)(16 * cells)));
-    wave = std::min<int64_t>(wave, 16384);
+    // searches in flight: 16 bytes of scratch per cell and search, whole warps.  A wave ends with its slowest search, so
+    // as many as possible run at once: up to a third of the free HBM (at most 48 GiB) — 180 GB per GPU is what makes
+    // 4096 searches over a 500x500 map (16 GiB) one wave
+    size_t free_b = 0, total_b = 0;
+    PM3D_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    const int64_t budget = std::max<int64_t>((int64_t)1 << 30, std::min<int64_t>((int64_t)((free_b + ctx->path_scratch_bytes) / 3), (int64_t)48 << 30));
+    int64_t wave = std::min<int64_t>(n, std::max<int64_t>(32, budget / (int64_t)(16 * cells)));
+    wave = std::min<int64_t>(wave, 65536);
     wave = (wave + 31) / 32 * 32;
     const size_t need = (size_t)wave * cells * 16;
     if (ctx->path_scratch_bytes < need) {

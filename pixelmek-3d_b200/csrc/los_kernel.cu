@@ -357,6 +357,17 @@ __global__ void __launch_bounds__(LOS_THREADS, LOS_MIN_BLOCKS) k_los(LosParams p
 //   truncated ray endpoints in x), so the reference's loop returns false: not visible.  (Mirror image for edges on
 //   y = c.)  |dx| >= 1e-90 keeps denom normal and makes an underflowing product an absolute error far below the margin.
 // VISIBLE proof.  No visited cell has a candidate: no segment can intersect (the k_los argument).
+// VISIBLE proof, verify mode (VERIFY, chosen at upload for maps where few cells have candidates, i.e. where most rays are
+// visible and long).  A cell whose candidates are all CLEAN — axis-parallel, on a lattice line, integer end points,
+// the collision outlines of wall cells — can be crossed without testing them: such a segment is a union of whole unit
+// edges, so the ray intersects it exactly when it crosses one of its unit edges (covered: blocked, above) or touches a
+// lattice point.  So every crossing is kept 2^-14 away from the lattice points of the line it crosses (one
+// subtraction per step in the walk's own units, see the loop), the ray's end points must lie 2^-20 off every lattice line, and a cell
+// holding a segment that is not clean (the border rectangles inset by clipDistance, arbitrary caller segments) is
+// DIRTY: any of these failing makes the ray undecided.  With them holding, every clean segment misses the ray by a
+// margin the reference's binary64 evaluation cannot bridge: on its lattice line x = c either c lies 2^-20 outside
+// [x1, x2] (t = (x1-c)/(x1-x2) is outside [0, 1] by more than 2^-35, against 2^-52 of rounding) or the crossing is
+// 2^-21 away from the segment's extent (u outside [0, 1] by 2^-21/|L| against an evaluation error < 2^-33/|L|).
 // Everything else — a failed margin (the ray grazes a lattice corner), candidates seen but the target reached, a ray
 // outside the binned area — is appended to the undecided list and decided by k_los with the exact predicate.
 #define LOSF_THREADS 512
@@ -366,6 +377,7 @@ __global__ void __launch_bounds__(LOS_THREADS, LOS_MIN_BLOCKS) k_los(LosParams p
 #define LOSF_E 4u
 #define LOSF_S 8u
 #define LOSF_N 16u
+#define LOSF_DIRTY 32u
 
 // A lane that stops walking only clears `active`; the margin test, the answer byte and the append to the undecided
 // list run later for all stopped lanes of the warp together, in the same convergent block that hands them their
@@ -378,7 +390,7 @@ __global__ void __launch_bounds__(LOS_THREADS, LOS_MIN_BLOCKS) k_los(LosParams p
 #define LOSF_REFILL 12   // idle lanes that trigger a refill
 #endif
 
-template <bool SMEM>
+template <bool SMEM, bool VERIFY>
 __global__ void __launch_bounds__(LOSF_THREADS, 2) k_los_fast(LosParams p, long long rays_per_warp) {
     extern __shared__ uint8_t s_code[];
     const int n_cells = p.bin_w * p.bin_h;
@@ -413,6 +425,23 @@ __global__ void __launch_bounds__(LOSF_THREADS, 2) k_los_fast(LosParams p, long 
     int cell = 0, exy = 0;                // target cell (x | y << 16)
     int dcx = 0, dcy = 0;                 // cell index increments of an x / y step
     unsigned xmask = 0, ymask = 0, cur = 0, seen = 0;
+    bool risky = false;                   // verify mode: something on the way could not be verified -> undecided
+    double mthr = 0.0;                    // verify mode: 2^-14 * max(|dx|, |dy|)
+
+    // margin test of the crossing of the lattice line the walk meets NEXT (x step: xs): true when the real crossing lies
+    // 2^-21 inside the unit edge between the two cells
+    auto crossing_inside = [&](bool xs, int nx, int ny) -> bool {
+        const int cx = (exy & 0xffff) - (dcx > 0 ? nx : -nx), cy = (exy >> 16) - (dcy > 0 ? ny : -ny);
+        const int fwd = xs ? (dcx > 0) : (dcy > 0);
+        const double c = (double)((xs ? cx + p.bin_x0 : cy + p.bin_y0) + fwd);  // the lattice line crossed
+        const double k = (double)(xs ? cy + p.bin_y0 : cx + p.bin_x0);          // the edge spans [k, k+1] on it
+        const double a0 = xs ? x1 : y1, b0 = xs ? y1 : x1;
+        const double da = xs ? dx : dy, db = xs ? dy : dx;
+        const double ada = fabs(da);
+        const double P = fabs(c - a0) * db;
+        const double lo = ((k + LOSF_MARGIN) - b0) * ada, hi = ((k + (1.0 - LOSF_MARGIN)) - b0) * ada;
+        return lo < P && P < hi && ada >= 1e-90;
+    };
 
     for (;;) {
         const unsigned idle = __ballot_sync(0xffffffffu, !active);
@@ -421,22 +450,17 @@ __global__ void __launch_bounds__(LOSF_THREADS, 2) k_los_fast(LosParams p, long 
             // ---- finalize the rays of the stopped lanes (together)
             int result = -1;  // 0 blocked, 1 visible, 2 undecided
             if (!active && idx >= 0) {
-                if (n2 == 0u) {
-                    result = (seen & LOSF_CAND) ? 2 : 1;  // target reached (or the ray left the bins: seen = CAND)
+                if (risky) {
+                    result = 2;
+                } else if (n2 == 0u) {
+                    // target reached (or the ray left the bins: seen = CAND): visible when no cell had a candidate, or,
+                    // in verify mode, when every crossing next to one was verified
+                    result = (!(seen & LOSF_CAND) || (VERIFY && !(seen & LOSF_DIRTY))) ? 1 : 2;
                 } else {
-                    // prove that the crossing lies inside the covered unit edge, margin 2^-20 from its ends
+                    // in front of a covered edge: prove that the crossing lies inside it, margin 2^-20 from its ends
                     const int nx = (int)(n2 & 0xffffu), ny = (int)(n2 >> 16);
                     const bool xs = (tX < tY) ? (nx > 0) : (ny == 0);
-                    const int cx = (exy & 0xffff) - (dcx > 0 ? nx : -nx), cy = (exy >> 16) - (dcy > 0 ? ny : -ny);
-                    const int fwd = xs ? (dcx > 0) : (dcy > 0);
-                    const double c = (double)((xs ? cx + p.bin_x0 : cy + p.bin_y0) + fwd);  // the lattice line crossed
-                    const double k = (double)(xs ? cy + p.bin_y0 : cx + p.bin_x0);          // the edge spans [k, k+1] on it
-                    const double a0 = xs ? x1 : y1, b0 = xs ? y1 : x1;
-                    const double da = xs ? dx : dy, db = xs ? dy : dx;
-                    const double ada = fabs(da);
-                    const double P = fabs(c - a0) * db;
-                    const double lo = ((k + LOSF_MARGIN) - b0) * ada, hi = ((k + (1.0 - LOSF_MARGIN)) - b0) * ada;
-                    result = (lo < P && P < hi && ada >= 1e-90) ? 0 : 2;
+                    result = crossing_inside(xs, nx, ny) ? 0 : 2;
                 }
                 if (result < 2) p.out_flag[idx] = (uint8_t)result;
             }
@@ -472,7 +496,8 @@ __global__ void __launch_bounds__(LOSF_THREADS, 2) k_los_fast(LosParams p, long 
                 const int ex = (int)floor(ray.z) - p.bin_x0, ey = (int)floor(ray.w) - p.bin_y0;
                 if (!((unsigned)cx < (unsigned)p.bin_w && (unsigned)ex < (unsigned)p.bin_w &&
                       (unsigned)cy < (unsigned)p.bin_h && (unsigned)ey < (unsigned)p.bin_h)) {
-                    n2 = 0u; seen = LOSF_CAND;  // not finite, or outside the binned area: undecided
+                    n2 = 0u; seen = LOSF_CAND | LOSF_DIRTY;  // not finite, or outside the binned area: undecided
+                    risky = false;
                 } else {
                     dx = ray.z - x1; dy = ray.w - y1;
                     const bool right = dx > 0, up = dy > 0;
@@ -486,7 +511,17 @@ __global__ void __launch_bounds__(LOSF_THREADS, 2) k_los_fast(LosParams p, long 
                     cell = cy * p.bin_w + cx;
                     cur = code_at(cell);
                     seen = cur;
-                    active = n2 != 0u;
+                    if (VERIFY) {
+                        // both end points 2^-20 off every lattice line (a point ON a line may touch a segment without crossing)
+                        const double fzx = ray.z - floor(ray.z), fzy = ray.w - floor(ray.w), fxx = x1 - fx, fyy = y1 - fy;
+                        const double m_ = LOSF_MARGIN, M_ = 1.0 - LOSF_MARGIN;
+                        risky = !(fxx > m_ && fxx < M_ && fyy > m_ && fyy < M_ && fzx > m_ && fzx < M_ && fzy > m_ && fzy < M_) ||
+                                (cur & LOSF_DIRTY) != 0u;
+                        mthr = 6.103515625e-05 * fmax(fabs(dx), fabs(dy));
+                    } else {
+                        risky = false;
+                    }
+                    active = n2 != 0u && !(VERIFY && risky);
                 }
             }
             if (idle == 0xffffffffu && __ballot_sync(0xffffffffu, idx >= 0) == 0u) break;
@@ -500,12 +535,20 @@ __global__ void __launch_bounds__(LOSF_THREADS, 2) k_los_fast(LosParams p, long 
                 if (cur & (xs ? xmask : ymask)) {
                     active = false;
                 } else {
+                    // verify mode: this crossing and the next crossing of the OTHER axis must be 2^-14 apart along the
+                    // crossed line, i.e. the ray keeps clear of the lattice point between them.  In the walk's own units
+                    // that is one subtraction: the x line is met at tX/(|dx||dy|), the y line at tY/(|dx||dy|), and the ray
+                    // moves |tX - tY|/|dx| along the x line (|tX - tY|/|dy| along the y line) in between.  Every pair of
+                    // crossings adjacent in the merged order is a pair of heads at some step, so testing the heads at
+                    // every step covers them all (tX, tY carry < 2^-16 of accumulated rounding on bin areas up to 4096^2).
+                    if (VERIFY && !(fabs(tX - tY) > mthr)) risky = true;
                     if (xs) tX += fabs(dy); else tY += fabs(dx);
                     n2 -= xs ? 1u : 0x10000u;
                     cell += xs ? dcx : dcy;
                     cur = code_at(cell);
                     seen |= cur;
-                    active = n2 != 0u;
+                    if (VERIFY && (cur & LOSF_DIRTY)) risky = true;  // a segment that is not a union of unit edges
+                    active = n2 != 0u && !(VERIFY && risky);
                 }
             }
         }
@@ -918,12 +961,15 @@ static int run_batch(pm3d_ctx *ctx, bool is_move, const double *rays, int64_t n,
         const size_t code_bytes = (((size_t)ctx->bin_w * ctx->bin_h + 15) / 16) * 16;
         const bool smem = code_bytes <= 100 * 1024;
         if (smem && !ctx->los_smem_optin) {
-            PM3D_CUDA(ctx, cudaFuncSetAttribute(k_los_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            PM3D_CUDA(ctx, cudaFuncSetAttribute(k_los_fast<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            PM3D_CUDA(ctx, cudaFuncSetAttribute(k_los_fast<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             ctx->los_smem_optin = true;
         }
         int per_sm_a = 1, per_sm_b = 2;
-        if (smem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, k_los_fast<true>, LOSF_THREADS, code_bytes);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, k_los_fast<false>, LOSF_THREADS, 0);
+        if (smem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, k_los_fast<true, true>, LOSF_THREADS, code_bytes);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, k_los_fast<false, true>, LOSF_THREADS, 0);
+        int verify = ctx->los_verify;
+        if (const char *e = getenv("PM3D_LOS_VERIFY")) verify = atoi(e) != 0;  // tuning / test override
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_los, LOS_THREADS, 0);
         if (per_sm_a < 1) per_sm_a = 1;
         if (per_sm_b < 1) per_sm_b = 1;
@@ -941,8 +987,10 @@ static int run_batch(pm3d_ctx *ctx, bool is_move, const double *rays, int64_t n,
             if (per_warp < 32) per_warp = 32;
             warps = (q.n + per_warp - 1) / per_warp;
             const unsigned blocks_a = (unsigned)((warps + LOSF_THREADS / 32 - 1) / (LOSF_THREADS / 32));
-            if (smem) k_los_fast<true><<<blocks_a, LOSF_THREADS, code_bytes, ctx->stream>>>(q, per_warp);
-            else k_los_fast<false><<<blocks_a, LOSF_THREADS, 0, ctx->stream>>>(q, per_warp);
+            if (smem && verify) k_los_fast<true, true><<<blocks_a, LOSF_THREADS, code_bytes, ctx->stream>>>(q, per_warp);
+            else if (smem) k_los_fast<true, false><<<blocks_a, LOSF_THREADS, code_bytes, ctx->stream>>>(q, per_warp);
+            else if (verify) k_los_fast<false, true><<<blocks_a, LOSF_THREADS, 0, ctx->stream>>>(q, per_warp);
+            else k_los_fast<false, false><<<blocks_a, LOSF_THREADS, 0, ctx->stream>>>(q, per_warp);
             // the second pass sizes its ranges from the device-side count; a grid of one wave is enough for any count
             long long warps_b = std::min<long long>((long long)ctx->sm_count * per_sm_b * (LOS_THREADS / 32), (q.n + 31) / 32);
             const unsigned blocks_b = (unsigned)((warps_b + LOS_THREADS / 32 - 1) / (LOS_THREADS / 32));

@@ -1071,11 +1071,22 @@ int pm3d_upload_segments(pm3d_ctx *ctx, const double *xyxy, int n) {
         for (int i = 0; i < n; i++) {
             const double *s = xyxy + (size_t)i * 4;
             const bool vertical = s[0] == s[2], horizontal = s[1] == s[3];
-            if (vertical == horizontal) continue;  // oblique, or a point
             const double line = vertical ? s[0] : s[1];
-            if (line != floor(line)) continue;     // not on the lattice (the border rectangles inset by clipDistance)
             const double lo = vertical ? std::min(s[1], s[3]) : std::min(s[0], s[2]);
             const double hi = vertical ? std::max(s[1], s[3]) : std::max(s[0], s[2]);
+            // CLEAN = axis-parallel, on a lattice line, integer end points: a union of whole unit edges.  Every other
+            // segment (oblique, a point, off the lattice like the border rectangles inset by clipDistance, fractional
+            // ends) makes the cells it is registered in DIRTY: the first pass never decides "visible" through them
+            const bool clean = vertical != horizontal && line == floor(line) && lo == floor(lo) && hi == floor(hi);
+            if (!clean) {
+                int cx0, cy0, cx1, cy1;
+                cell_range(s, cx0, cy0, cx1, cy1);
+                for (int cy = cy0; cy <= cy1; cy++)
+                    for (int cx = cx0; cx <= cx1; cx++)
+                        if (touches(s, cx, cy)) code[(size_t)cy * bw + cx] |= 32u;
+            }
+            if (vertical == horizontal) continue;  // oblique, or a point
+            if (line != floor(line)) continue;     // not on the lattice
             const int c = (int)line;
             for (int k = (int)ceil(lo); (double)(k + 1) <= hi; k++) {  // unit edges [k, k+1] inside [lo, hi]
                 if (vertical) {
@@ -1091,6 +1102,11 @@ int pm3d_upload_segments(pm3d_ctx *ctx, const double *xyxy, int n) {
                 }
             }
         }
+        // verify mode of the first pass pays when most cells have no candidates (long visible rays); on dense maps the
+        // rays end at a covered edge after a few cells and the extra crossing tests would only cost
+        size_t n_cand = 0;
+        for (size_t c = 0; c < (size_t)bw * bh; c++) n_cand += code[c] & 1u;
+        ctx->los_verify = n_cand * 4 < (size_t)bw * bh && bw <= 4096 && bh <= 4096;  // (the rounding bound of the walk's tX / tY)
         if ((rc = dev_realloc(ctx, &ctx->cell_code, code.size()))) return rc;
         PM3D_CUDA(ctx, cudaMemcpy(ctx->cell_code, code.data(), code.size(), cudaMemcpyHostToDevice));
     }

@@ -223,6 +223,7 @@ struct pm3d_ctx {
     size_t los_list_bytes = 0;
     unsigned *los_count = nullptr;
     bool los_smem_optin = false;
+    int los_verify = 0;  // first pass verifies crossings next to candidate cells (maps where few cells have candidates)
     // batched Pathing.FindPath (path_kernel.cu): node states and queues of the searches in flight
     void *path_scratch = nullptr;
     size_t path_scratch_bytes = 0;

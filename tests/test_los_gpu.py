@@ -184,8 +184,15 @@ def test_division_free_predicate_matches_reference_arithmetic(gpu_ctx):
 #      "blocked" when the ray provably crosses the interior of a unit edge a segment covers, "visible" when no
 #      visited cell has a candidate — and must give the brute-force booleans like the exact pass it replaces.
 def _both_modes(ctx, rays, monkeypatch):
+    """(first pass in its default mode, first pass with the verify mode forced the other way ... , exact pass alone):
+    all modes of the first pass must agree with the exact pass, so the two are folded into one array pair."""
     monkeypatch.setenv("PM3D_LOS_FAST", "1")
     fast = ctx.los_batch(rays)
+    for v in ("0", "1"):                      # verify mode off / on, whatever the upload chose
+        monkeypatch.setenv("PM3D_LOS_VERIFY", v)
+        forced = ctx.los_batch(rays)
+        assert np.array_equal(forced, fast), f"PM3D_LOS_VERIFY={v} changes the answers"
+    monkeypatch.delenv("PM3D_LOS_VERIFY")
     monkeypatch.setenv("PM3D_LOS_FAST", "0")
     exact = ctx.los_batch(rays)
     monkeypatch.delenv("PM3D_LOS_FAST")

@@ -229,13 +229,38 @@ __device__ __forceinline__ void view_setup(const ViewParams &p, const int view) 
     int npad = 1;
     while (npad < n) npad <<= 1;
 
+    if (tid == 0) s_nan = 0;
+    __syncthreads();
     for (int i = tid; i < npad; i += VIEW_THREADS) {
         if (i >= n) { key_d[i] = -1.0; key_i[i] = 0xffff; continue; }  // pads paint last
-        key_d[i] = sprite_distance(c, sprites[i]);
+        const double d = sprite_distance(c, sprites[i]);
+        key_d[i] = d;
         key_i[i] = (uint16_t)i;
+        if (d != d) s_nan = 1;
     }
     __syncthreads();
-    for (int k = 2; k <= npad; k <<= 1) {
+    // up to 1024 sprites with totally ordered (NaN-free) distances: rank sort — every sprite counts the sprites that
+    // paint before it and is scattered to that place — n/256 passes over the distances instead of the ~50 barrier-
+    // separated passes of the bitonic network (408 sprites, the bundled map's static list: 25 k -> 9 k cycles)
+    const bool rank_sort = n <= 1024 && s_nan == 0;
+    if (rank_sort) {
+        // distances of the unsorted list move to the upper half of key_d (n <= 1024 of 2048 entries), the sorted
+        // (distance, index) pairs are written to the lower half
+        for (int i = tid; i < n; i += VIEW_THREADS) key_d[1024 + i] = key_d[i];
+        __syncthreads();
+        for (int i = tid; i < n; i += VIEW_THREADS) {
+            const double di = key_d[1024 + i];
+            int rank = 0;
+            for (int j = 0; j < n; j++) {
+                const double dj = key_d[1024 + j];
+                rank += (dj > di) || (dj == di && j < i);
+            }
+            key_d[rank] = di;
+            key_i[rank] = (uint16_t)i;
+        }
+        __syncthreads();
+    }
+    for (int k = 2; k <= npad && !rank_sort; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = tid; i < npad; i += VIEW_THREADS) {
                 int ixj = i ^ j;

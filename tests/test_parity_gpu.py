@@ -191,6 +191,23 @@ def test_many_overlapping_sprites_and_duplicates(gpu_ctx):
     check_all(gpu_ctx, got, want, off, n)
 
 
+@pytest.mark.parametrize("n", [257, 1024, 1500, 2048])
+def test_view_setup_orderings(gpu_ctx, n):
+    """The per-view sprite ordering has three implementations by list size — placement by counting (<= 256), rank sort
+    (<= 1024) and the bitonic network (<= 2048, the per-view limit): sizes at and across the boundaries, with ties."""
+    scene = edge_scene()
+    w, h = 160, 90
+    rng = W.SplitMix64(100 + n)
+    u = rng.uniform(n * 3).reshape(n, 3)
+    xyzs = np.stack([1.5 + 20.0 * u[:, 0], 1.5 + 13.0 * u[:, 1], np.zeros(n), 0.2 + 0.3 * u[:, 2]], axis=1)
+    xyzs[5:40, :2] = np.round(xyzs[5:40, :2])   # many equal distances from the cell-centred camera
+    spr = W.sprite_records(xyzs, (u[:, 2] * 4).astype(np.int32), np.zeros(n, np.uint8), scene.sheets)
+    views = W.make_views(scene, w, h, [(12.5, 8.5, 0.5, 2.5, 0.0)], render_distance=-1.0)
+    off = np.array([0, n], dtype=np.int32)
+    got, want = render_both(gpu_ctx, scene, w, h, views, spr, off)
+    check_all(gpu_ctx, got, want, off, n)
+
+
 @pytest.mark.parametrize("rows", [2, 4, 8, 16])
 def test_warp_list_overflow_in_both_sprite_modes(gpu_ctx, rows, monkeypatch):
     """700 billboards stacked on one patch overflow the warp-private sprite list in latency mode (64 entries, 2/4 rows

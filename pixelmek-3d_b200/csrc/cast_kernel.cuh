@@ -140,13 +140,20 @@ __device__ __forceinline__ void cast_ray(const CastParams &p, const int view, co
         while (ok) {
             N += Dq;
             int i, j;
-            if (x_dead) { i = 0; j = N; jside = 1; }
-            else if (y_dead) { i = N; j = 0; jside = 0; }
-            else ok = dda_jump(sideDistX, sideDistY, deltaDistX, deltaDistY, c0, inv, N, i, j, jside);
-            if (!ok) break;
+            if (x_dead) { i = 0; j = N; }
+            else if (y_dead) { i = N; j = 0; }
+            else dda_jump_split(deltaDistY, c0, inv, N, i, j);
+            // the landing cell's probe distance is requested BEFORE the certificate is evaluated (an in-range load is
+            // harmless if the certificate fails): the L2 round trip overlaps ~10 dependent binary64 operations
             jx = mx + i * stepX; jy = my + j * stepY;
-            if ((unsigned)jx < (unsigned)p.map_w && (unsigned)jy < (unsigned)p.map_h) {
-                Dq = __ldg(qd + jx * p.map_h + jy);
+            const bool inside = (unsigned)jx < (unsigned)p.map_w && (unsigned)jy < (unsigned)p.map_h;
+            const int Dn = inside ? (int)__ldg(qd + jx * p.map_h + jy) : 0;
+            if (x_dead) jside = 1;
+            else if (y_dead) jside = 0;
+            else ok = dda_jump_certify(sideDistX, sideDistY, deltaDistX, deltaDistY, N, i, j, jside);
+            if (!ok) break;
+            if (inside) {
+                Dq = Dn;
                 if (Dq == 0) { jhit = 1; break; }
             } else {
                 jhit = 2;

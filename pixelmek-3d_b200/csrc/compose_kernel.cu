@@ -703,10 +703,14 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
         //            near over its nearest opaque layer (sprite texel or background) — the layers behind an opaque
         //            texel cannot show, so this is the painter's result.  When the list overflowed or the painter is
         //            forced, every sprite is blended over the background.
+        // (a warp without sprites — most warps of a batch of views — skips all of it on one uniform branch)
+        unsigned repaint = 0u;
+        if (n_list > 0 || overflow) {
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-            if ((s_base >> j) & 1u) px[j] = s_top[j];
-        const unsigned repaint = p.force_painter ? (n_list > 0 ? full : 0u) : s_trans;
+            for (int j = 0; j < 4; j++)
+                if ((s_base >> j) & 1u) px[j] = s_top[j];
+            repaint = p.force_painter ? (n_list > 0 ? full : 0u) : s_trans;
+        }
         if (repaint) {
             if (overflow) {
                 // the far entries first (paint order), for the pixels repainted from the background

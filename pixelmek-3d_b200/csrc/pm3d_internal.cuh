@@ -377,16 +377,19 @@ __device__ __forceinline__ bool floor_fast_index(double w, double D, double P, u
 // certificate (a near tie: rays on exact diagonals, or non-finite operands, whose comparisons all read false)
 // returns false and the caller runs the reference loop instead.  Requires A_0, B_0 >= 0.
 // pm3d_selfcheck_dda compares it with the sequential loop on random and tie-prone rays (selfcheck.cu).
-__device__ __forceinline__ bool dda_jump(double sX0, double sY0, double dX, double dY, double c0, double inv, int N,
-                                         int &i_out, int &j_out, int &side_out) {
+// The two halves are separate so that the caller can fetch the landing cell's probe distance between them: the
+// load then overlaps the certificate instead of waiting for it.
+__device__ __forceinline__ void dda_jump_split(double dY, double c0, double inv, int N, int &i_out, int &j_out) {
     double r = ceil(__fma_rn((double)(N - 1), dY, c0) * inv);
     r = fmin(fmax(r, 0.0), (double)N);  // (NaN -> 0)
-    const int i = (int)r, j = N - i;
+    i_out = (int)r;
+    j_out = N - i_out;
+}
+__device__ __forceinline__ bool dda_jump_certify(double sX0, double sY0, double dX, double dY, int N, int i, int j, int &side_out) {
     const double a0 = __fma_rn((double)i, dX, sX0), b0 = __fma_rn((double)j, dY, sY0);  // A_i, B_j
     const double a1 = i > 0 ? __fma_rn((double)(i - 1), dX, sX0) : -INFINITY;           // A_{i-1}
     const double b1 = j > 0 ? __fma_rn((double)(j - 1), dY, sY0) : -INFINITY;           // B_{j-1}
     const double T = (double)(N + 8) * 8.8817841970012523e-16 * fmax(a0, b0);           // 2^-50
-    i_out = i; j_out = j;
     if (a1 - b1 > T) {          // the last step was an x step; B_{j-1} < A_{i-1} <= A_i holds, certify A_{i-1} < B_j
         side_out = 0;
         return b0 - a1 > T;
@@ -396,6 +399,11 @@ __device__ __forceinline__ bool dda_jump(double sX0, double sY0, double dX, doub
         return a0 - b1 > T;
     }
     return false;
+}
+__device__ __forceinline__ bool dda_jump(double sX0, double sY0, double dX, double dY, double c0, double inv, int N,
+                                         int &i_out, int &j_out, int &side_out) {
+    dda_jump_split(dY, c0, inv, N, i_out, j_out);
+    return dda_jump_certify(sX0, sY0, dX, dY, N, i_out, j_out, side_out);
 }
 
 // lighting: byte(ClampInt(int(base + sqrt(dist)*falloff + illumination (+ extra)), min, max)) per channel

@@ -101,7 +101,7 @@ __device__ __noinline__ uint32_t sprite_texel(const DrawRec &d, const uint32_t *
 // (inlined twice in the front-to-back walk so that the loads of two sprites are in flight together)
 #define NO_TEXEL 0xffffffffffffffffull
 #ifndef SPRITE_BATCH
-#define SPRITE_BATCH 2
+#define SPRITE_BATCH 2   // sprites fetched together per step of the latency-mode walk in the 80-register shapes
 #endif
 __device__ __forceinline__ uint64_t sprite_index(const DrawRec &d, int x, int y, double z) {
     if (x < d.dsx || x >= d.dex || x <= 0 || y < d.dsy || y >= d.dey) return NO_TEXEL;
@@ -230,6 +230,10 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
     constexpr int MAX_WARP_SPRITES = LATENCY ? LATENCY_LIST : 256;
     static_assert(MAX_WARP_SPRITES % 32 == 0, "the per-lane masks are whole 32-bit words");
     constexpr int WARP_WORDS = MAX_WARP_SPRITES / 32;
+    // the 64-register / 8-CTA shapes (frames sharing the chip: PM3D_OPT_LANES > 1) walk one sprite per step: the second
+    // sprite's records and texels in flight cost them spills, and the other lanes' warps hide the latency anyway
+    // (c2, 4 lanes: 55.6 k -> 62.1 k frames/s; a frame that has the chip to itself is the same either way)
+    constexpr int SB = (LATENCY && MIN_BLOCKS >= 8) ? 1 : SPRITE_BATCH;
     __shared__ WarpList<MAX_WARP_SPRITES, LATENCY> s_list[COMPOSE_WARPS];
     __shared__ uint32_t s_xm[COMPOSE_WARPS][WARP_WORDS][32];  // per-lane sprite masks (kept out of registers and out of unrolled code)
     // latency mode: per pixel, the listed sprites whose texel was TRANSLUCENT in the front-to-back walk (bit = list
@@ -488,7 +492,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
             for (int j = 0; j < 4; j++)
 #pragma unroll
                 for (int wq = 0; wq < WARP_WORDS; wq++) s_hit[warp][j][wq][lane] = 0u;
-            // Latency mode (few rows per warp, single frames).  SPRITE_BATCH sprites per step: a lane's walk is a chain of
+            // Latency mode (few rows per warp, single frames).  SB sprites per step: a lane's walk is a chain of
             // dependent loads (record -> texel), so the records and texels of the next few candidates are fetched
             // together and then resolved nearest first.
             int wd = n_words - 1;
@@ -508,16 +512,16 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
             };
 #pragma unroll 1
             while (s_got != full) {
-                int ids[SPRITE_BATCH];
+                int ids[SB];
 #pragma unroll
-                for (int b = 0; b < SPRITE_BATCH; b++) ids[b] = (b == 0 || ids[b - 1] >= 0) ? next_sprite() : -1;
+                for (int b = 0; b < SB; b++) ids[b] = (b == 0 || ids[b - 1] >= 0) ? next_sprite() : -1;
                 if (ids[0] < 0) break;
-                const DrawRec *dr[SPRITE_BATCH];
+                const DrawRec *dr[SB];
 #pragma unroll
-                for (int b = 0; b < SPRITE_BATCH; b++) dr[b] = &list_rec(ids[b] < 0 ? ids[0] : ids[b]);
-                uint32_t tx[SPRITE_BATCH][4];
+                for (int b = 0; b < SB; b++) dr[b] = &list_rec(ids[b] < 0 ? ids[0] : ids[b]);
+                uint32_t tx[SB][4];
 #pragma unroll
-                for (int b = 0; b < SPRITE_BATCH; b++) {
+                for (int b = 0; b < SB; b++) {
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const bool need = j < nvalid && !((s_got >> j) & 1u) && ids[b] >= 0;
@@ -526,7 +530,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                     }
                 }
 #pragma unroll
-                for (int b = 0; b < SPRITE_BATCH; b++) {  // resolve nearest first
+                for (int b = 0; b < SB; b++) {  // resolve nearest first
                     const uint32_t tint = dr[b]->tint;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {

@@ -221,6 +221,9 @@ __device__ __forceinline__ void load4(const int2 *base, size_t i, bool vec, int 
 // COMPOSE_WARPS warps per CTA: 4 for single frames, 2 for large batches (a CTA's slot is held until its slowest warp
 // ends, and small CTAs waste fewer warp slots); MIN_BLOCKS is given for 4-warp CTAs and scaled.
 // LATENCY: single frames with sprites (see the sprite list above)
+#ifndef COMPOSE_RUN_MIN_ROWS
+#define COMPOSE_RUN_MIN_ROWS 8  // shapes with at least this many rows per warp take sky / floor runs (see RUNS in the kernel)
+#endif
 #ifndef LATENCY_LIST
 #define LATENCY_LIST 64  // 24 KB of shared memory per 4-warp CTA: 8 CTAs per SM fit (96 entries cap it at 6)
 #endif
@@ -295,6 +298,123 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                 sky_below = min(sky_below, min(a.x, a.y));
                 fs_max = max(fs_max, a.z);
             }
+        }
+    }
+
+    // ---- RUNS (many rows per warp, i.e. large batches and 4K frames), BEFORE anything else of the warp exists: when
+    //      no sprite of the group touches the warp's rows, the leading row pairs that are sky only (above every slice
+    //      of the group) and the trailing ones that are floor only (below every floor start) are written by two tight
+    //      loops.  Inside a run a lane owns 2 adjacent columns x 2 rows, so everything per column — the three
+    //      fast-floor-cast parameters, the box texel columns — is a handful of registers loaded ONCE per run instead
+    //      of six 16 B loads per row pair, both row records are warp-uniform, and none of the general loop's state
+    //      (sprite list, masks, slice spans, per-pixel flags) is live yet: the runs are allocated ~40 registers, not the
+    //      64 the general loop spills at.  The arithmetic is that of the two fast branches of the general loop, value
+    //      for value; whatever a run cannot prove for ALL lanes of a row pair (a nil floor tile, a translucent texel, a
+    //      zero fraction in floor_fast_index, a row beyond the fast cast's weight bound) ends the run, and the general
+    //      loop below takes the row pairs no run has written (bit mask run_done).  A warp whose rows are all done
+    //      returns here: no sprite list, no masks, no per-column records.
+    constexpr bool RUNS = WARP_ROWS >= COMPOSE_RUN_MIN_ROWS;
+    constexpr int N_IT = WARP_ROWS / 2;
+    uint32_t run_done = 0u;
+    if (RUNS && !p.force_painter && gx0 + GROUP_COLS <= p.w && (p.w & 3) == 0) {
+        const int4 gi = p.bin_count[view * p.n_groups + group];  // entries, min dsy, max dey
+        if (!(gi.x > 0 && gi.z > wrow0 && gi.y < wrow1)) {
+            const int xa = gx0 + 2 * lane;  // this lane's two columns inside a run
+            const uint32_t tm = (uint32_t)p.tex_size - 1u;
+            uint2 *o = reinterpret_cast<uint2 *>(reinterpret_cast<uint32_t *>(p.out) + ((size_t)view * p.h + wrow0) * p.w + xa);
+            const RowRec *rr = p.row_rec + (size_t)view * p.h + wrow0;
+            const int opitch = p.w >> 1;
+            int it = 0;
+            {   // sky run
+                const int ylim = min(sky_below, p.h) - wrow0;  // row pairs [2 it, 2 it + 1] below this are sky only
+                if (1 < ylim) {
+                    uint32_t u[2];
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        const uint32_t uu = (uint32_t)((((uint64_t)(2 * (int64_t)(xa + j) + 1)) * p.xstep) >> 33);
+                        u[j] = uu > tm ? tm : uu;
+                    }
+#pragma unroll 1
+                    for (; it < N_IT && 2 * it + 1 < ylim; it++) {
+                        uint32_t t[2][2];
+                        bool ok = true;
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            const uint32_t inf = rr[2 * it + k].info;
+                            const int tile = (inf & 0x40000000u) ? p.sky_tile : p.floorbox_tile;
+                            ok = ok && tile >= 0;
+                            const uint32_t base = ((((uint32_t)max(tile, 0) << p.tex_shift) | (inf & 0xffffu)) << p.tex_shift);
+#pragma unroll
+                            for (int j = 0; j < 2; j++) t[k][j] = __ldg(p.atlas + (base | u[j]));
+                        }
+                        ok = ok && (t[0][0] & t[0][1] & t[1][0] & t[1][1]) >= 0xff000000u;
+                        if (!__all_sync(0xffffffffu, ok)) break;
+#pragma unroll
+                        for (int k = 0; k < 2; k++)
+                            o[(size_t)(2 * it + k) * opitch] = make_uint2(shade_opaque(t[k][0], box_tint), shade_opaque(t[k][1], box_tint));
+                    }
+                }
+            }
+            run_done = (1u << it) - 1u;  // the sky run wrote row pairs [0, it)
+            // floor run: from the first row pair at or below every floor start of the group to the warp's last one
+            it = max(it, (max(fs_max - wrow0, 0) + 1) >> 1);
+            const int it_floor = it;
+            if (it < N_IT && wrow0 + 2 * it + 1 < p.h) {
+                const size_t fa = (size_t)view * p.w + xa;
+                const double2 cw = *reinterpret_cast<const double2 *>(p.flo_dw + fa), cr = *reinterpret_cast<const double2 *>(p.flo_rc + fa);
+                const double2 dx = *reinterpret_cast<const double2 *>(p.flo_dx + fa), dy = *reinterpret_cast<const double2 *>(p.flo_dy + fa);
+                // largest row distance for which both columns keep |weight| <= 4 (negative: a column is not eligible)
+                const double cd_max = (cr.x != 0.0 && cr.y != 0.0) ? 4.0 * fmin(fabs(cw.x), fabs(cw.y)) : -1.0;
+                const double texd_ = (double)p.tex_size;
+                const double ptx = c.pos_x * texd_, pty = c.pos_y * texd_;  // texel-unit camera position
+                const uint32_t bx = (uint32_t)min((uint64_t)p.map_w << p.tex_shift, (uint64_t)0x80000000u);
+                const uint32_t by = (uint32_t)min((uint64_t)p.map_h << p.tex_shift, (uint64_t)0x80000000u);
+                const int last = p.h - 1 - wrow0;  // last existing row of the view, relative to the warp's first
+                RowRec r[2] = {rr[2 * it], rr[2 * it + 1]};
+#pragma unroll 1
+                for (; it < N_IT && 2 * it + 1 <= last; it++) {
+                    const uint32_t tint[2] = {r[0].tint, r[1].tint};
+                    bool ok = (r[0].info & r[1].info & 0x80000000u) && (r[0].info & r[1].info & 0x20000000u) && r[0].cd <= cd_max && r[1].cd <= cd_max;
+                    uint32_t tx[2][2], ty[2][2];
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        const double w0 = r[k].cd * cr.x, w1 = r[k].cd * cr.y;
+                        ok = floor_fast_index(w0, dx.x, ptx, bx, tx[k][0]) && ok;
+                        ok = floor_fast_index(w0, dy.x, pty, by, ty[k][0]) && ok;
+                        ok = floor_fast_index(w1, dx.y, ptx, bx, tx[k][1]) && ok;
+                        ok = floor_fast_index(w1, dy.y, pty, by, ty[k][1]) && ok;
+                    }
+                    // the next pair's row records are requested before this pair's texels are waited for
+                    r[0] = rr[min(2 * it + 2, last)];
+                    r[1] = rr[min(2 * it + 3, last)];
+                    uint32_t t[2][2] = {{0u, 0u}, {0u, 0u}};
+                    if (ok) {
+                        int ft[2][2];
+#pragma unroll
+                        for (int k = 0; k < 2; k++)
+#pragma unroll
+                            for (int j = 0; j < 2; j++)
+                                ft[k][j] = __ldg(p.floor_tiles + (tx[k][j] >> p.tex_shift) * p.map_h + (ty[k][j] >> p.tex_shift));
+                        if ((ft[0][0] | ft[0][1] | ft[1][0] | ft[1][1]) >= 0) {
+#pragma unroll
+                            for (int k = 0; k < 2; k++)
+#pragma unroll
+                                for (int j = 0; j < 2; j++)
+                                    t[k][j] = __ldg(p.atlas + (((((uint32_t)ft[k][j] << p.tex_shift) | (ty[k][j] & tm)) << p.tex_shift) | (tx[k][j] & tm)));
+                        }
+                    }
+                    ok = (t[0][0] & t[0][1] & t[1][0] & t[1][1]) >= 0xff000000u;  // (all zero when a step above failed)
+                    if (!__all_sync(0xffffffffu, ok)) break;
+#pragma unroll
+                    for (int k = 0; k < 2; k++)
+                        o[(size_t)(2 * it + k) * opitch] = make_uint2(floor_tint(t[k][0], tint[k]), floor_tint(t[k][1], tint[k]));
+                }
+                run_done |= ((1u << it) - 1u) & ~((1u << it_floor) - 1u);  // the floor run wrote row pairs [it_floor, it)
+            }
+            // every row pair written: nothing is left for this warp — unless it owns the screen centre (convergence)
+            const int n_it = (wrow1 - wrow0 + 1) >> 1;
+            const int cx = p.w / 2, cy = p.h / 2;
+            if (run_done == (1u << n_it) - 1u && !(cx >= gx0 && cx < gx0 + GROUP_COLS && cy >= wrow0 && cy < wrow1)) return;
         }
     }
 
@@ -473,6 +593,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
 
 #pragma unroll 1
     for (int it = 0; it < WARP_ROWS / 2; it++) {
+        if (RUNS && ((run_done >> it) & 1u)) continue;  // this row pair was written by a run
         const int y = wrow0 + it * 2 + ly;
         if (y >= p.h) break;
         const RowRec r = p.row_rec[(size_t)view * p.h + y];

@@ -27,8 +27,26 @@
 // (Camera.GetConvergenceSprite, game/scene_game.go:164).
 #include <stddef.h>
 #include <stdlib.h>
+#include <stdio.h>
+#include <vector>
 
 #include "pm3d_internal.cuh"
+
+#ifndef COMPOSE_RUN_MIN_ROWS
+#define COMPOSE_RUN_MIN_ROWS 8  // shapes with at least this many rows per warp take sky / floor runs (see RUNS in the kernel)
+#endif
+#ifndef COMPOSE_TP_LIST
+#define COMPOSE_TP_LIST 256  // warp-private sprite list of the throughput shapes (entries)
+#endif
+#ifndef COMPOSE_TP_WARPS
+#define COMPOSE_TP_WARPS 1   // warps per CTA of the 16-row shape (large batches): a slot is not held for a slower sibling warp
+#endif
+#ifndef COMPOSE_SKY_NP
+#define COMPOSE_SKY_NP 1    // row pairs per step of a sky run
+#endif
+#ifndef COMPOSE_FLOOR_NP
+#define COMPOSE_FLOOR_NP 1  // row pairs per step of a floor run
+#endif
 
 // rows per warp (WARP_ROWS, a template parameter: 2, 4 or 8 = 1, 2 or 4 iterations of 2 rows) trades the
 // per-warp prologue against the length of the serial chain: single frames want many short warps, large
@@ -64,7 +82,13 @@ struct ComposeParams {
     uint8_t *out;
     uint64_t xstep;  // span_step(tex_size, w): box texel column of screen column x
     int w, h, num_levels, tex_size, tex_shift, map_w, map_h, n_groups, sky_tile, floorbox_tile, force_painter;
+    int row_major;  // grid = (groups, views, row blocks) instead of (groups, row blocks, views)
 };
+
+// texel (tx, ty) of atlas tile `tile`
+__device__ __forceinline__ uint32_t atlas_fetch(const ComposeParams &p, uint32_t tile, uint32_t ty, uint32_t tx) {
+    return __ldg(p.atlas + ((((tile << p.tex_shift) | ty) << p.tex_shift) | tx));  // 32-bit texel index (pm3d_upload_atlas checks the size)
+}
 
 // screen rect of a listed sprite, clamped to int16 (screens are <= 16384 wide/high, so clamping never
 // changes a comparison against a screen coordinate)
@@ -141,7 +165,7 @@ __device__ __forceinline__ uint32_t floor_texel(const ComposeParams &p, double f
     const int ft = __ldg(p.floor_tiles + (tx >> p.tex_shift) * p.map_h + (ty >> p.tex_shift));
     if (ft < 0) return 0u;
     const int m = p.tex_size - 1;
-    const uint32_t px = __ldg(p.atlas + (((((uint32_t)ft << p.tex_shift) | (uint32_t)(ty & m)) << p.tex_shift) | (uint32_t)(tx & m)));
+    const uint32_t px = atlas_fetch(p, (uint32_t)ft, (uint32_t)(ty & m), (uint32_t)(tx & m));
     if ((px >> 24) == 0) return 0u;
     return floor_tint(px, r.tint);
 }
@@ -150,14 +174,14 @@ __device__ __forceinline__ uint32_t wall_texel(const ComposeParams &p, uint32_t 
     uint32_t ty = (uint32_t)((ps.x + (uint64_t)(int64_t)y * ps.y) >> 33);
     if (ty > (uint32_t)p.tex_size - 1) ty = p.tex_size - 1;
     const uint32_t tile = tile_texx >> 16, tx = tile_texx & 0xffffu;
-    return __ldg(p.atlas + ((((tile << p.tex_shift) | ty) << p.tex_shift) | tx));  // 32-bit texel index (pm3d_upload_atlas checks the size)
+    return atlas_fetch(p, tile, ty, tx);
 }
 
 __device__ __forceinline__ uint32_t box_texel(const ComposeParams &p, uint32_t info, uint32_t u) {
     const int tile = (info & 0x40000000u) ? p.sky_tile : p.floorbox_tile;
     if (tile < 0) return 0u;
     const uint32_t v = info & 0xffffu;
-    return __ldg(p.atlas + (((((uint32_t)tile << p.tex_shift) | v) << p.tex_shift) | u));
+    return atlas_fetch(p, (uint32_t)tile, v, u);
 }
 
 // tinted opaque texel over anything: (c*tint + 127)/255, alpha 255
@@ -218,204 +242,263 @@ __device__ __forceinline__ void load4(const int2 *base, size_t i, bool vec, int 
     }
 }
 
-// COMPOSE_WARPS warps per CTA: 4 for single frames, 2 for large batches (a CTA's slot is held until its slowest warp
-// ends, and small CTAs waste fewer warp slots); MIN_BLOCKS is given for 4-warp CTAs and scaled.
-// LATENCY: single frames with sprites (see the sprite list above)
-#ifndef COMPOSE_RUN_MIN_ROWS
-#define COMPOSE_RUN_MIN_ROWS 8  // shapes with at least this many rows per warp take sky / floor runs (see RUNS in the kernel)
-#endif
+// Row blocks are issued from the horizon outwards: the rows around it carry the sprites and the mixed
+// wall/floor/sky rows, i.e. the longest CTAs, and a single frame is only a few waves of CTAs — started
+// last they would be the tail of the launch.  (n row blocks of block_rows rows; k = blockIdx.y)
+__device__ __forceinline__ int compose_yblock(int h, int pitch_px, int block_rows, int n, int k) {
+    int cb = (h / 2 + pitch_px) / block_rows;
+    cb = cb < 0 ? 0 : (cb > n - 1 ? n - 1 : cb);
+    const int lo = cb, hi = n - 1 - cb;                      // blocks above / below the horizon block
+    const int m = lo < hi ? lo : hi;
+    if (k <= 2 * m) return (k & 1) ? cb - ((k + 1) >> 1) : cb + (k >> 1);
+    return lo < hi ? k : n - 1 - k;
+}
+// ---- RUNS: tight loops over row pairs that are sky only / floor only for a whole 64-column group (k_compose decides
+// which; shapes with many rows per warp).  Inside a run a lane owns 2 adjacent columns x 2 rows per pair and NP pairs per
+// step, so everything per column — the three fast-floor-cast parameters, the box texel columns — is a handful of
+// registers loaded ONCE per run (the general loop re-reads six 16 B vectors per row pair), the row records come out of
+// the warp's own registers by shuffle (lane l holds row l), the texel loads of all NP pairs of a step are in flight
+// together, and none of the general loop's state (sprite list, masks, slice spans, per-pixel flags) is live.  The
+// arithmetic is that of the two fast branches of the general loop, value for value; whatever a step cannot prove for
+// ALL lanes (a nil floor tile, a translucent texel, a zero fraction in floor_fast_index, a row beyond the fast cast's
+// weight bound) ends the run and the general loop takes the row pairs from there.  Both return the first pair not written.
+template <int NP>
+__device__ __forceinline__ bool sky_step(const ComposeParams &p, const RowRec &mine, uint2 *o, const uint32_t (&u)[2], uint32_t box_tint, int it) {
+    uint32_t t[NP][2][2];
+    bool ok = true;
+#pragma unroll
+    for (int q = 0; q < NP; q++)
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const uint32_t inf = __shfl_sync(0xffffffffu, mine.info, 2 * (it + q) + k);
+            const int tile = (inf & 0x40000000u) ? p.sky_tile : p.floorbox_tile;
+            ok = ok && tile >= 0;
+#pragma unroll
+            for (int j = 0; j < 2; j++) t[q][k][j] = atlas_fetch(p, (uint32_t)max(tile, 0), inf & 0xffffu, u[j]);
+        }
+    uint32_t all = 0xffffffffu;
+#pragma unroll
+    for (int q = 0; q < NP; q++) all &= t[q][0][0] & t[q][0][1] & t[q][1][0] & t[q][1][1];
+    ok = ok && all >= 0xff000000u;
+    if (!__all_sync(0xffffffffu, ok)) return false;
+    const int opitch = p.w >> 1;
+#pragma unroll
+    for (int q = 0; q < NP; q++)
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+            o[(size_t)(2 * (it + q) + k) * opitch] = make_uint2(shade_opaque(t[q][k][0], box_tint), shade_opaque(t[q][k][1], box_tint));
+    return true;
+}
+template <int N_IT>
+__device__ __forceinline__ int run_sky(const ComposeParams &p, const RowRec &mine, uint2 *o, int xa, uint32_t box_tint, int end) {
+    const uint32_t tm = (uint32_t)p.tex_size - 1u;
+    uint32_t u[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const uint32_t uu = (uint32_t)((((uint64_t)(2 * (int64_t)(xa + j) + 1)) * p.xstep) >> 33);
+        u[j] = uu > tm ? tm : uu;
+    }
+    int it = 0;
+    if (N_IT >= 2 && COMPOSE_SKY_NP >= 2) {
+#pragma unroll 1
+        for (; it + 2 <= end; it += 2)
+            if (!sky_step<2>(p, mine, o, u, box_tint, it)) break;
+    }
+#pragma unroll 1
+    for (; it < end; it++)
+        if (!sky_step<1>(p, mine, o, u, box_tint, it)) break;
+    return it;
+}
+
+struct FloorRun {
+    double2 cr, dx, dy;
+    double cd_max, ptx, pty;
+    uint32_t bx, by, tm;
+};
+template <int NP>
+__device__ __forceinline__ bool floor_step(const ComposeParams &p, const FloorRun &f, const RowRec &mine, uint2 *o, int it) {
+    uint32_t tx[NP][2][2], ty[NP][2][2];
+    bool ok = true;
+#pragma unroll
+    for (int q = 0; q < NP; q++)
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int row = 2 * (it + q) + k;
+            const double cd = __shfl_sync(0xffffffffu, mine.cd, row);
+            const uint32_t inf = __shfl_sync(0xffffffffu, mine.info, row);
+            ok = ok && (inf & 0x80000000u) && (inf & 0x20000000u) && cd <= f.cd_max;
+            const double w0 = cd * f.cr.x, w1 = cd * f.cr.y;
+            ok = floor_fast_index(w0, f.dx.x, f.ptx, f.bx, tx[q][k][0]) && ok;
+            ok = floor_fast_index(w0, f.dy.x, f.pty, f.by, ty[q][k][0]) && ok;
+            ok = floor_fast_index(w1, f.dx.y, f.ptx, f.bx, tx[q][k][1]) && ok;
+            ok = floor_fast_index(w1, f.dy.y, f.pty, f.by, ty[q][k][1]) && ok;
+        }
+    uint32_t t[NP][2][2];
+#pragma unroll
+    for (int q = 0; q < NP; q++)
+#pragma unroll
+        for (int k = 0; k < 2; k++) t[q][k][0] = t[q][k][1] = 0u;
+    if (ok) {
+        int ft[NP][2][2], any = 0;
+#pragma unroll
+        for (int q = 0; q < NP; q++)
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    ft[q][k][j] = __ldg(p.floor_tiles + (tx[q][k][j] >> p.tex_shift) * p.map_h + (ty[q][k][j] >> p.tex_shift));
+                    any |= ft[q][k][j];
+                }
+        if (any >= 0) {
+#pragma unroll
+            for (int q = 0; q < NP; q++)
+#pragma unroll
+                for (int k = 0; k < 2; k++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++)
+                        t[q][k][j] = atlas_fetch(p, (uint32_t)ft[q][k][j], ty[q][k][j] & f.tm, tx[q][k][j] & f.tm);
+        }
+    }
+    uint32_t all = 0xffffffffu;  // (the texels are all zero when a step above failed)
+#pragma unroll
+    for (int q = 0; q < NP; q++) all &= t[q][0][0] & t[q][0][1] & t[q][1][0] & t[q][1][1];
+    if (!__all_sync(0xffffffffu, all >= 0xff000000u)) return false;
+    const int opitch = p.w >> 1;
+#pragma unroll
+    for (int q = 0; q < NP; q++)
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const uint32_t tint = __shfl_sync(0xffffffffu, mine.tint, 2 * (it + q) + k);
+            o[(size_t)(2 * (it + q) + k) * opitch] = make_uint2(floor_tint(t[q][k][0], tint), floor_tint(t[q][k][1], tint));
+        }
+    return true;
+}
+template <int N_IT>
+__device__ __forceinline__ int run_floor(const ComposeParams &p, const pm3d_view &c, const RowRec &mine, uint2 *o, size_t fa, int it, int end) {
+    FloorRun f;
+    const double2 cw = *reinterpret_cast<const double2 *>(p.flo_dw + fa);
+    f.cr = *reinterpret_cast<const double2 *>(p.flo_rc + fa);
+    f.dx = *reinterpret_cast<const double2 *>(p.flo_dx + fa);
+    f.dy = *reinterpret_cast<const double2 *>(p.flo_dy + fa);
+    // largest row distance for which both columns keep |weight| <= 4 (negative: a column is not eligible)
+    f.cd_max = (f.cr.x != 0.0 && f.cr.y != 0.0) ? 4.0 * fmin(fabs(cw.x), fabs(cw.y)) : -1.0;
+    const double texd = (double)p.tex_size;
+    f.ptx = c.pos_x * texd; f.pty = c.pos_y * texd;  // texel-unit camera position
+    f.bx = (uint32_t)min((uint64_t)p.map_w << p.tex_shift, (uint64_t)0x80000000u);
+    f.by = (uint32_t)min((uint64_t)p.map_h << p.tex_shift, (uint64_t)0x80000000u);
+    f.tm = (uint32_t)p.tex_size - 1u;
+    if (N_IT >= 2 && COMPOSE_FLOOR_NP >= 2) {
+#pragma unroll 1
+        for (; it + 2 <= end; it += 2)
+            if (!floor_step<2>(p, f, mine, o, it)) break;
+    }
+#pragma unroll 1
+    for (; it < end; it++)
+        if (!floor_step<1>(p, f, mine, o, it)) break;
+    return it;
+}
+
+// group aggregates written by the cast: rows >= fs_max are floor candidates in every column, rows < sky_below are
+// above every wall slice and every floor start, no column of the group has a z-buffer value above zmax
+__device__ __forceinline__ void compose_aggregates(const ComposeParams &p, int view, int group, int &fs_max, int &sky_below, double &zmax) {
+    // every lane reads the same 2*L contiguous records (broadcast transactions at immediate offsets from one base:
+    // cheaper than a strided read followed by ten shuffles); level 0 carries the floor starts and the z bound
+    const int L = p.num_levels;
+    const int4 *ag = p.agg + (size_t)((unsigned)(view * p.n_groups + group) * (unsigned)(2 * L));
+    const int4 a0 = __ldg(ag), a1 = __ldg(ag + 1);
+    fs_max = max(a0.z, a1.z);
+    sky_below = min(min(a0.x, a0.y), min(a1.x, a1.y));
+    zmax = (double)fmaxf(__int_as_float(a0.w), __int_as_float(a1.w));
+    if (L <= 4) {
+        // the usual stacks (the bundled maps have 3 levels): no loop; a slot past the last record re-reads the last
+        // one (min / max do not mind), so there is nothing to predicate
+        const int last = 2 * L - 1;
+#pragma unroll
+        for (int k = 2; k < 8; k++) {
+            const int4 a = __ldg(ag + min(k, last));
+            sky_below = min(sky_below, min(a.x, a.y));
+            fs_max = max(fs_max, a.z);
+        }
+    } else {
+#pragma unroll 2
+        for (int k = 2; k < 2 * L; k++) {
+            const int4 a = __ldg(ag + k);
+            sky_below = min(sky_below, min(a.x, a.y));
+            fs_max = max(fs_max, a.z);
+        }
+    }
+}
+
+// The runs of one warp (whole warp, converged): returns the bit mask of the row pairs it wrote.  When no sprite of the
+// group touches the warp's rows, the leading row pairs that are sky only (above every slice of the group) and the
+// trailing ones that are floor only (at or below every floor start) are written by run_sky / run_floor.
+template <int WARP_ROWS>
+__device__ __forceinline__ uint32_t compose_runs(const ComposeParams &p, const pm3d_view &c, int view, int group, int lane, int wrow0, int wrow1,
+                                                 int fs_max, int sky_below, uint32_t box_tint) {
+    constexpr int N_IT = WARP_ROWS / 2;
+    const int gx0 = group * GROUP_COLS;
+    if (p.force_painter || gx0 + GROUP_COLS > p.w || (p.w & 3) != 0) return 0u;
+    const int4 gi = p.bin_count[view * p.n_groups + group];  // entries, min dsy, max dey
+    if (gi.x > 0 && gi.z > wrow0 && gi.y < wrow1) return 0u;
+    const int xa = gx0 + 2 * lane;  // this lane's two columns inside a run
+    uint2 *o = reinterpret_cast<uint2 *>(reinterpret_cast<uint32_t *>(p.out) + ((size_t)view * p.h + wrow0) * p.w + xa);
+    const int last = p.h - 1 - wrow0;  // last existing row of the view, relative to the warp's first
+    // lane l holds the record of the warp's row l; the loops fetch them by shuffle (no load in the loops)
+    const RowRec mine = p.row_rec[(size_t)view * p.h + wrow0 + min(lane, last)];
+    const int n_pairs = min(N_IT, (last + 1) >> 1);  // complete row pairs of this warp
+    // sky run: row pairs whose rows are all above every slice and floor start of the group
+    const int sky_pairs = min(n_pairs, max(min(sky_below, p.h) - wrow0, 0) >> 1);
+    int it = 0;
+    if (sky_pairs > 0) it = run_sky<N_IT>(p, mine, o, xa, box_tint, sky_pairs);
+    uint32_t done = (1u << it) - 1u;  // the sky run wrote row pairs [0, it)
+    // floor run: from the first row pair at or below every floor start of the group to the warp's last one
+    const int it_floor = max(it, (max(fs_max - wrow0, 0) + 1) >> 1);
+    if (it_floor < n_pairs) {
+        it = run_floor<N_IT>(p, c, mine, o, (size_t)view * p.w + xa, it_floor, n_pairs);
+        done |= ((1u << it) - 1u) & ~((1u << it_floor) - 1u);  // the floor run wrote row pairs [it_floor, it)
+    }
+    return done;
+}
+// every row pair written: nothing is left for this warp — unless it owns the screen centre (convergence)
+__device__ __forceinline__ bool compose_runs_complete(const ComposeParams &p, uint32_t done, int gx0, int wrow0, int wrow1) {
+    const int n_it = (wrow1 - wrow0 + 1) >> 1;
+    const int cx = p.w / 2, cy = p.h / 2;
+    return done == (1u << n_it) - 1u && !(cx >= gx0 && cx < gx0 + GROUP_COLS && cy >= wrow0 && cy < wrow1);
+}
+
 #ifndef LATENCY_LIST
 #define LATENCY_LIST 64  // 24 KB of shared memory per 4-warp CTA: 8 CTAs per SM fit (96 entries cap it at 6)
 #endif
-template <int WARP_ROWS, int MIN_BLOCKS, int COMPOSE_WARPS, bool LATENCY = false>
-__global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_WARPS) k_compose(const __grid_constant__ ComposeParams p) {
-    constexpr int COMPOSE_ROWS = COMPOSE_WARPS * WARP_ROWS;
-    constexpr int MAX_WARP_SPRITES = LATENCY ? LATENCY_LIST : 256;
+// One warp's work: 64 columns x WARP_ROWS rows starting at row wrow0 of column group `group` of view `view`.  `wl`,
+// `xm`, `hit` are the warp's private shared-memory scratch (sprite list, per-lane sprite masks, translucent-hit masks).
+// Called by the whole warp; lanes may return at different points (the caller re-converges the warp).
+template <int WARP_ROWS, bool LATENCY, int SB, int MAX_WARP_SPRITES>
+__device__ __forceinline__ void compose_warp(const ComposeParams &p, WarpList<MAX_WARP_SPRITES, LATENCY> &wl,
+                                             uint32_t (&xm)[MAX_WARP_SPRITES / 32][32], uint32_t (&hit)[4][LATENCY ? MAX_WARP_SPRITES / 32 : 1][32],
+                                             const int group, const int view, const int wrow0, const int lane) {
     static_assert(MAX_WARP_SPRITES % 32 == 0, "the per-lane masks are whole 32-bit words");
     constexpr int WARP_WORDS = MAX_WARP_SPRITES / 32;
-    // the 64-register / 8-CTA shapes (frames sharing the chip: PM3D_OPT_LANES > 1) walk one sprite per step: the second
-    // sprite's records and texels in flight cost them spills, and the other lanes' warps hide the latency anyway
-    // (c2, 4 lanes: 55.6 k -> 62.1 k frames/s; a frame that has the chip to itself is the same either way)
-    constexpr int SB = (LATENCY && MIN_BLOCKS >= 8) ? 1 : SPRITE_BATCH;
-    __shared__ WarpList<MAX_WARP_SPRITES, LATENCY> s_list[COMPOSE_WARPS];
-    __shared__ uint32_t s_xm[COMPOSE_WARPS][WARP_WORDS][32];  // per-lane sprite masks (kept out of registers and out of unrolled code)
-    // latency mode: per pixel, the listed sprites whose texel was TRANSLUCENT in the front-to-back walk (bit = list
-    // index).  The repaint of such a pixel blends exactly these over its opaque base instead of testing every sprite
-    // of the lane again (the bundled trees are mostly fully transparent texels around a few translucent ones)
-    __shared__ uint32_t s_hit[LATENCY ? COMPOSE_WARPS : 1][4][LATENCY ? WARP_WORDS : 1][32];
-
-    const int group = blockIdx.x, view = blockIdx.z;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const pm3d_view &c = p.views[view];
-    // Row blocks are issued from the horizon outwards: the rows around it carry the sprites and the mixed
-    // wall/floor/sky rows, i.e. the longest CTAs, and a single frame is only a few waves of CTAs — started
-    // last they would be the tail of the launch.
-    int yblock;
-    {
-        const int n = gridDim.y, k = blockIdx.y;
-        int cb = (p.h / 2 + c.pitch_px) / COMPOSE_ROWS;
-        cb = cb < 0 ? 0 : (cb > n - 1 ? n - 1 : cb);
-        const int lo = cb, hi = n - 1 - cb;                      // blocks above / below the horizon block
-        const int m = lo < hi ? lo : hi;
-        if (k <= 2 * m) yblock = (k & 1) ? cb - ((k + 1) >> 1) : cb + (k >> 1);
-        else yblock = lo < hi ? k : n - 1 - k;
-    }
-    const int wrow0 = yblock * COMPOSE_ROWS + warp * WARP_ROWS;
-    if (wrow0 >= p.h) return;
     const int wrow1 = min(wrow0 + WARP_ROWS, p.h);
     const int gx0 = group * GROUP_COLS;
     const uint32_t box_tint = (uint32_t)c.max_light[0] | ((uint32_t)c.max_light[1] << 8) |
                               ((uint32_t)c.max_light[2] << 16) | 0xff000000u;
-    WarpList<MAX_WARP_SPRITES, LATENCY> &wl = s_list[warp];
 
     // ---- group aggregates written by the cast: rows >= fs_max are floor candidates in every column,
     //      rows < sky_below are above every wall slice and every floor start
-    int fs_max = 0, sky_below = 0x7fffffff;
-    double zmax_group = INFINITY;  // no column of the group has a z-buffer value above this
-    {
-        // every lane reads the same 2*L contiguous records (broadcast transactions at immediate offsets from one base:
-        // cheaper than a strided read followed by ten shuffles); level 0 carries the floor starts and the z bound
-        const int L = p.num_levels;
-        const int4 *ag = p.agg + (size_t)((unsigned)(view * p.n_groups + group) * (unsigned)(2 * L));
-        const int4 a0 = __ldg(ag), a1 = __ldg(ag + 1);
-        fs_max = max(a0.z, a1.z);
-        sky_below = min(min(a0.x, a0.y), min(a1.x, a1.y));
-        zmax_group = (double)fmaxf(__int_as_float(a0.w), __int_as_float(a1.w));
-        if (L <= 4) {
-            // the usual stacks (the bundled maps have 3 levels): no loop; a slot past the last record re-reads the last
-            // one (min / max do not mind), so there is nothing to predicate
-            const int last = 2 * L - 1;
-#pragma unroll
-            for (int k = 2; k < 8; k++) {
-                const int4 a = __ldg(ag + min(k, last));
-                sky_below = min(sky_below, min(a.x, a.y));
-                fs_max = max(fs_max, a.z);
-            }
-        } else {
-#pragma unroll 2
-            for (int k = 2; k < 2 * L; k++) {
-                const int4 a = __ldg(ag + k);
-                sky_below = min(sky_below, min(a.x, a.y));
-                fs_max = max(fs_max, a.z);
-            }
-        }
-    }
+    int fs_max, sky_below;
+    double zmax_group;  // no column of the group has a z-buffer value above this
+    compose_aggregates(p, view, group, fs_max, sky_below, zmax_group);
 
-    // ---- RUNS (many rows per warp, i.e. large batches and 4K frames), BEFORE anything else of the warp exists: when
-    //      no sprite of the group touches the warp's rows, the leading row pairs that are sky only (above every slice
-    //      of the group) and the trailing ones that are floor only (below every floor start) are written by two tight
-    //      loops.  Inside a run a lane owns 2 adjacent columns x 2 rows, so everything per column — the three
-    //      fast-floor-cast parameters, the box texel columns — is a handful of registers loaded ONCE per run instead
-    //      of six 16 B loads per row pair, both row records are warp-uniform, and none of the general loop's state
-    //      (sprite list, masks, slice spans, per-pixel flags) is live yet: the runs are allocated ~40 registers, not the
-    //      64 the general loop spills at.  The arithmetic is that of the two fast branches of the general loop, value
-    //      for value; whatever a run cannot prove for ALL lanes of a row pair (a nil floor tile, a translucent texel, a
-    //      zero fraction in floor_fast_index, a row beyond the fast cast's weight bound) ends the run, and the general
-    //      loop below takes the row pairs no run has written (bit mask run_done).  A warp whose rows are all done
-    //      returns here: no sprite list, no masks, no per-column records.
+    // ---- RUNS (shapes with many rows per warp), before anything else of the warp exists: the sky-only and floor-only
+    //      row pairs of a warp no sprite touches are written by tight loops (compose_runs).  A warp whose rows are all
+    //      done returns: no sprite list, no masks, no per-column records; the general loop below takes the row pairs no
+    //      run has written (bit mask run_done).
     constexpr bool RUNS = WARP_ROWS >= COMPOSE_RUN_MIN_ROWS;
-    constexpr int N_IT = WARP_ROWS / 2;
     uint32_t run_done = 0u;
-    if (RUNS && !p.force_painter && gx0 + GROUP_COLS <= p.w && (p.w & 3) == 0) {
-        const int4 gi = p.bin_count[view * p.n_groups + group];  // entries, min dsy, max dey
-        if (!(gi.x > 0 && gi.z > wrow0 && gi.y < wrow1)) {
-            const int xa = gx0 + 2 * lane;  // this lane's two columns inside a run
-            const uint32_t tm = (uint32_t)p.tex_size - 1u;
-            uint2 *o = reinterpret_cast<uint2 *>(reinterpret_cast<uint32_t *>(p.out) + ((size_t)view * p.h + wrow0) * p.w + xa);
-            const RowRec *rr = p.row_rec + (size_t)view * p.h + wrow0;
-            const int opitch = p.w >> 1;
-            int it = 0;
-            {   // sky run
-                const int ylim = min(sky_below, p.h) - wrow0;  // row pairs [2 it, 2 it + 1] below this are sky only
-                if (1 < ylim) {
-                    uint32_t u[2];
-#pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        const uint32_t uu = (uint32_t)((((uint64_t)(2 * (int64_t)(xa + j) + 1)) * p.xstep) >> 33);
-                        u[j] = uu > tm ? tm : uu;
-                    }
-#pragma unroll 1
-                    for (; it < N_IT && 2 * it + 1 < ylim; it++) {
-                        uint32_t t[2][2];
-                        bool ok = true;
-#pragma unroll
-                        for (int k = 0; k < 2; k++) {
-                            const uint32_t inf = rr[2 * it + k].info;
-                            const int tile = (inf & 0x40000000u) ? p.sky_tile : p.floorbox_tile;
-                            ok = ok && tile >= 0;
-                            const uint32_t base = ((((uint32_t)max(tile, 0) << p.tex_shift) | (inf & 0xffffu)) << p.tex_shift);
-#pragma unroll
-                            for (int j = 0; j < 2; j++) t[k][j] = __ldg(p.atlas + (base | u[j]));
-                        }
-                        ok = ok && (t[0][0] & t[0][1] & t[1][0] & t[1][1]) >= 0xff000000u;
-                        if (!__all_sync(0xffffffffu, ok)) break;
-#pragma unroll
-                        for (int k = 0; k < 2; k++)
-                            o[(size_t)(2 * it + k) * opitch] = make_uint2(shade_opaque(t[k][0], box_tint), shade_opaque(t[k][1], box_tint));
-                    }
-                }
-            }
-            run_done = (1u << it) - 1u;  // the sky run wrote row pairs [0, it)
-            // floor run: from the first row pair at or below every floor start of the group to the warp's last one
-            it = max(it, (max(fs_max - wrow0, 0) + 1) >> 1);
-            const int it_floor = it;
-            if (it < N_IT && wrow0 + 2 * it + 1 < p.h) {
-                const size_t fa = (size_t)view * p.w + xa;
-                const double2 cw = *reinterpret_cast<const double2 *>(p.flo_dw + fa), cr = *reinterpret_cast<const double2 *>(p.flo_rc + fa);
-                const double2 dx = *reinterpret_cast<const double2 *>(p.flo_dx + fa), dy = *reinterpret_cast<const double2 *>(p.flo_dy + fa);
-                // largest row distance for which both columns keep |weight| <= 4 (negative: a column is not eligible)
-                const double cd_max = (cr.x != 0.0 && cr.y != 0.0) ? 4.0 * fmin(fabs(cw.x), fabs(cw.y)) : -1.0;
-                const double texd_ = (double)p.tex_size;
-                const double ptx = c.pos_x * texd_, pty = c.pos_y * texd_;  // texel-unit camera position
-                const uint32_t bx = (uint32_t)min((uint64_t)p.map_w << p.tex_shift, (uint64_t)0x80000000u);
-                const uint32_t by = (uint32_t)min((uint64_t)p.map_h << p.tex_shift, (uint64_t)0x80000000u);
-                const int last = p.h - 1 - wrow0;  // last existing row of the view, relative to the warp's first
-                RowRec r[2] = {rr[2 * it], rr[2 * it + 1]};
-#pragma unroll 1
-                for (; it < N_IT && 2 * it + 1 <= last; it++) {
-                    const uint32_t tint[2] = {r[0].tint, r[1].tint};
-                    bool ok = (r[0].info & r[1].info & 0x80000000u) && (r[0].info & r[1].info & 0x20000000u) && r[0].cd <= cd_max && r[1].cd <= cd_max;
-                    uint32_t tx[2][2], ty[2][2];
-#pragma unroll
-                    for (int k = 0; k < 2; k++) {
-                        const double w0 = r[k].cd * cr.x, w1 = r[k].cd * cr.y;
-                        ok = floor_fast_index(w0, dx.x, ptx, bx, tx[k][0]) && ok;
-                        ok = floor_fast_index(w0, dy.x, pty, by, ty[k][0]) && ok;
-                        ok = floor_fast_index(w1, dx.y, ptx, bx, tx[k][1]) && ok;
-                        ok = floor_fast_index(w1, dy.y, pty, by, ty[k][1]) && ok;
-                    }
-                    // the next pair's row records are requested before this pair's texels are waited for
-                    r[0] = rr[min(2 * it + 2, last)];
-                    r[1] = rr[min(2 * it + 3, last)];
-                    uint32_t t[2][2] = {{0u, 0u}, {0u, 0u}};
-                    if (ok) {
-                        int ft[2][2];
-#pragma unroll
-                        for (int k = 0; k < 2; k++)
-#pragma unroll
-                            for (int j = 0; j < 2; j++)
-                                ft[k][j] = __ldg(p.floor_tiles + (tx[k][j] >> p.tex_shift) * p.map_h + (ty[k][j] >> p.tex_shift));
-                        if ((ft[0][0] | ft[0][1] | ft[1][0] | ft[1][1]) >= 0) {
-#pragma unroll
-                            for (int k = 0; k < 2; k++)
-#pragma unroll
-                                for (int j = 0; j < 2; j++)
-                                    t[k][j] = __ldg(p.atlas + (((((uint32_t)ft[k][j] << p.tex_shift) | (ty[k][j] & tm)) << p.tex_shift) | (tx[k][j] & tm)));
-                        }
-                    }
-                    ok = (t[0][0] & t[0][1] & t[1][0] & t[1][1]) >= 0xff000000u;  // (all zero when a step above failed)
-                    if (!__all_sync(0xffffffffu, ok)) break;
-#pragma unroll
-                    for (int k = 0; k < 2; k++)
-                        o[(size_t)(2 * it + k) * opitch] = make_uint2(floor_tint(t[k][0], tint[k]), floor_tint(t[k][1], tint[k]));
-                }
-                run_done |= ((1u << it) - 1u) & ~((1u << it_floor) - 1u);  // the floor run wrote row pairs [it_floor, it)
-            }
-            // every row pair written: nothing is left for this warp — unless it owns the screen centre (convergence)
-            const int n_it = (wrow1 - wrow0 + 1) >> 1;
-            const int cx = p.w / 2, cy = p.h / 2;
-            if (run_done == (1u << n_it) - 1u && !(cx >= gx0 && cx < gx0 + GROUP_COLS && cy >= wrow0 && cy < wrow1)) return;
-        }
+    if (RUNS) {
+        run_done = compose_runs<WARP_ROWS>(p, c, view, group, lane, wrow0, wrow1, fs_max, sky_below, box_tint);
+        if (compose_runs_complete(p, run_done, gx0, wrow0, wrow1)) return;
     }
 
     // ---- warp-private sprite list: entries of the group list whose rows intersect this warp's rows
@@ -551,7 +634,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                 const unsigned bal = __ballot_sync(0xffffffffu, (q >> k) & 1u);
                 if (lx_ == k) m = bal;
             }
-            s_xm[warp][wd][lane] = m;
+            xm[wd][lane] = m;
         }
     }
 
@@ -612,17 +695,17 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
 #pragma unroll
             for (int j = 0; j < 4; j++)
 #pragma unroll
-                for (int wq = 0; wq < WARP_WORDS; wq++) s_hit[warp][j][wq][lane] = 0u;
+                for (int wq = 0; wq < WARP_WORDS; wq++) hit[j][wq][lane] = 0u;
             // Latency mode (few rows per warp, single frames).  SB sprites per step: a lane's walk is a chain of
             // dependent loads (record -> texel), so the records and texels of the next few candidates are fetched
             // together and then resolved nearest first.
             int wd = n_words - 1;
-            uint32_t m = s_xm[warp][wd][lane];
+            uint32_t m = xm[wd][lane];
             auto next_sprite = [&]() -> int {  // nearest remaining sprite of this lane that crosses row y, or -1
                 for (;;) {
                     while (m == 0u) {
                         if (--wd < 0) return -1;
-                        m = s_xm[warp][wd][lane];
+                        m = xm[wd][lane];
                     }
                     const int bit = 31 - __clz(m);
                     m &= ~(1u << bit);
@@ -658,7 +741,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                         if ((s_got >> j) & 1u) continue;
                         const uint32_t a = tx[b][j] >> 24;
                         if (a == 255u) { s_top[j] = blend_over(0u, tx[b][j], tint); s_got |= 1u << j; s_stop |= (uint32_t)ids[b] << (8 * j); }
-                        else if (a != 0u) { s_trans |= 1u << j; s_hit[warp][j][ids[b] >> 5][lane] |= 1u << (ids[b] & 31); }
+                        else if (a != 0u) { s_trans |= 1u << j; hit[j][ids[b] >> 5][lane] |= 1u << (ids[b] & 31); }
                     }
                 }
             }
@@ -667,7 +750,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
             // throughput mode (large batches of views): one sprite at a time, no speculative fetches
 #pragma unroll 1
             for (int wd = n_words - 1; wd >= 0; wd--) {
-                uint32_t m = s_xm[warp][wd][lane];
+                uint32_t m = xm[wd][lane];
                 while (m && s_got != full) {
                     const int bit = 31 - __clz(m);
                     m &= ~(1u << bit);
@@ -746,7 +829,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                         uint32_t t[4];
 #pragma unroll
                         for (int j = 0; j < 4; j++)
-                            t[j] = __ldg(p.atlas + (((((uint32_t)ft[j] << p.tex_shift) | (ty[j] & (uint32_t)tmask)) << p.tex_shift) | (tx[j] & (uint32_t)tmask)));
+                            t[j] = atlas_fetch(p, (uint32_t)ft[j], ty[j] & (uint32_t)tmask, tx[j] & (uint32_t)tmask);
                         if ((t[0] & t[1] & t[2] & t[3]) >= 0xff000000u) {
 #pragma unroll
                             for (int j = 0; j < 4; j++) px[j] = floor_tint(t[j], r.tint);
@@ -856,7 +939,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
                 for (int wd = 0; wd < n_words; wd++) {
                     uint32_t hm[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) hm[j] = ((repaint >> j) & 1u) ? s_hit[warp][j][wd][lane] : 0u;
+                    for (int j = 0; j < 4; j++) hm[j] = ((repaint >> j) & 1u) ? hit[j][wd][lane] : 0u;
                     uint32_t m = hm[0] | hm[1] | hm[2] | hm[3];
                     while (m) {
                         const int bit = __ffs(m) - 1;
@@ -877,7 +960,7 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
             } else
 #pragma unroll 1
             for (int wd = 0; wd < n_words; wd++) {
-                uint32_t m = s_xm[warp][wd][lane];
+                uint32_t m = xm[wd][lane];
                 while (m) {
                     const int i = wd * 32 + __ffs(m) - 1;
                     m &= m - 1u;
@@ -920,6 +1003,33 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
             for (int j = 0; j < nvalid; j++) o[j] = px[j];
         }
     }
+}
+
+// COMPOSE_WARPS warps per CTA: 4 for single frames, 2 for large batches (a CTA's slot is held until its slowest warp
+// ends, and small CTAs waste fewer warp slots); MIN_BLOCKS is given for 4-warp CTAs and scaled.
+// LATENCY: single frames with sprites (see the sprite list above)
+template <int WARP_ROWS, int MIN_BLOCKS, int COMPOSE_WARPS, bool LATENCY = false>
+__global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_WARPS) k_compose(const __grid_constant__ ComposeParams p) {
+    constexpr int COMPOSE_ROWS = COMPOSE_WARPS * WARP_ROWS;
+    constexpr int MAX_WARP_SPRITES = LATENCY ? LATENCY_LIST : COMPOSE_TP_LIST;
+    constexpr int WARP_WORDS = MAX_WARP_SPRITES / 32;
+    // the 64-register / 8-CTA shapes (frames sharing the chip: PM3D_OPT_LANES > 1) walk one sprite per step: the second
+    // sprite's records and texels in flight cost them spills, and the other lanes' warps hide the latency anyway
+    // (c2, 4 lanes: 55.6 k -> 62.1 k frames/s; a frame that has the chip to itself is the same either way)
+    constexpr int SB = (LATENCY && MIN_BLOCKS >= 8) ? 1 : SPRITE_BATCH;
+    __shared__ WarpList<MAX_WARP_SPRITES, LATENCY> s_list[COMPOSE_WARPS];
+    __shared__ uint32_t s_xm[COMPOSE_WARPS][WARP_WORDS][32];  // per-lane sprite masks (kept out of registers and out of unrolled code)
+    // latency mode: per pixel, the listed sprites whose texel was TRANSLUCENT in the front-to-back walk (bit = list
+    // index).  The repaint of such a pixel blends exactly these over its opaque base instead of testing every sprite
+    // of the lane again (the bundled trees are mostly fully transparent texels around a few translucent ones)
+    __shared__ uint32_t s_hit[LATENCY ? COMPOSE_WARPS : 1][4][LATENCY ? WARP_WORDS : 1][32];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int view = p.row_major ? blockIdx.y : blockIdx.z;
+    const int yblock = compose_yblock(p.h, p.views[view].pitch_px, COMPOSE_ROWS, p.row_major ? gridDim.z : gridDim.y, p.row_major ? blockIdx.z : blockIdx.y);
+    const int wrow0 = yblock * COMPOSE_ROWS + warp * WARP_ROWS;
+    if (wrow0 >= p.h) return;
+    compose_warp<WARP_ROWS, LATENCY, SB, MAX_WARP_SPRITES>(p, s_list[warp], s_xm[warp], s_hit[LATENCY ? warp : 0], blockIdx.x, view, wrow0, lane);
 }
 
 // ---- per-view FNV-1a style checksum (order-independent combine of per-word hashes: a sum mod 2^64, so the split
@@ -983,6 +1093,7 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     p.w = ctx->w; p.h = ctx->h; p.num_levels = ctx->num_levels; p.tex_size = ctx->tex_size; p.tex_shift = ctx->tex_shift;
     p.map_w = ctx->map_w; p.map_h = ctx->map_h; p.n_groups = ctx->n_groups;
     p.sky_tile = ctx->sky_tile; p.floorbox_tile = ctx->floorbox_tile; p.force_painter = ctx->force_painter;
+    p.row_major = 0;
     // rows per warp: enough warps to fill the chip a few times over, otherwise as long as possible
     const long long warps8 = (long long)ctx->n_groups * ((ctx->h + 7) / 8) * n_views;
     const long long resident = (long long)ctx->sm_count * 24;
@@ -1006,10 +1117,20 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     }
     const int cta_warps = rows >= 8 ? 2 : 4;
     const bool with_sprites = ctx->cur_n_sprites > 0;  // latency-mode sprite walk (records in shared memory)
-    dim3 block(cta_warps * 32), grid(ctx->n_groups, (ctx->h + cta_warps * rows - 1) / (cta_warps * rows), n_views);
+    dim3 block(cta_warps * 32), grid(ctx->n_groups, (ctx->h + cta_warps * rows - 1) / (cta_warps * rows), n_views);  // (x, row blocks, views)
     cudaStream_t cstream = ctx->cur_cstream ? ctx->cur_cstream : ctx->stream;  // the lane of this frame batch
     pm3d_kt_mark(ctx, 2, 0, cstream);
-    if (rows == 16) k_compose<16, 8, 2><<<grid, block, 0, cstream>>>(p);
+    // batches of views are issued ROW BLOCK BY ROW BLOCK from the horizon outwards, every view's block of one rank
+    // before any block of the next: the horizon blocks carry the sprites and the mixed rows — 5 to 30 times the time of
+    // a sky or floor block (per-task timings: mean 56 us, up to 0.9 ms, against 7 us) — and issued view by view the
+    // last views' horizon blocks were a tail of a few dozen busy warps a third as long as the whole launch
+    p.row_major = n_views > 1 && n_views <= 65535;
+    if (p.row_major) grid = dim3(grid.x, n_views, grid.y);
+    if (rows == 16) {
+        const int yb = (ctx->h + COMPOSE_TP_WARPS * 16 - 1) / (COMPOSE_TP_WARPS * 16);
+        dim3 g16 = p.row_major ? dim3(ctx->n_groups, n_views, yb) : dim3(ctx->n_groups, yb, n_views);
+        k_compose<16, 8, COMPOSE_TP_WARPS><<<g16, COMPOSE_TP_WARPS * 32, 0, cstream>>>(p);
+    }
     else if (rows == 8 && minb == 8) k_compose<8, 8, 2><<<grid, block, 0, cstream>>>(p);
     else if (rows == 8) k_compose<8, 6, 2><<<grid, block, 0, cstream>>>(p);
     else if (rows == 4 && minb == 8) k_compose<4, 8, 4><<<grid, block, 0, cstream>>>(p);

@@ -235,6 +235,61 @@ def test_warp_list_overflow_in_both_sprite_modes(gpu_ctx, rows, monkeypatch):
     assert np.array_equal(fast, slow)
 
 
+@pytest.mark.parametrize("rows", [8, 16])
+@pytest.mark.parametrize("case", ["plain", "floor_holes", "translucent_floor", "translucent_sky", "no_boxes", "odd_height", "ragged_width", "short_render_distance"])
+def test_sky_and_floor_runs(gpu_ctx, rows, case, monkeypatch):
+    """The >= 8-row shapes write sky-only / floor-only row pairs in tight runs ahead of the general row loop
+    (k_compose_runs: 2 columns x 2 rows per lane, row records by shuffle).  Whatever ends a run — nil floor tiles, a
+    translucent floor or sky texel, rows beyond the render distance, a missing sky / floor box, a last row without a
+    partner, a partial 64-column group — must hand the row pair to the general loop: frames equal the oracle's and
+    the literal painter's, with sprites only on some of the views (a view's sprite rows take no runs)."""
+    scene = edge_scene()
+    w, h, rd = 256, 160, -1.0
+    if case == "floor_holes":
+        scene.floor_tiles = scene.floor_tiles.copy()
+        scene.floor_tiles[::3, ::2] = -1
+        scene.floor_tiles[7:11, :] = -1
+    elif case == "translucent_floor":
+        scene.atlas = scene.atlas.copy()
+        ft = int(scene.floor_tiles[scene.floor_tiles >= 0][0])
+        scene.atlas[ft, 10:40, 20:50, 3] = 128
+        scene.atlas[ft, 100:110, :, 3] = 0
+        scene.atlas[ft, 10:40, 20:50, :3] //= 2     # keep it premultiplied
+        scene.atlas[ft, 100:110, :, :3] = 0
+    elif case == "translucent_sky":
+        scene.atlas = scene.atlas.copy()
+        scene.atlas[scene.sky_tile, 5:60, 30:90, 3] = 200
+        scene.atlas[scene.sky_tile, 5:60, 30:90, :3] = np.minimum(scene.atlas[scene.sky_tile, 5:60, 30:90, :3], 200)
+    elif case == "no_boxes":
+        scene.sky_tile = scene.floorbox_tile = -1
+    elif case == "odd_height":
+        h = 161
+    elif case == "ragged_width":
+        w = 300
+    elif case == "short_render_distance":
+        rd = 4.0
+    poses = [(5.5, 5.5, 0.5, 0.9, 0.0), (12.5, 8.5, 0.5, 5.5, 0.1), (5.5, 5.5, 0.05, 1.1, -math.pi / 8),
+             (5.5, 5.5, 2.9, 2.2, math.pi / 4), (20.5, 14.5, 0.5, 3.6, -0.2), (1.5, 1.5, 0.5, 0.8, 0.3)]
+    views = W.make_views(scene, w, h, poses, render_distance=rd)
+    xyzs = np.array([[8.5, 7.5, 0.0, 0.8], [7.0, 6.2, 0.3, 0.5], [14.0, 9.0, 0.0, 1.2]])
+    spr = W.sprite_records(xyzs, np.array([0, 2, 1], np.int32), np.array([0, 1, 0], np.uint8), scene.sheets)
+    counts = [3, 0, 3, 0, 0, 3]
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    sprites = np.concatenate([spr if k else spr[:0] for k in counts])
+    monkeypatch.setenv("PM3D_COMPOSE_ROWS", str(rows))
+    got, want = render_both(gpu_ctx, scene, w, h, views, sprites, off, keep_columns=False)
+    for i, ref in enumerate(want):
+        assert_frame_equal(got["rgba"][i], ref["rgba"], f"{case} rows {rows} view {i}")
+        assert int(got["conv"][i]["sprite"]) == ref["convergence"]["sprite"]
+    fast = got["rgba"].copy()
+    gpu_ctx.set_option(pm3d._lib.OPT_FORCE_PAINTER, 1)
+    try:
+        slow = gpu_ctx.render(views, sprites, off)["rgba"].copy()
+    finally:
+        gpu_ctx.set_option(pm3d._lib.OPT_FORCE_PAINTER, 0)
+    assert np.array_equal(fast, slow)
+
+
 @pytest.mark.parametrize("rows,minb", [(2, 6), (2, 8), (4, 6), (4, 8), (8, 6), (8, 8), (16, 8)])
 def test_every_compose_instantiation_gives_the_same_frame(gpu_ctx, rows, minb, monkeypatch):
     """The launcher picks rows-per-warp, CTA shape and latency/throughput sprite stage by problem size; every

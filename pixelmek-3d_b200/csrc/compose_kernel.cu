@@ -33,10 +33,16 @@
 #include "pm3d_internal.cuh"
 
 #ifndef COMPOSE_RUN_MIN_ROWS
-#define COMPOSE_RUN_MIN_ROWS 8  // shapes with at least this many rows per warp take sky / floor runs (see RUNS in the kernel)
+#define COMPOSE_RUN_MIN_ROWS 2  // shapes with at least this many rows per warp take sky / floor runs: all of them (a 2-row warp is one row pair)
 #endif
 #ifndef COMPOSE_TP_LIST
 #define COMPOSE_TP_LIST 256  // warp-private sprite list of the throughput shapes (entries)
+#endif
+#ifndef COMPOSE_TP_LATENCY_LIST
+#define COMPOSE_TP_LATENCY_LIST 32  // sprite list of the >= 8-row shapes in latency mode (records in shared memory): 3.5 KB per warp
+#endif
+#ifndef COMPOSE_TP_LATENCY
+#define COMPOSE_TP_LATENCY 1        // batches with sprites: the >= 8-row shapes walk sprites in latency mode
 #endif
 #ifndef COMPOSE_TP_WARPS
 #define COMPOSE_TP_WARPS 1   // warps per CTA of the 16-row shape (large batches): a slot is not held for a slower sibling warp
@@ -1011,7 +1017,7 @@ __device__ __forceinline__ void compose_warp(const ComposeParams &p, WarpList<MA
 template <int WARP_ROWS, int MIN_BLOCKS, int COMPOSE_WARPS, bool LATENCY = false>
 __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_WARPS) k_compose(const __grid_constant__ ComposeParams p) {
     constexpr int COMPOSE_ROWS = COMPOSE_WARPS * WARP_ROWS;
-    constexpr int MAX_WARP_SPRITES = LATENCY ? LATENCY_LIST : COMPOSE_TP_LIST;
+    constexpr int MAX_WARP_SPRITES = LATENCY ? (WARP_ROWS >= 8 ? COMPOSE_TP_LATENCY_LIST : LATENCY_LIST) : COMPOSE_TP_LIST;
     constexpr int WARP_WORDS = MAX_WARP_SPRITES / 32;
     // the 64-register / 8-CTA shapes (frames sharing the chip: PM3D_OPT_LANES > 1) walk one sprite per step: the second
     // sprite's records and texels in flight cost them spills, and the other lanes' warps hide the latency anyway
@@ -1129,8 +1135,10 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     if (rows == 16) {
         const int yb = (ctx->h + COMPOSE_TP_WARPS * 16 - 1) / (COMPOSE_TP_WARPS * 16);
         dim3 g16 = p.row_major ? dim3(ctx->n_groups, n_views, yb) : dim3(ctx->n_groups, yb, n_views);
-        k_compose<16, 8, COMPOSE_TP_WARPS><<<g16, COMPOSE_TP_WARPS * 32, 0, cstream>>>(p);
+        if (with_sprites && COMPOSE_TP_LATENCY) k_compose<16, 8, COMPOSE_TP_WARPS, true><<<g16, COMPOSE_TP_WARPS * 32, 0, cstream>>>(p);
+        else k_compose<16, 8, COMPOSE_TP_WARPS><<<g16, COMPOSE_TP_WARPS * 32, 0, cstream>>>(p);
     }
+    else if (rows == 8 && minb == 8 && with_sprites && COMPOSE_TP_LATENCY) k_compose<8, 8, 2, true><<<grid, block, 0, cstream>>>(p);
     else if (rows == 8 && minb == 8) k_compose<8, 8, 2><<<grid, block, 0, cstream>>>(p);
     else if (rows == 8) k_compose<8, 6, 2><<<grid, block, 0, cstream>>>(p);
     else if (rows == 4 && minb == 8) k_compose<4, 8, 4><<<grid, block, 0, cstream>>>(p);

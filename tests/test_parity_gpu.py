@@ -235,11 +235,11 @@ def test_warp_list_overflow_in_both_sprite_modes(gpu_ctx, rows, monkeypatch):
     assert np.array_equal(fast, slow)
 
 
-@pytest.mark.parametrize("rows", [8, 16])
+@pytest.mark.parametrize("rows", [2, 4, 8, 16])
 @pytest.mark.parametrize("case", ["plain", "floor_holes", "translucent_floor", "translucent_sky", "no_boxes", "odd_height", "ragged_width", "short_render_distance"])
 def test_sky_and_floor_runs(gpu_ctx, rows, case, monkeypatch):
-    """The >= 8-row shapes write sky-only / floor-only row pairs in tight runs ahead of the general row loop
-    (k_compose_runs: 2 columns x 2 rows per lane, row records by shuffle).  Whatever ends a run — nil floor tiles, a
+    """Every shape writes the sky-only / floor-only row pairs of a sprite-free warp in tight runs ahead of the general
+    row loop (compose_runs: 2 columns x 2 rows per lane, row records by shuffle).  Whatever ends a run — nil floor tiles, a
     translucent floor or sky texel, rows beyond the render distance, a missing sky / floor box, a last row without a
     partner, a partial 64-column group — must hand the row pair to the general loop: frames equal the oracle's and
     the literal painter's, with sprites only on some of the views (a view's sprite rows take no runs)."""

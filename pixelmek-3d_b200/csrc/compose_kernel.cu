@@ -1104,10 +1104,10 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     const long long warps8 = (long long)ctx->n_groups * ((ctx->h + 7) / 8) * n_views;
     const long long resident = (long long)ctx->sm_count * 24;
     int rows = warps8 >= 64 * resident ? 16 : (warps8 >= 4 * resident ? 8 : (warps8 >= 2 * resident ? 4 : 2));  // 4K single frame: 8
-    // with sprites a mid-size batch (a few hundred to ~900 views of 320x200) is better off in the latency-mode sprite
-    // walk of the 4-row shape: the throughput-mode walk of the 8-row shape repaints translucent pixels sprite by sprite
-    // (512 views with the bundled trees: 294 -> 256 us, 256 views: 233 -> 169 us)
-    if (ctx->cur_n_sprites > 0 && rows == 8 && warps8 < 32 * resident) rows = 4;
+    // with sprites a small batch (up to ~350 views of 320x200) is better off with the 4-row warps of the single-frame
+    // shapes (more, shorter warps for the sprite-heavy horizon rows); from there on the 8-row shape, which walks sprites
+    // in latency mode too (256 views: 4 rows 99 us, 8 rows 122 us; 512 views: 168 / 152 us; 1024 views: 304 / 256 us)
+    if (ctx->cur_n_sprites > 0 && rows == 8 && warps8 < 12 * resident) rows = 4;
     // 64 registers / 8 CTAs per SM for the >= 8-row (large batch) shapes, and for single frames when several of them
     // share the chip (PM3D_OPT_LANES > 1): a few spills buy a third more resident warps, which is what hides the texel
     // latency at saturation (3-4 lanes: +12 % frames/s); a frame that has the chip to itself is 3 % faster with 80

@@ -154,6 +154,12 @@ __device__ bool any_hit(const LosParams &p, const double4 &ray) {
 #ifndef LOS_LANE_CAP
 #define LOS_LANE_CAP 8
 #endif
+#ifndef LOS_MAX_SPLIT_SHIFT
+#define LOS_MAX_SPLIT_SHIFT 6  // the exact second pass cuts a ray into at most 2^6 parts (see k_los)
+#endif
+#ifndef LOS_SPLIT_ROUNDS
+#define LOS_SPLIT_ROUNDS 4     // ... as long as the parts are no more than this many per lane of the grid
+#endif
 #ifndef LOS_MIN_BLOCKS
 #define LOS_MIN_BLOCKS 4
 #endif
@@ -161,10 +167,19 @@ __global__ void __launch_bounds__(LOS_THREADS, LOS_MIN_BLOCKS) k_los(LosParams p
     const int lane = threadIdx.x & 31;
     const long long warp_id = (long long)blockIdx.x * (LOS_THREADS / 32) + (threadIdx.x >> 5);
     long long n_work = p.n;
+    // Second pass (p.list): the rays k_los_fast could not decide; their number is only known on the device.  A ray's
+    // walk is a chain of a few hundred dependent cell steps (~130 us for a ray across the map, however few rays are
+    // left), and "blocked" is an OR over its cells — so when the list is shorter than the grid is wide, every ray is
+    // cut into 2^kshift PARTS at the parameters k / 2^kshift, each part walks the cells of its own sub-segment and runs
+    // the exact predicate on the WHOLE ray.  The parts of a ray meet at bitwise identical points, a sub-segment's
+    // cells are those of the ray up to the rounding of its end points (1e-13 against the bins' 1e-3 dilation,
+    // pm3d_upload_segments), and the answer byte holds "visible" from the first pass: a part that finds a hit clears it.
+    int kshift = 0;
     if (p.list) {
-        // second pass: the rays k_los_fast could not decide; their number is only known on the device
-        n_work = (long long)*p.list_count;
+        const long long n_rays = (long long)*p.list_count;
         const long long warps = (long long)gridDim.x * (LOS_THREADS / 32);
+        while (kshift < LOS_MAX_SPLIT_SHIFT && (n_rays << (kshift + 1)) <= warps * 32 * LOS_SPLIT_ROUNDS) kshift++;
+        n_work = n_rays << kshift;
         rays_per_warp = (n_work + warps - 1) / warps;
         if (rays_per_warp < 32) rays_per_warp = 32;
     }
@@ -210,26 +225,32 @@ __global__ void __launch_bounds__(LOS_THREADS, LOS_MIN_BLOCKS) k_los(LosParams p
             const long long mine = next + __popc(idle & ((1u << lane) - 1u));
             next += __popc(idle);
             if (!active && mine < end) {
-                idx = p.list ? (long long)p.list[mine] : mine;
+                idx = p.list ? (long long)p.list[mine >> kshift] : mine;
+                const int part = (int)(mine & ((1ll << kshift) - 1)), n_parts = 1 << kshift;
                 ray = p.rays[idx];
                 lr = go_rect(go_int(ray.x), go_int(ray.y), go_int(ray.z), go_int(ray.w));
                 const bool inside = ray.x >= gx0 && ray.x < gx1 && ray.z >= gx0 && ray.z < gx1 && ray.y >= gy0 &&
                                     ray.y < gy1 && ray.w >= gy0 && ray.w < gy1;
                 if (!inside) {
-                    // not finite, or leaves the binned area: every segment is a candidate
+                    // not finite, or leaves the binned area: every segment is a candidate (the first part takes them all)
                     bool hit = false;
-                    for (int id = 0; id < p.n_segs && !hit; id++) hit = test(id);
-                    p.out_flag[idx] = hit ? 0 : 1;
+                    for (int id = 0; id < p.n_segs && !hit && part == 0; id++) hit = test(id);
+                    if (hit) p.out_flag[idx] = 0;
+                    else if (!p.list) p.out_flag[idx] = 1;
                 } else {
-                    const double fx = floor(ray.x), fy = floor(ray.y);
+                    // this part's sub-segment (the whole ray when it is not split; the ray's own end points at its ends)
+                    const double t0 = (double)part / (double)n_parts, t1 = (double)(part + 1) / (double)n_parts;
+                    const double ax = part == 0 ? ray.x : ray.x + t0 * (ray.z - ray.x), ay = part == 0 ? ray.y : ray.y + t0 * (ray.w - ray.y);
+                    const double bx = part == n_parts - 1 ? ray.z : ray.x + t1 * (ray.z - ray.x), by = part == n_parts - 1 ? ray.w : ray.y + t1 * (ray.w - ray.y);
+                    const double fx = floor(ax), fy = floor(ay);
                     cx = (int)fx - p.bin_x0; cy = (int)fy - p.bin_y0;
-                    ex = (int)floor(ray.z) - p.bin_x0; ey = (int)floor(ray.w) - p.bin_y0;
-                    const double dx = ray.z - ray.x, dy = ray.w - ray.y;
+                    ex = (int)floor(bx) - p.bin_x0; ey = (int)floor(by) - p.bin_y0;
+                    const double dx = bx - ax, dy = by - ay;
                     sx = dx > 0 ? 1 : -1; sy = dy > 0 ? 1 : -1;
                     inv_dx = dx != 0 ? 1.0 / fabs(dx) : 0.0;
                     inv_dy = dy != 0 ? 1.0 / fabs(dy) : 0.0;
-                    tx = dx != 0 ? (dx > 0 ? (fx + 1.0 - ray.x) : (ray.x - fx)) * inv_dx : 1e300;
-                    ty = dy != 0 ? (dy > 0 ? (fy + 1.0 - ray.y) : (ray.y - fy)) * inv_dy : 1e300;
+                    tx = dx != 0 ? (dx > 0 ? (fx + 1.0 - ax) : (ax - fx)) * inv_dx : 1e300;
+                    ty = dy != 0 ? (dy > 0 ? (fy + 1.0 - ay) : (ay - fy)) * inv_dy : 1e300;
                     steps = abs(ex - cx) + abs(ey - cy);
                     cur = __ldg(p.cell_rec + cy * p.bin_w + cx);
                     cbase = 0;
@@ -317,7 +338,7 @@ __global__ void __launch_bounds__(LOS_THREADS, LOS_MIN_BLOCKS) k_los(LosParams p
             } else if (left > n_put) {
                 cbase += n_put;  // more candidates in this cell than one round takes
             } else if (!more) {
-                p.out_flag[idx] = 1;
+                if (!p.list) p.out_flag[idx] = 1;  // (second pass: the first pass wrote "visible unless a part finds a hit")
                 active = false;
             } else {
                 steps--;
@@ -462,7 +483,7 @@ __global__ void __launch_bounds__(LOSF_THREADS, 2) k_los_fast(LosParams p, long 
                     const bool xs = (tX < tY) ? (nx > 0) : (ny == 0);
                     result = crossing_inside(xs, nx, ny) ? 0 : 2;
                 }
-                if (result < 2) p.out_flag[idx] = (uint8_t)result;
+                p.out_flag[idx] = result == 0 ? 0 : 1;  // undecided (2): visible unless the exact pass finds a hit
             }
             const unsigned und = __ballot_sync(0xffffffffu, result == 2);
             if (und) {

@@ -89,6 +89,9 @@ struct ComposeParams {
     uint64_t xstep;  // span_step(tex_size, w): box texel column of screen column x
     int w, h, num_levels, tex_size, tex_shift, map_w, map_h, n_groups, sky_tile, floorbox_tile, force_painter;
     int row_major;  // grid = (groups, views, row blocks) instead of (groups, row blocks, views)
+#ifdef PM3D_COMPOSE_STATS
+    unsigned long long *task_log;  // tools builds: per warp {start ns, end ns, SM, first row} (tools/exp_tasklog.py)
+#endif
 };
 
 // texel (tx, ty) of atlas tile `tile`
@@ -1035,7 +1038,21 @@ __global__ void __launch_bounds__(COMPOSE_WARPS * 32, MIN_BLOCKS * 4 / COMPOSE_W
     const int yblock = compose_yblock(p.h, p.views[view].pitch_px, COMPOSE_ROWS, p.row_major ? gridDim.z : gridDim.y, p.row_major ? blockIdx.z : blockIdx.y);
     const int wrow0 = yblock * COMPOSE_ROWS + warp * WARP_ROWS;
     if (wrow0 >= p.h) return;
+#ifdef PM3D_COMPOSE_STATS
+    unsigned long long t0 = 0;
+    if (p.task_log) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+#endif
     compose_warp<WARP_ROWS, LATENCY, SB, MAX_WARP_SPRITES>(p, s_list[warp], s_xm[warp], s_hit[LATENCY ? warp : 0], blockIdx.x, view, wrow0, lane);
+#ifdef PM3D_COMPOSE_STATS
+    __syncwarp();
+    if (p.task_log && lane == 0) {
+        unsigned long long t1; unsigned int sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        unsigned long long *e = p.task_log + 4 * ((((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * COMPOSE_WARPS + warp);
+        e[0] = t0; e[1] = t1; e[2] = sm; e[3] = (unsigned long long)wrow0;
+    }
+#endif
 }
 
 // ---- per-view FNV-1a style checksum (order-independent combine of per-word hashes: a sum mod 2^64, so the split
@@ -1132,6 +1149,13 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     // last views' horizon blocks were a tail of a few dozen busy warps a third as long as the whole launch
     p.row_major = n_views > 1 && n_views <= 65535;
     if (p.row_major) grid = dim3(grid.x, n_views, grid.y);
+#ifdef PM3D_COMPOSE_STATS
+    // tools builds only: PM3D_COMPOSE_LOG=path dumps per-warp start / end times of this launch (it synchronises)
+    p.task_log = nullptr;
+    const char *log_path = getenv("PM3D_COMPOSE_LOG");
+    const size_t log_warps = (size_t)ctx->n_groups * ((ctx->h + rows - 1) / rows + 4) * n_views;
+    if (log_path) { PM3D_CUDA(ctx, cudaMalloc((void **)&p.task_log, log_warps * 32)); PM3D_CUDA(ctx, cudaMemset(p.task_log, 0, log_warps * 32)); }
+#endif
     if (rows == 16) {
         const int yb = (ctx->h + COMPOSE_TP_WARPS * 16 - 1) / (COMPOSE_TP_WARPS * 16);
         dim3 g16 = p.row_major ? dim3(ctx->n_groups, n_views, yb) : dim3(ctx->n_groups, yb, n_views);
@@ -1149,6 +1173,15 @@ int pm3d_launch_compose(pm3d_ctx *ctx, int n_views, uint8_t *out) {
     else if (with_sprites) k_compose<2, 6, 4, true><<<grid, block, 0, cstream>>>(p);
     else k_compose<2, 6, 4><<<grid, block, 0, cstream>>>(p);
     pm3d_kt_mark(ctx, 2, 1, cstream);
+#ifdef PM3D_COMPOSE_STATS
+    if (p.task_log) {
+        std::vector<unsigned long long> hlog(log_warps * 4);
+        PM3D_CUDA(ctx, cudaStreamSynchronize(cstream));
+        PM3D_CUDA(ctx, cudaMemcpy(hlog.data(), p.task_log, hlog.size() * 8, cudaMemcpyDeviceToHost));
+        if (FILE *f = fopen(log_path, "wb")) { fwrite(hlog.data(), 8, hlog.size(), f); fclose(f); }
+        cudaFree(p.task_log);
+    }
+#endif
     ctx->launches++;
     PM3D_CUDA(ctx, cudaGetLastError());
     return PM3D_OK;

@@ -1,4 +1,5 @@
-"""Per-task timings of one persistent compose launch (library built with -DPM3D_COMPOSE_STATS; PM3D_COMPOSE_LOG=path):
+"""Per-warp task timings of one compose launch (library built with -DPM3D_COMPOSE_STATS, e.g. tools/build_variant.sh stats
+-DPM3D_COMPOSE_STATS; PM3D_COMPOSE_LOG=path python tools/prof_batch.py 4096 1):
     python tools/exp_tasklog.py gpurun_out/tasklog.bin"""
 import sys, numpy as np
 a = np.fromfile(sys.argv[1], dtype=np.uint64).reshape(-1, 4)

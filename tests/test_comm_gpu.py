@@ -72,7 +72,16 @@ def run_rank(rank, world, uid, cfg, views, sprites, offsets, w, h, segs, rays, o
         ctx.sync()
         vis = np.zeros(len(rays), dtype=np.uint8)
         ctx.d2h(vis, d_all)
-        out[rank] = (conv, sums, vis)
+        # a batch whose shards are whole 32-ray words travels as bits (k_pack_bits / k_unpack_bits); twice: staging reuse
+        n2 = 98304
+        lo, hi = shard.ray_shard(n2, rank, world)
+        ctx.h2d(d_r, rays[lo:hi])
+        for _ in range(2):
+            ctx.comm_los_batch(d_r, hi - lo, n2, d_all)
+        ctx.sync()
+        vis2 = np.zeros(n2, dtype=np.uint8)
+        ctx.d2h(vis2, d_all)
+        out[rank] = (conv, sums, vis, vis2)
         ctx.close()
     except Exception as e:  # surfaced by the caller
         out[rank] = e
@@ -96,10 +105,11 @@ def test_comm_ranks_gather_every_view_and_ray(gpu_ctx, world):
     for r in range(world):
         if isinstance(out[r], Exception):
             raise out[r]
-        conv, sums, vis = out[r]
+        conv, sums, vis, vis2 = out[r]
         assert conv.tobytes() == want_conv.tobytes(), f"rank {r}: convergence records differ"
         assert np.array_equal(sums, want_sums), f"rank {r}: checksums differ"
         assert np.array_equal(vis, want_vis), f"rank {r}: LOS answers differ"
+        assert np.array_equal(vis2, want_vis[:len(vis2)]), f"rank {r}: LOS answers of the bit-packed gather differ"
     assert 0 < want_vis.sum() < len(rays)
 
 

@@ -205,7 +205,7 @@ def sweep_c4(ctx, rank, world, dist, torch, dev):
     for _ in range(3):
         call()
     ctx.sync()
-    reps = 5
+    reps = 10   # (a sweep is 0.3 - 1.3 ms: ten of them dilute the ranks' skew at the start of the timed region)
     if world > 1:
         dist.barrier()
     ctx.flush_l2()
@@ -322,7 +322,7 @@ def sweep_c5(ctx, rank, world, dist, torch, dev):
     ctx.sync()
     if world > 1:
         dist.barrier()
-    reps = 3
+    reps = 10   # (a batch is 0.2 - 0.75 ms)
     ctx.timer_start(3)
     for _ in range(reps):
         call()

@@ -8,6 +8,11 @@
 // the struct-of-arrays the cast wrote (a lane's four columns are one contiguous 32/64 B load,
 // L1-resident after the first row pair), and the only shared memory is a warp-private list of
 // the sprites that touch the warp's rows.
+// Before any of that exists, a warp no sprite touches writes its sky-only and floor-only row pairs
+// in two tight loops with their own mapping (compose_runs: 2 columns x 2 rows per lane, per-column
+// parameters in registers, row records by shuffle) and returns if nothing is left; compose_warp is
+// the general path for what remains.  Batches of views issue their row blocks horizon-first across
+// ALL views (pm3d_launch_compose): the horizon blocks are the expensive ones.
 //
 // Layer order is the reference's painter's order (DESIGN.md "frame composition"):
 //   sky / floor box -> walls (top level .. 0) -> textured floor -> sprites far .. near.
@@ -54,11 +59,12 @@
 #define COMPOSE_FLOOR_NP 1  // row pairs per step of a floor run
 #endif
 
-// rows per warp (WARP_ROWS, a template parameter: 2, 4 or 8 = 1, 2 or 4 iterations of 2 rows) trades the
+// rows per warp (WARP_ROWS, a template parameter: 2, 4, 8 or 16 = 1 .. 8 iterations of 2 rows) trades the
 // per-warp prologue against the length of the serial chain: single frames want many short warps, large
 // batches of views want few long ones.
-// Warp-private sprite list.  Throughput mode (many rows per warp, large batches): up to 256 entries, the draw records
-// stay in global memory.  Latency mode (single frames with sprites): up to LATENCY_LIST entries whose record prefix (everything
+// Warp-private sprite list.  Throughput mode (batches without sprites to speak of): up to 256 entries, the draw records
+// stay in global memory.  Latency mode (frames and batches with sprites): up to LATENCY_LIST (2/4-row shapes) or
+// COMPOSE_TP_LATENCY_LIST (8/16-row shapes) entries whose record prefix (everything
 // sprite_index reads: the first 80 bytes of a DrawRec) is copied to shared memory while the list is built, so the
 // lanes' front-to-back walks — chains of dependent loads on the rows where sprites pile up, the slowest warps of the
 // launch — read their records with an LDS instead of an L2 round trip.

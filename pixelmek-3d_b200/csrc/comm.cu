@@ -12,6 +12,7 @@
 // between the compute and the gather.
 #include <dlfcn.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -152,9 +153,12 @@ __global__ void k_unpack_bits(const uint32_t *words, uint8_t *bytes, int64_t n_w
     reinterpret_cast<uint4 *>(bytes)[2 * i + 1] = make_uint4(v[4], v[5], v[6], v[7]);
 }
 // equal shards of whole 32-ray words in a 16 B aligned array, more than one rank
+// (PM3D_COMM_FORCE_BITS=1, a test override: a single rank packs, gathers and unpacks its own range too, so that one GPU
+//  exercises both kernels)
+static bool force_bits() { const char *e = getenv("PM3D_COMM_FORCE_BITS"); return e && atoi(e) != 0; }
 bool rays_packable(const pm3d_ctx *ctx, const uint8_t *d_all, int64_t n_global) {
     const int n = ctx->comm_size;
-    return n > 1 && n_global % n == 0 && (n_global / n) % 32 == 0 && ((uintptr_t)d_all & 15u) == 0;
+    return (n > 1 || force_bits()) && n_global % n == 0 && (n_global / n) % 32 == 0 && ((uintptr_t)d_all & 15u) == 0;
 }
 int rays_gather_packed(pm3d_ctx *ctx, NcclApi *api, uint8_t *d_all, int64_t n_global) {
     const int n = ctx->comm_size;
@@ -164,7 +168,8 @@ int rays_gather_packed(pm3d_ctx *ctx, NcclApi *api, uint8_t *d_all, int64_t n_gl
     if ((rc = ensure_buf(ctx, &ctx->comm_recv, &ctx->comm_recv_bytes, (size_t)all_words * 4))) return rc;
     k_pack_bits<<<(unsigned)((words + 255) / 256), 256, 0, ctx->stream>>>(d_all + cnt * ctx->comm_rank, (uint32_t *)ctx->comm_send, words);
     PM3D_NCCL(ctx, api, api->AllGather(ctx->comm_send, ctx->comm_recv, (size_t)words * 4, NCCL_UINT8, (ncclComm_t)ctx->comm, ctx->stream));
-    k_unpack_bits<<<(unsigned)((all_words + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t *)ctx->comm_recv, d_all, all_words, words * ctx->comm_rank, words * (ctx->comm_rank + 1));
+    const bool own_too = n == 1;  // (forced single rank: nothing else to unpack)
+    k_unpack_bits<<<(unsigned)((all_words + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t *)ctx->comm_recv, d_all, all_words, own_too ? 0 : words * ctx->comm_rank, own_too ? 0 : words * (ctx->comm_rank + 1));
     ctx->launches += 2;
     PM3D_CUDA(ctx, cudaGetLastError());
     return PM3D_OK;

@@ -88,9 +88,11 @@ def run_rank(rank, world, uid, cfg, views, sprites, offsets, w, h, segs, rays, o
 
 
 @pytest.mark.parametrize("world", [1, 2, 3])
-def test_comm_ranks_gather_every_view_and_ray(gpu_ctx, world):
+def test_comm_ranks_gather_every_view_and_ray(gpu_ctx, world, monkeypatch):
     if n_devices() < world:
         pytest.skip(f"needs {world} GPUs")
+    if world == 1:
+        monkeypatch.setenv("PM3D_COMM_FORCE_BITS", "1")   # one rank packs / unpacks its own answers too
     w, h = 160, 100
     cfg, views, sprites, offsets = small_batch(37, w, h)
     want_conv, want_sums = single_gpu_results(gpu_ctx, cfg, views, sprites, offsets, w, h)

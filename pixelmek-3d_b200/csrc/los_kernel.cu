@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(LOS_THREADS, LOS_MIN_BLOCKS) k_los(LosParams p
 // next rays (a lane finishing alone ran that tail at 1.7 of 32 lanes).  Why it stopped is read off its registers:
 // no steps left (n2 == 0) = it reached the target cell, otherwise it stands in front of a covered edge.
 #ifndef LOSF_STEPS
-#define LOSF_STEPS 4     // cells per lane between two looks at the warp's idle lanes
+#define LOSF_STEPS 8     // cells per lane between two looks at the warp's idle lanes
 #endif
 #ifndef LOSF_REFILL
 #define LOSF_REFILL 12   // idle lanes that trigger a refill

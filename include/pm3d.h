@@ -421,7 +421,8 @@ int pm3d_comm_render_views(pm3d_ctx *ctx, const pm3d_view *d_views, int n_local,
                            pm3d_convergence *d_all_conv, uint64_t *d_all_checksums);
 /* pm3d_los_batch for THIS rank's contiguous range of a batch of n_global rays (d_rays holds rays [lo, hi) of
  * pm3d_shard_ray_range), written straight into d_all_out + lo, then the gather: d_all_out[n_global] holds every
- * ray's answer on every rank (enqueue only). */
+ * ray's answer on every rank (enqueue only).  The answers cross the links as bits (1/8 of the bytes) when n_global is a
+ * multiple of 32 * n_ranks and d_all_out is 16-byte aligned, as bytes otherwise: same result either way. */
 int pm3d_comm_los_batch(pm3d_ctx *ctx, const double *d_rays, int64_t n_local, int64_t n_global, uint8_t *d_all_out);
 
 /* One process driving n GPUs (what a single Go game-server process does). */
